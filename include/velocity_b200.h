@@ -1,0 +1,158 @@
+/*
+ * velocity_b200.h -- C ABI of libvelocity_b200.so (B200 / sm_100a).
+ *
+ * This is the drop-in boundary for the SFM speed-estimation hot path of ultralytics/velocity.
+ * The reference has no FFI layer of its own (pure Python calling cv2/numpy); each
+ * entry point below replaces the arithmetic behind one reference call site, cited per function.
+ * The Python package velocity_b200/ binds these with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add to utils/KLT.py etc.).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all data pointers are DEVICE pointers unless the name ends
+ *     in _host; the caller owns every buffer, the library never frees or retains them.
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*; NULL = default
+ *     stream), performs no hidden synchronisation and is re-entrant across streams.
+ *   - return value: VEL_OK or a negative VEL_ERR_*; vel_last_error() returns a thread-local
+ *     description of the last failure.  No exceptions cross this boundary.
+ *   - points are float32 (x, y) pairs, 0-based pixel centres, exactly as cv2 takes them.
+ *   - images are uint8, row-major, `pitch` bytes between rows.
+ */
+#ifndef VELOCITY_B200_H
+#define VELOCITY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VEL_OK 0
+#define VEL_ERR_INVALID (-1)     /* bad argument */
+#define VEL_ERR_CUDA (-2)        /* CUDA runtime error (message in vel_last_error) */
+#define VEL_ERR_UNSUPPORTED (-3) /* valid request outside the implemented envelope */
+
+#define VEL_MAX_LEVELS 8
+
+typedef void* vel_stream_t; /* cudaStream_t */
+
+/* Geometry of one frame's image pyramid.  Level 0 is the caller's frame itself (never copied);
+ * levels >= 1 live in a separate pyramid buffer at byte offset `offset[l]`, row pitch `pitch[l]`. */
+typedef struct vel_pyr_layout {
+    int32_t max_level; /* effective top level after OpenCV's truncation rule (levels 0..max_level) */
+    int32_t width[VEL_MAX_LEVELS];
+    int32_t height[VEL_MAX_LEVELS];
+    int32_t pitch[VEL_MAX_LEVELS]; /* pitch[0] is ignored: level-0 pitch is passed per call */
+    int64_t offset[VEL_MAX_LEVELS];
+    int64_t bytes; /* pyramid buffer bytes per frame (levels >= 1), 256-byte aligned */
+} vel_pyr_layout;
+
+/* cv2.calcOpticalFlowPyrLK parameters as the reference passes them (utils/KLT.py:106-107). */
+typedef struct vel_lk_params {
+    int32_t win_w, win_h;
+    int32_t max_level;       /* requested; the layout carries the effective value */
+    int32_t max_count;       /* TERM_CRITERIA_COUNT, clamped to [0,100] like OpenCV */
+    double eps;              /* TERM_CRITERIA_EPS (squared internally), clamped to [0,10] */
+    float min_eig_threshold; /* 1e-4 = OpenCV default, which is what the reference uses */
+    float fb_threshold;      /* >= 0: fused backward pass + forward-backward gate (utils/KLT.py:47-50); < 0: forward only */
+} vel_lk_params;
+
+int vel_version(void);
+const char* vel_last_error(void);
+
+/* Pyramid geometry for a w x h frame tracked with a win_w x win_h window up to max_level
+ * (OpenCV buildOpticalFlowPyramid rule: stop before the first level with width <= win_w or
+ * height <= win_h).  Host-only helper, no CUDA call. */
+int vel_pyr_layout_make(int32_t width, int32_t height, int32_t win_w, int32_t win_h, int32_t max_level,
+                        vel_pyr_layout* out);
+
+/* K1.  cv2.pyrDown chain (5-tap [1 4 6 4 1]/16 separable, BORDER_REFLECT_101, (s+128)>>8) for a
+ * batch of frames: the pyramid that cv2.calcOpticalFlowPyrLK builds internally (utils/KLT.py:45,48).
+ * frames + i*frame_stride is frame i (level 0, row pitch `pitch`); levels 1.. are written to
+ * pyr + i*pyr_stride + layout->offset[l]. */
+int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t pitch, int32_t nframes,
+                   const vel_pyr_layout* layout, uint8_t* pyr, int64_t pyr_stride, vel_stream_t stream);
+
+/* cv2.resize(im, (0,0), fx=1/4, fy=1/4, INTER_NEAREST) == im[::4, ::4] (utils/KLT.py:111,113). */
+int vel_decimate4_u8(const uint8_t* src, int32_t width, int32_t height, int32_t pitch, uint8_t* dst, int32_t dst_width,
+                     int32_t dst_height, int32_t dst_pitch, vel_stream_t stream);
+
+/* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
+ * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
+ * forward result fused in the same kernel with
+ *     status = st_fwd & st_bwd & (||p1 - p1'||_2 < fb_threshold).
+ * Pair k tracks prev frame k -> next frame k.  prev_pts + k*pts_stride floats holds npts (x,y)
+ * pairs (pts_stride 0 = the same points for every pair).  Outputs are [npairs][npts]:
+ * next_pts (x,y) float32, status uint8 (0/1), err float32 (cv2's L1 patch error of the forward
+ * pass; 0 where the forward status is 0).  back_pts may be NULL. */
+int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, int32_t prev_pitch, const uint8_t* prev_pyr,
+                 int64_t prev_pyr_stride, const uint8_t* next_frames, int64_t next_frame_stride, int32_t next_pitch,
+                 const uint8_t* next_pyr, int64_t next_pyr_stride, const vel_pyr_layout* layout, int32_t npairs,
+                 const float* prev_pts, int64_t pts_stride, int32_t npts, const vel_lk_params* params, float* next_pts,
+                 uint8_t* status, float* err, float* back_pts, vel_stream_t stream);
+
+/* K3.  utils/KLT.py:70-73: float32 affine map of the ROI grid x in [x0,x0+dw), y in [y0,y0+dh)
+ * through the 3x2 row-vector affine T (T[0..5] = T00,T01,T10,T11,T20,T21, HOST pointer), then
+ * cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) in OpenCV's fixed point (1/32 px, 15-bit weights). */
+int vel_remap_affine_u8(const uint8_t* src, int32_t width, int32_t height, int32_t pitch, const float* T_host, int32_t x0,
+                        int32_t y0, int32_t dst_width, int32_t dst_height, uint8_t* dst, int32_t dst_pitch,
+                        vel_stream_t stream);
+
+/* K5.  fcnNLS_t (utils/NLS.py:102-129) for a batch of independent frames: 3-dof translation
+ * Levenberg-Marquardt with the reference's forward-difference Jacobian (dx = 1e-6), fixed damping
+ * JtJ + I, step schedule min(((i+1)*0.2)^2, 1), <= 30 iterations, stop at rms(delta) < 1e-8.
+ * K is the 3x3 row-vector intrinsic matrix (float64, row-major, DEVICE).  Problem b uses
+ * n[b] points at offset first[b] of p (float64 [.,2]) and pw (float64 [.,3]); x0/x are [nprob][3].
+ * iters[b] receives the number of iterations run, or -(30) if the iteration cap was hit (the
+ * reference prints a WARNING in that case).  All float64. */
+int vel_nls_t(const double* K, const double* p, const double* pw, const int32_t* first, const int32_t* n, int32_t nprob,
+              const double* x0, double* x, int32_t* iters, vel_stream_t stream);
+
+/* fcnNLS_Rt (utils/NLS.py:133-183): 6-dof (roll,pitch,yaw,t) variant; x0/x are [nprob][6]. */
+int vel_nls_rt(const double* K, const double* p, const double* pw, const int32_t* first, const int32_t* n, int32_t nprob,
+               const double* x0, double* x, int32_t* iters, vel_stream_t stream);
+
+/* K6.  fcn2vintercept (utils/MSV.py:98-142): mean of the closest-approach points over all
+ * C(nf,2) ray pairs.  A [nf][3] ray origins, U [3][nf][nv] unit directions, C0 [nv][3]; float64. */
+int vel_triangulate_2v(const double* A, const double* U, int32_t nf, int32_t nv, double* C0, vel_stream_t stream);
+
+/* fcnNvintercept (utils/MSV.py:146-175): least-squares intersection of nf rays per point. */
+int vel_triangulate_nv(const double* A, const double* U, int32_t nf, int32_t nv, double* C0, vel_stream_t stream);
+
+/* K7.  One Gauss-Newton linearisation of fcnNLS_batch (utils/NLS.py:186-250) in block form.
+ * Parameters x = [points nt*3 | camera positions nc*3 | camera rpy nc*3] (camera 0 is fixed at
+ * identity and not a parameter); z = observations [2][(nc+1)][nt] (all x then all y, track
+ * fastest, utils/NLS.py:198-199).  Writes, for J = forward-difference Jacobian (1e-6):
+ *   V  [nt][6]      upper triangle of the 3x3 point blocks of JtJ
+ *   U  [nc][21]     upper triangle of the 6x6 camera blocks of JtJ (pos, rpy)
+ *   W  [nc][nt][18] camera-point cross blocks (6x3, row-major)   (may be NULL)
+ *   g  [nt*3+nc*6]  Jt (z - zhat), in parameter order
+ *   cost[1]         sum of squared residuals
+ * cam_first/cam_count select the slice of cameras 1..nc this call (this rank) owns: V and the
+ * point part of g then hold PARTIAL sums to be all-reduced across ranks. */
+int vel_ba_accumulate(const double* K, const double* x, const double* z, int32_t nt, int32_t nc, int32_t cam_first,
+                      int32_t cam_count, double* V, double* U, double* W, double* g, double* cost, vel_stream_t stream);
+
+/* K8.  Solve (JtJ + I) delta = g by Schur complement on the point blocks and apply
+ * x += 0.9 * delta (utils/NLS.py:234-235).  work must hold vel_ba_solve_workspace(nt, nc) bytes.
+ * rms_delta[1] receives rms(delta) (the reference's convergence measure, :238). */
+size_t vel_ba_solve_workspace(int32_t nt, int32_t nc);
+int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
+                 double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
+
+/* K4.  cv2.BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) for 256-bit descriptors (the ORB variant
+ * of the reference's descriptor fallback, utils/KLT.py:16-26; BASELINE config 4): the two nearest
+ * train rows per query, ascending distance, ties to the lower train index.  q [nq][32], t [nt][32]
+ * uint8; idx/dist [nq][2] int32 (-1 where nt < 2). */
+int vel_match_knn2_hamming256(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
+                              vel_stream_t stream);
+
+/* cv2.BFMatcher().knnMatch(q, t, k=2), NORM_L2 on float32 descriptors (what utils/KLT.py:16,25
+ * literally runs on SURF descriptors).  dist = sqrt(sum (a-b)^2) in float32. */
+int vel_match_knn2_l2(const float* q, int32_t nq, const float* t, int32_t nt, int32_t dim, int32_t* idx, float* dist,
+                      vel_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VELOCITY_B200_H */

@@ -1,0 +1,124 @@
+"""Parity of the CUDA tracker path (K1 pyramid, K2 LK + forward-backward, K3 remap, KLTregional,
+KLTmain) against the CPU oracle (bit-exact) and the reference-generated golden vectors."""
+import numpy as np
+import pytest
+
+from util import LK_CASES, LK_ERR_TOL, LK_POINT_TOL_PX, PRIM_CASES, fbt_of, golden, lk_images, lk_kwargs
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from velocity_b200 import _lib
+
+    _lib.lib()
+    return torch
+
+
+@pytest.mark.parametrize("name", PRIM_CASES)
+def test_pyramid_remap_decimate_bit_exact(cuda, name):
+    from oracle import cv_oracle as O
+    from velocity_b200 import KLT
+    from velocity_b200.lk import FrameBatch
+
+    g = golden(name)
+    im = g["im"]
+    d = cuda.from_numpy(im).cuda()
+    fb = FrameBatch(d, (3, 3), 3).build()
+    lvl = im
+    for l in range(1, fb.layout.max_level + 1):
+        lvl = O.pyrDown(lvl)
+        assert np.array_equal(fb.level(0, l).cpu().numpy(), lvl), "pyramid level %d" % l
+    assert np.array_equal(fb.level(0, 1).cpu().numpy(), g["pyrdown"])
+    assert np.array_equal(KLT._decimate4_device(d).cpu().numpy(), g["quarter"])
+    x0, x1, y0, y1 = (int(v) for v in g["roi"])
+    out = KLT._remap_affine_device(d, g["T"], x0, x1, y0, y1).cpu().numpy()
+    assert np.array_equal(out, g["remap"])
+    assert np.array_equal(out, O.remap_affine(im, g["T"], x0, x1, y0, y1))
+
+
+def test_pyramid_batch_1080p_matches_oracle(cuda):
+    from oracle import cv_oracle as O
+    from velocity_b200 import synth
+    from velocity_b200.lk import FrameBatch
+
+    frames = np.stack([synth.texture(1080, 1920, s) for s in (1, 2, 3)])
+    fb = FrameBatch(cuda.from_numpy(frames).cuda(), (15, 15), 4).build()
+    assert fb.layout.max_level == 4
+    for i in range(3):
+        lvl = frames[i]
+        for l in range(1, 5):
+            lvl = O.pyrDown(lvl)
+            assert np.array_equal(fb.level(i, l).cpu().numpy(), lvl), (i, l)
+
+
+@pytest.mark.parametrize("name", LK_CASES)
+def test_lk_matches_oracle_bit_exact_and_reference_golden(cuda, name):
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT
+
+    g = golden(name)
+    im0, im1 = lk_images(g)
+    lk, fbt = lk_kwargs(g), fbt_of(g)
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, g["p"], None, fbt=fbt, **lk)
+    assert p2.dtype == np.float32 and p2.shape == g["p2"].shape
+    assert v.dtype == bool and v.shape == g["v"].shape
+    assert err.dtype == np.float32 and err.shape == g["err"].shape
+    # (1) CUDA == oracle, bit for bit (same integer accumulation, same float32 op order)
+    o2, ov, oerr = KO.lk_forward_backward(im0, im1, g["p"], fbt=fbt, **lk)
+    assert np.array_equal(v, ov)
+    assert np.array_equal(p2, o2)
+    fwd_ok = oerr.ravel() != 0
+    assert np.array_equal(err[fwd_ok], oerr[fwd_ok])
+    # (2) CUDA vs the reference's own output (cv2 4.13): masks exact, points within tolerance
+    assert np.array_equal(v, g["v"])
+    assert np.abs(p2 - g["p2"])[g["v"]].max() <= LK_POINT_TOL_PX
+    assert np.abs(err - g["err"])[g["v"]].max() <= LK_ERR_TOL
+
+
+@pytest.mark.parametrize("name,translate", [("regional_translate", True), ("regional_affine", False)])
+def test_kltregional(cuda, name, translate):
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT
+
+    g = golden(name)
+    lk = lk_kwargs(g)
+    p, v = KLT.KLTregional(g["im0"], g["im1"], g["p0"], g["T"], lk, fbt=float(g["fbt"]), translateFlag=translate)
+    po, vo = KO.klt_regional(g["im0"], g["im1"], g["p0"], g["T"], lk, fbt=float(g["fbt"]), translate=translate)
+    assert np.array_equal(v, vo) and np.array_equal(p, po)
+    assert p.dtype == g["p"].dtype and np.array_equal(v, g["v"])
+    assert np.abs(p - g["p"])[g["v"]].max() <= LK_POINT_TOL_PX
+
+
+def test_kltmain(cuda):
+    from velocity_b200 import KLT
+
+    g = golden("kltmain_pair")
+    p, v, im_small = KLT.KLTmain(g["im1"], g["im0"], None, g["p0"])
+    assert np.array_equal(v, g["v"])
+    assert p.shape == g["p"].shape and np.abs(p - g["p"]).max() <= LK_POINT_TOL_PX
+    assert np.array_equal(im_small.cpu().numpy(), g["im_small"])
+
+
+def test_lk_full_size_properties(cuda):
+    """BASELINE config 2 size (1080p, 4096 tracks, 15x15, 3 levels, FB 1.0): identity pair returns
+    the input points with zero error; a pure integer shift is recovered; CUDA == oracle on a sample."""
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT, synth
+
+    im0 = synth.texture(1080, 1920, 1234)
+    pts = synth.harris_tracks(im0, 4096)
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im0, pts, None, fbt=1.0, **lk)
+    assert v.all() and np.abs(p2 - pts).max() <= 1e-3 and err.max() == 0
+    im1 = np.roll(im0, (2, 3), (0, 1))
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, pts, None, fbt=1.0, **lk)
+    assert v.mean() > 0.99
+    assert np.abs(p2[v] - pts[v] - np.float32([3, 2])).max() < 0.05
+    sel = np.arange(0, 4096, 16)
+    o2, ov, _ = KO.lk_forward_backward(im0, im1, pts[sel], fbt=1.0, **lk)
+    assert np.array_equal(v[sel], ov) and np.array_equal(p2[sel], o2)

@@ -1,0 +1,175 @@
+"""Drop-in for the reference's utils/KLT.py: same function names, arguments, return types.
+
+    cv2calcOpticalFlowPyrLK  utils/KLT.py:37-51
+    KLTregional              utils/KLT.py:55-95
+    KLTmain                  utils/KLT.py:99-134
+    estimateAffine2D_SURF    utils/KLT.py:10-33
+
+All pixel/point arithmetic runs in the sm_100a kernels of libvelocity_b200.so (K1 pyramid, K2
+Lucas-Kanade with fused forward-backward gate, K3 affine remap, K4 descriptor matcher).  Images
+may be numpy arrays (uploaded per call) or CUDA uint8 tensors (used in place, ROI slices are free).
+Outputs are numpy arrays with the reference's shapes and dtypes.  The RANSAC affine fit stays on
+the host in cv2.estimateAffine2D exactly as in the reference (fixed-seed RNG => bit-identical
+inlier masks).  There is no CPU fallback for the kernels.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .common import addcol1
+from .device import image_view, ptr, stream_ptr
+from .images import boundingRect
+from .lk import FrameBatch, lk_params, track_pairs
+
+TERM_CRITERIA_COUNT, TERM_CRITERIA_EPS = 1, 2
+
+LK_COARSE = dict(winSize=(15, 15), maxLevel=4, criteria=(TERM_CRITERIA_EPS | TERM_CRITERIA_COUNT, 10, 0.1))
+LK_FINE = dict(winSize=(51, 51), maxLevel=0, criteria=(TERM_CRITERIA_EPS | TERM_CRITERIA_COUNT, 30, 0.001))
+
+
+def _as_cuda_image(im):
+    t, _, w, h, pitch = image_view(im)
+    return t  # [h, w] uint8 CUDA tensor, last stride 1
+
+
+def lk_device(im1, im2, p1, fbt=None, **lk_param):
+    """Device-resident core of cv2calcOpticalFlowPyrLK: CUDA tensors in, CUDA tensors out
+    (next [N,2] f32, status [N] u8 -- already forward-backward gated when fbt is given --, err [N] f32)."""
+    a, b = _as_cuda_image(im1), _as_cuda_image(im2)
+    if a.shape != b.shape:
+        raise ValueError("image sizes differ: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
+    params = lk_params(fbt=fbt, **lk_param)
+    win = (params.win_w, params.win_h)
+    fa = FrameBatch(a, win, params.max_level).build()
+    fb = FrameBatch(b, win, params.max_level).build()
+    pts = p1 if isinstance(p1, torch.Tensor) and p1.is_cuda else torch.from_numpy(
+        np.ascontiguousarray(np.asarray(p1, np.float32).reshape(-1, 2))).cuda()
+    out, status, err, _ = track_pairs(fa, fb, pts.to(torch.float32), params)
+    return out[0], status[0], err[0]
+
+
+def cv2calcOpticalFlowPyrLK(im1, im2, p1, p2hat=None, fbt=None, **lk_param):
+    """Pyramidal LK forward (and, with fbt, backward + forward-backward gate).  Returns
+    (p2 float32 [N,2], v bool [N], err float32 [N,1]) like the reference."""
+    out, status, err = lk_device(im1, im2, p1, fbt=fbt, **lk_param)
+    packed = torch.cat([out, err.unsqueeze(1), status.to(torch.float32).unsqueeze(1)], 1).cpu().numpy()  # one D2H copy
+    return np.ascontiguousarray(packed[:, 0:2]), packed[:, 3] != 0, np.ascontiguousarray(packed[:, 2:3])
+
+
+def _remap_affine_device(im, T32, x0, x1, y0, y1):
+    src, p, w, h, pitch = image_view(im)
+    out = torch.empty((y1 - y0, x1 - x0), dtype=torch.uint8, device=src.device)
+    Tc = (C.c_float * 6)(*[float(v) for v in np.asarray(T32, np.float32).reshape(6)])
+    _lib.check(_lib.lib().vel_remap_affine_u8(C.c_void_p(p), w, h, pitch, Tc, x0, y0, x1 - x0, y1 - y0, ptr(out),
+                                              out.stride(0), stream_ptr()), "vel_remap_affine_u8")
+    return out
+
+
+def KLTregional(im0, im, p0, T, lk_param, fbt=1.0, translateFlag=False):
+    """ROI tracker: warp the current frame into the previous frame's coordinates (integer shift or
+    affine remap), LK forward+backward on the ROI, map the result back through T."""
+    T = np.asarray(T).astype(np.float32)
+    p0 = np.asarray(p0)
+    d0, dn = _as_cuda_image(im0), _as_cuda_image(im)
+    x0, x1, y0, y1 = boundingRect(p0, tuple(dn.shape), border=(50, 50))
+    roi_prev = d0[y0:y1, x0:x1]
+    xy0 = np.float32([x0, y0])
+    p0_roi = p0 - xy0
+    if translateFlag:
+        dx, dy = int(T[2, 0]), int(T[2, 1])
+        ya, yb, xa, xb = y0 + dy, y1 + dy, x0 + dx, x1 + dx
+        if ya < 0 or xa < 0 or yb > dn.shape[0] or xb > dn.shape[1]:
+            raise ValueError("KLTregional: shifted ROI leaves the frame (cv2 asserts on mismatched pyramid sizes here)")
+        roi_next = dn[ya:yb, xa:xb]
+    else:
+        roi_next = _remap_affine_device(dn, T, x0, x1, y0, y1)
+    pa, v, _ = cv2calcOpticalFlowPyrLK(roi_prev, roi_next, p0_roi, None, fbt=fbt, **lk_param)
+    if translateFlag:
+        p = pa + (xy0 + [dx, dy]).astype(np.float32)
+    else:
+        p = addcol1(pa + xy0) @ T
+    return p, v
+
+
+def _decimate4_device(im):
+    src, p, w, h, pitch = image_view(im)
+    dw, dh = int(np.rint(w * 0.25)), int(np.rint(h * 0.25))
+    out = torch.empty((dh, dw), dtype=torch.uint8, device=src.device)
+    _lib.check(_lib.lib().vel_decimate4_u8(C.c_void_p(p), w, h, pitch, ptr(out), dw, dh, out.stride(0), stream_ptr()),
+               "vel_decimate4_u8")
+    return out
+
+
+def KLTmain(im, im0, im0_small, p0):
+    """Three-stage tracker: quarter-scale LK -> RANSAC -> translated-ROI LK (FB 1.0) -> RANSAC ->
+    affine-ROI fine LK (FB 0.3).  Returns (p[v] float32, v bool [N], im_small) like the reference;
+    im_small is returned in the form it was produced (CUDA tensor), pass it back as im0_small."""
+    import cv2  # host RANSAC only
+
+    p0 = np.asarray(p0)
+    d_im, d_im0 = _as_cuda_image(im), _as_cuda_image(im0)
+    scale = 1 / 4
+    im_small = _decimate4_device(d_im)
+    if im0_small is None:
+        im0_small = _decimate4_device(d_im0)
+    p, v, _ = cv2calcOpticalFlowPyrLK(im0_small, im_small, p0 * scale, None, **LK_COARSE)
+    p /= scale
+    T23, inliers = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+    v[v] = inliers.ravel().astype(bool)
+
+    translation = p[v] - p0[v]
+    T = np.eye(3, 2)
+    T[2] = translation.mean(0)
+    p, v = KLTregional(d_im0, d_im, p0, T, LK_COARSE, fbt=1, translateFlag=True)
+
+    if v.sum() > 10:
+        T23, inliers = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+    else:
+        print("KLT coarse-affine failure, running SURF matches full scale.")
+        T23, inliers = estimateAffine2D_SURF(d_im0, d_im, p0, scale=1)
+
+    p, v = KLTregional(d_im0, d_im, p0, T23.T, LK_FINE, fbt=0.3)
+    return p[v], v, im_small
+
+
+def knnMatch2(des1, des2):
+    """cv2.BFMatcher(norm).knnMatch(des1, des2, k=2) on the GPU: uint8 [.,32] -> Hamming,
+    float32 [.,D] -> L2.  Returns (idx int32 [nq,2], dist [nq,2])."""
+    from .match import knn2_hamming256, knn2_l2
+
+    des1, des2 = np.asarray(des1), np.asarray(des2)
+    if des1.dtype == np.uint8:
+        return knn2_hamming256(des1, des2)
+    return knn2_l2(des1.astype(np.float32), des2.astype(np.float32))
+
+
+def estimateAffine2D_SURF(im1, im2, p1, scale=1.0):
+    """Descriptor-matching fallback (utils/KLT.py:10-33).  The reference asks for SURF, which is a
+    non-free module absent from opencv-python; this build extracts ORB descriptors on the host
+    (BASELINE.json config 4 names ORB) and runs the all-pairs 2-NN match on the GPU (K4)."""
+    import cv2
+
+    def host(im):
+        return im.cpu().numpy() if isinstance(im, torch.Tensor) else np.asarray(im)
+
+    im1 = cv2.resize(host(im1), (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_NEAREST)
+    im2 = cv2.resize(host(im2), (0, 0), fx=scale, fy=scale, interpolation=cv2.INTER_NEAREST)
+    orb = cv2.ORB_create(nfeatures=8192)
+    kp2, des2 = orb.detectAndCompute(im2, mask=None)
+    a, ngood, good = 0, 0, []
+    while ngood < 10:
+        border = int(a * scale)
+        x0, x1, y0, y1 = boundingRect(np.asarray(p1) * scale, im1.shape, border=(border, border))
+        kp1, des1 = orb.detectAndCompute(np.ascontiguousarray(im1[y0:y1, x0:x1]), mask=None)
+        if des1 is not None and len(des1) >= 1 and des2 is not None and len(des2) >= 2:
+            idx, dist = knnMatch2(des1, des2)
+            good = [(q, int(idx[q, 0])) for q in range(len(des1)) if dist[q, 0] < 0.6 * dist[q, 1]]
+        ngood = len(good)
+        a += 10
+        if x0 <= 1 and y0 <= 1 and x1 >= im1.shape[1] and y1 >= im1.shape[0] and ngood < 10:
+            raise RuntimeError("estimateAffine2D_SURF: fewer than 10 ratio-test matches on the full frame")
+    m1 = np.float32([kp1[q].pt for q, _ in good]) + np.float32([x0, y0])
+    m2 = np.float32([kp2[t].pt for _, t in good])
+    return cv2.estimateAffine2D(m1 / scale, m2 / scale, method=cv2.RANSAC)

@@ -1,0 +1,60 @@
+// Shared device/host helpers for libvelocity_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/velocity_b200.h"
+
+#define VEL_API extern "C" __attribute__((visibility("default")))
+
+// thread-local last-error buffer (defined in api.cu)
+void vel_set_error(const char* fmt, ...);
+
+#define VEL_CHECK_ARG(cond, ...)          \
+    do {                                  \
+        if (!(cond)) {                    \
+            vel_set_error(__VA_ARGS__);   \
+            return VEL_ERR_INVALID;       \
+        }                                 \
+    } while (0)
+
+#define VEL_CUDA(call)                                                                      \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            vel_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+            return VEL_ERR_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define VEL_LAUNCH_CHECK(name)                                                         \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            vel_set_error("launch of %s failed: %s", name, cudaGetErrorString(e__));   \
+            return VEL_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+static constexpr int kNumSMs = 148;  // B200
+
+// BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba).  Valid for any overshoot when n > 1.
+__host__ __device__ __forceinline__ int reflect101(int i, int n)
+{
+    if (n == 1) return 0;
+    while (i < 0 || i >= n) {
+        i = i < 0 ? -i : 2 * n - 2 - i;
+    }
+    return i;
+}
+
+// single-overshoot version for hot loops (callers guarantee |overshoot| < n)
+__device__ __forceinline__ int reflect101_1(int i, int n)
+{
+    i = i < 0 ? -i : i;
+    return i >= n ? 2 * n - 2 - i : i;
+}
+
+__device__ __forceinline__ unsigned ldg_u8(const uint8_t* p) { return (unsigned)__ldg(p); }

@@ -1,0 +1,409 @@
+// K2: pyramidal Lucas-Kanade tracker with fused forward-backward check.
+//
+// Replaces cv2.calcOpticalFlowPyrLK as the reference drives it through cv2calcOpticalFlowPyrLK
+// (utils/KLT.py:37-51): forward pass, optional backward pass from the forward result, and
+// v = st_fwd & st_bwd & (||p1 - p1'||_2 < fbt).  Arithmetic follows OpenCV 4.13's LKTrackerInvoker
+// (restated on the CPU in oracle/velocity_oracle.c, which is pinned against cv2 by tests/golden):
+//   * bilinear weights in 14-bit fixed point (round-half-even of float32 products),
+//   * template I with 5 fractional bits, Scharr derivatives (REFLECT_101 inside the image,
+//     constant 0 in the window padding) interpolated with the same weights,
+//   * G = sum [Ix^2, IxIy; IxIy, Iy^2] and b = sum diff*[Ix, Iy] accumulated EXACTLY in int64 and
+//     converted to float32 once (cv2 accumulates float32 SIMD lanes; <= 2e-3 px apart, see tests),
+//   * float32 2x2 solve, eps^2 / oscillation stopping rules, minEig and bounds status rules.
+// All float32 steps use explicit round-to-nearest intrinsics so no FMA contraction can make the
+// device differ from the oracle: device == oracle bit for bit.
+//
+// Work decomposition: one GROUP of NT threads owns one point for all pyramid levels and both
+// passes.  NT = 32 (a warp, 8 points per CTA) for windows up to 1024 px^2, NT = 128 (a CTA) above.
+// The template (I, Ix, Iy as int16) lives in shared memory; J is gathered from global memory
+// through L1/L2 (the whole pyramid of a 1080p frame is 2.7 MB, i.e. L2 resident).
+#include "common.cuh"
+
+namespace {
+
+struct LkLevels {
+    int max_level;
+    int w[VEL_MAX_LEVELS], h[VEL_MAX_LEVELS], pitch[VEL_MAX_LEVELS];
+    long long off[VEL_MAX_LEVELS];
+};
+
+struct LkArgs {
+    const uint8_t* prev0; long long prev_stride; int prev_pitch;
+    const uint8_t* prev_pyr; long long prev_pyr_stride;
+    const uint8_t* next0; long long next_stride; int next_pitch;
+    const uint8_t* next_pyr; long long next_pyr_stride;
+    LkLevels lv;
+    const float* pts; long long pts_stride; int npts;
+    float* out; uint8_t* status; float* err; float* back;
+    int win_w, win_h, max_count;
+    float eps2, min_eig, fbt;
+};
+
+struct Img {
+    const uint8_t* p;
+    int w, h, pitch;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+__device__ __forceinline__ int px_reflect(const Img& im, int x, int y)
+{
+    return (int)ldg_u8(im.p + (long long)reflect101_1(y, im.h) * im.pitch + reflect101_1(x, im.w));
+}
+
+// unnormalised Scharr pair at an in-image pixel, REFLECT_101 at the edge (OpenCV calcSharrDeriv)
+__device__ __forceinline__ void scharr_at(const Img& im, int x, int y, int& gx, int& gy)
+{
+    const int xm = x > 0 ? x - 1 : (im.w > 1 ? 1 : 0);
+    const int xp = x < im.w - 1 ? x + 1 : (im.w > 1 ? im.w - 2 : 0);
+    const int ym = y > 0 ? y - 1 : (im.h > 1 ? 1 : 0);
+    const int yp = y < im.h - 1 ? y + 1 : (im.h > 1 ? im.h - 2 : 0);
+    const uint8_t* r0 = im.p + (long long)ym * im.pitch;
+    const uint8_t* r1 = im.p + (long long)y * im.pitch;
+    const uint8_t* r2 = im.p + (long long)yp * im.pitch;
+    const int a0 = ldg_u8(r0 + xm), a1 = ldg_u8(r0 + x), a2 = ldg_u8(r0 + xp);
+    const int b0 = ldg_u8(r1 + xm), b2 = ldg_u8(r1 + xp);
+    const int c0 = ldg_u8(r2 + xm), c1 = ldg_u8(r2 + x), c2 = ldg_u8(r2 + xp);
+    gx = 3 * (a2 + c2) + 10 * b2 - 3 * (a0 + c0) - 10 * b0;
+    gy = 3 * ((c0 - a0) + (c2 - a2)) + 10 * (c1 - a1);
+}
+
+struct Weights {
+    int w00, w01, w10, w11;
+};
+
+__device__ __forceinline__ Weights bilin_weights(float a, float b)
+{
+    const float one_a = fsub(1.f, a), one_b = fsub(1.f, b);
+    Weights w;
+    w.w00 = __float2int_rn(fmul(fmul(one_a, one_b), 16384.f));
+    w.w01 = __float2int_rn(fmul(fmul(a, one_b), 16384.f));
+    w.w10 = __float2int_rn(fmul(fmul(one_a, b), 16384.f));
+    w.w11 = 16384 - w.w00 - w.w01 - w.w10;
+    return w;
+}
+
+// ---- group-wide exact reductions --------------------------------------------------------------
+template <int NT>
+__device__ __forceinline__ void group_sync()
+{
+    if (NT == 32) __syncwarp();
+    else __syncthreads();
+}
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Sums K int64 values over the group; every thread receives the totals.  `red` is a per-group
+// shared scratch of 2 * (NT/32) * K int64 (double-buffered by `parity` so one barrier suffices).
+template <int NT, int K>
+__device__ __forceinline__ void group_sum(long long (&v)[K], long long* red, int& parity, int tid)
+{
+#pragma unroll
+    for (int k = 0; k < K; ++k) v[k] = warp_sum_ll(v[k]);
+    if (NT > 32) {
+        constexpr int NW = NT / 32;
+        long long* buf = red + parity * (NW * K);
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < K; ++k) buf[(tid >> 5) * K + k] = v[k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            long long s = 0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) s += buf[w * K + k];
+            v[k] = s;
+        }
+        parity ^= 1;
+    }
+}
+
+// ---- one pass (all levels) for one point --------------------------------------------------------
+// I: template pyramid, J: search pyramid.  Returns status (1/0); writes next position and err.
+template <int NT>
+__device__ void track_point(const LkArgs& A, const uint8_t* I0, int I0_pitch, const uint8_t* Ipyr, const uint8_t* J0,
+                            int J0_pitch, const uint8_t* Jpyr, float px, float py, float& out_x, float& out_y, int& out_status,
+                            float& out_err, short2* sD, short* sI, short2* sG, long long* red, int& parity, int tid)
+{
+    const int ww = A.win_w, wh = A.win_h, npx = ww * wh;
+    const int tw = ww + 1, th = wh + 1;
+    const float half_x = fmul((float)(ww - 1), 0.5f), half_y = fmul((float)(wh - 1), 0.5f);
+    const float FLT_SCALE = 1.f / 1048576.f;
+
+    int status = 1;
+    float err = 0.f;
+    float next_x = 0.f, next_y = 0.f;
+
+    for (int level = A.lv.max_level; level >= 0; --level) {
+        Img I, J;
+        I.w = J.w = A.lv.w[level];
+        I.h = J.h = A.lv.h[level];
+        if (level == 0) { I.p = I0; I.pitch = I0_pitch; J.p = J0; J.pitch = J0_pitch; }
+        else { I.p = Ipyr + A.lv.off[level]; J.p = Jpyr + A.lv.off[level]; I.pitch = J.pitch = A.lv.pitch[level]; }
+
+        const float scale = 1.f / (float)(1 << level);
+        float prev_x = fmul(px, scale), prev_y = fmul(py, scale);
+        float nx, ny;
+        if (level == A.lv.max_level) { nx = prev_x; ny = prev_y; }
+        else { nx = fmul(next_x, 2.f); ny = fmul(next_y, 2.f); }
+        next_x = nx; next_y = ny;
+
+        prev_x = fsub(prev_x, half_x); prev_y = fsub(prev_y, half_y);
+        const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
+        if (ipx < -ww || ipx >= I.w || ipy < -wh || ipy >= I.h) {
+            if (level == 0) { status = 0; err = 0.f; }
+            continue;
+        }
+        Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
+
+        group_sync<NT>();  // previous level's readers of sD/sI/sG are done
+        // (1) Scharr derivative tile over the (ww+1) x (wh+1) bilinear footprint
+        for (int t = tid; t < tw * th; t += NT) {
+            const int ty = t / tw, tx = t - ty * tw;
+            const int X = ipx + tx, Y = ipy + ty;
+            int gx = 0, gy = 0;
+            if (X >= 0 && Y >= 0 && X < I.w && Y < I.h) scharr_at(I, X, Y, gx, gy);
+            sD[t] = make_short2((short)gx, (short)gy);
+        }
+        group_sync<NT>();
+        // (2) template patch + gradient matrix
+        long long acc[3] = {0, 0, 0};
+        {
+            const bool inside = ipx >= 0 && ipy >= 0 && ipx + ww < I.w && ipy + wh < I.h;
+            for (int i = tid; i < npx; i += NT) {
+                const int y = i / ww, x = i - y * ww;
+                int i00, i01, i10, i11;
+                if (inside) {
+                    const uint8_t* r = I.p + (long long)(ipy + y) * I.pitch + ipx + x;
+                    i00 = ldg_u8(r); i01 = ldg_u8(r + 1); i10 = ldg_u8(r + I.pitch); i11 = ldg_u8(r + I.pitch + 1);
+                } else {
+                    i00 = px_reflect(I, ipx + x, ipy + y); i01 = px_reflect(I, ipx + x + 1, ipy + y);
+                    i10 = px_reflect(I, ipx + x, ipy + y + 1); i11 = px_reflect(I, ipx + x + 1, ipy + y + 1);
+                }
+                const int ival = (i00 * w.w00 + i01 * w.w01 + i10 * w.w10 + i11 * w.w11 + (1 << 8)) >> 9;
+                const short2 d00 = sD[y * tw + x], d01 = sD[y * tw + x + 1], d10 = sD[(y + 1) * tw + x],
+                             d11 = sD[(y + 1) * tw + x + 1];
+                const int ix = (d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11 + (1 << 13)) >> 14;
+                const int iy = (d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11 + (1 << 13)) >> 14;
+                sI[i] = (short)ival;
+                sG[i] = make_short2((short)ix, (short)iy);
+                acc[0] += (long long)(ix * ix);
+                acc[1] += (long long)(ix * iy);
+                acc[2] += (long long)(iy * iy);
+            }
+        }
+        if (NT == 32) __syncwarp();  // template visible to the whole warp (NT > 32: barrier inside group_sum)
+        group_sum<NT, 3>(acc, red, parity, tid);
+        const float A11 = fmul(__ll2float_rn(acc[0]), FLT_SCALE), A12 = fmul(__ll2float_rn(acc[1]), FLT_SCALE),
+                    A22 = fmul(__ll2float_rn(acc[2]), FLT_SCALE);
+        float D = fsub(fmul(A11, A22), fmul(A12, A12));
+        const float dA = fsub(A11, A22);
+        const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
+        const float min_eig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(disc)), (float)(2 * ww * wh));
+        if (min_eig < A.min_eig || D < 1.1920928955078125e-07f) {
+            if (level == 0) status = 0;
+            continue;
+        }
+        D = __fdiv_rn(1.f, D);
+
+        nx = fsub(nx, half_x); ny = fsub(ny, half_y);
+        float pdx = 0.f, pdy = 0.f;
+        for (int j = 0; j < A.max_count; ++j) {
+            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
+            if (inx < -ww || inx >= J.w || iny < -wh || iny >= J.h) {
+                if (level == 0) status = 0;
+                break;
+            }
+            w = bilin_weights(fsub(nx, (float)inx), fsub(ny, (float)iny));
+            long long b[2] = {0, 0};
+            const bool inside = inx >= 0 && iny >= 0 && inx + ww < J.w && iny + wh < J.h;
+            if (inside) {
+                const uint8_t* base = J.p + (long long)iny * J.pitch + inx;
+                for (int i = tid; i < npx; i += NT) {
+                    const int y = i / ww, x = i - y * ww;
+                    const uint8_t* r = base + (long long)y * J.pitch + x;
+                    const int j00 = ldg_u8(r), j01 = ldg_u8(r + 1), j10 = ldg_u8(r + J.pitch), j11 = ldg_u8(r + J.pitch + 1);
+                    const int diff = ((j00 * w.w00 + j01 * w.w01 + j10 * w.w10 + j11 * w.w11 + (1 << 8)) >> 9) - (int)sI[i];
+                    const short2 g = sG[i];
+                    b[0] += (long long)(diff * (int)g.x);
+                    b[1] += (long long)(diff * (int)g.y);
+                }
+            } else {
+                for (int i = tid; i < npx; i += NT) {
+                    const int y = i / ww, x = i - y * ww;
+                    const int j00 = px_reflect(J, inx + x, iny + y), j01 = px_reflect(J, inx + x + 1, iny + y);
+                    const int j10 = px_reflect(J, inx + x, iny + y + 1), j11 = px_reflect(J, inx + x + 1, iny + y + 1);
+                    const int diff = ((j00 * w.w00 + j01 * w.w01 + j10 * w.w10 + j11 * w.w11 + (1 << 8)) >> 9) - (int)sI[i];
+                    const short2 g = sG[i];
+                    b[0] += (long long)(diff * (int)g.x);
+                    b[1] += (long long)(diff * (int)g.y);
+                }
+            }
+            group_sum<NT, 2>(b, red, parity, tid);
+            const float b1 = fmul(__ll2float_rn(b[0]), FLT_SCALE), b2 = fmul(__ll2float_rn(b[1]), FLT_SCALE);
+            const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
+            const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
+            nx = fadd(nx, dx); ny = fadd(ny, dy);
+            next_x = fadd(nx, half_x); next_y = fadd(ny, half_y);
+            if (fadd(fmul(dx, dx), fmul(dy, dy)) <= A.eps2) break;
+            if (j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
+                next_x = fsub(next_x, fmul(dx, 0.5f));
+                next_y = fsub(next_y, fmul(dy, 0.5f));
+                break;
+            }
+            pdx = dx; pdy = dy;
+        }
+
+        if (level == 0 && status) {
+            const float fx = fsub(next_x, half_x), fy = fsub(next_y, half_y);
+            const int inx = __float2int_rd(fx), iny = __float2int_rd(fy);
+            if (inx < -ww || inx >= J.w || iny < -wh || iny >= J.h) {
+                status = 0;
+            } else {
+                w = bilin_weights(fsub(fx, (float)inx), fsub(fy, (float)iny));
+                long long e[1] = {0};
+                for (int i = tid; i < npx; i += NT) {
+                    const int y = i / ww, x = i - y * ww;
+                    const int j00 = px_reflect(J, inx + x, iny + y), j01 = px_reflect(J, inx + x + 1, iny + y);
+                    const int j10 = px_reflect(J, inx + x, iny + y + 1), j11 = px_reflect(J, inx + x + 1, iny + y + 1);
+                    const int diff = ((j00 * w.w00 + j01 * w.w01 + j10 * w.w10 + j11 * w.w11 + (1 << 8)) >> 9) - (int)sI[i];
+                    e[0] += (long long)abs(diff);
+                }
+                group_sum<NT, 1>(e, red, parity, tid);
+                err = __fdiv_rn(__ll2float_rn(e[0]), (float)(32 * ww * wh));
+            }
+        }
+    }
+    out_x = next_x; out_y = next_y; out_status = status; out_err = err;
+}
+
+template <int NT, int GROUPS>
+__global__ void __launch_bounds__(NT * GROUPS)
+lk_track_kernel(const LkArgs A)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int group = threadIdx.x / NT, tid = threadIdx.x % NT;
+    const int pair = blockIdx.y;
+    const int pt = blockIdx.x * GROUPS + group;
+    if (NT == 32 && pt >= A.npts) return;  // warp-granular groups may exit independently
+
+    const int npx = A.win_w * A.win_h, ntile = (A.win_w + 1) * (A.win_h + 1);
+    // per-group shared slices: sD (short2 x ntile) | sG (short2 x npx) | sI (short x npx) | red
+    const size_t bytes_D = ((size_t)ntile * 4 + 15) & ~(size_t)15;
+    const size_t bytes_G = ((size_t)npx * 4 + 15) & ~(size_t)15;
+    const size_t bytes_I = ((size_t)npx * 2 + 15) & ~(size_t)15;
+    const size_t bytes_R = (NT > 32) ? (size_t)2 * (NT / 32) * 3 * sizeof(long long) : 0;
+    unsigned char* base = smem_raw + (size_t)group * (bytes_D + bytes_G + bytes_I + bytes_R);
+    short2* sD = reinterpret_cast<short2*>(base);
+    short2* sG = reinterpret_cast<short2*>(base + bytes_D);
+    short* sI = reinterpret_cast<short*>(base + bytes_D + bytes_G);
+    long long* red = reinterpret_cast<long long*>(base + bytes_D + bytes_G + bytes_I);
+    int parity = 0;
+
+    const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
+    const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
+    const uint8_t* N0 = A.next0 + (long long)pair * A.next_stride;
+    const uint8_t* Np = A.next_pyr ? A.next_pyr + (long long)pair * A.next_pyr_stride : nullptr;
+
+    const float* pin = A.pts + (long long)pair * A.pts_stride + 2ll * pt;
+    const float px = __ldg(pin), py = __ldg(pin + 1);
+
+    float fx, fy, ferr;
+    int fst;
+    track_point<NT>(A, P0, A.prev_pitch, Pp, N0, A.next_pitch, Np, px, py, fx, fy, fst, ferr, sD, sI, sG, red, parity, tid);
+    int st = fst;
+    float bx = 0.f, by = 0.f;
+    if (A.fbt >= 0.f && fst) {
+        float berr;
+        int bst;
+        track_point<NT>(A, N0, A.next_pitch, Np, P0, A.prev_pitch, Pp, fx, fy, bx, by, bst, berr, sD, sI, sG, red, parity, tid);
+        const float ddx = fsub(px, bx), ddy = fsub(py, by);
+        const float fbe = __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+        st = bst && (fbe < A.fbt);
+    }
+    if (tid == 0) {
+        const long long o = (long long)pair * A.npts + pt;
+        A.out[2 * o] = fx;
+        A.out[2 * o + 1] = fy;
+        A.status[o] = (uint8_t)st;
+        A.err[o] = fst ? ferr : 0.f;
+        if (A.back) { A.back[2 * o] = bx; A.back[2 * o + 1] = by; }
+    }
+}
+
+size_t group_smem_bytes(int win_w, int win_h, int nt)
+{
+    const size_t npx = (size_t)win_w * win_h, ntile = (size_t)(win_w + 1) * (win_h + 1);
+    size_t b = ((ntile * 4 + 15) & ~(size_t)15) + ((npx * 4 + 15) & ~(size_t)15) + ((npx * 2 + 15) & ~(size_t)15);
+    if (nt > 32) b += (size_t)2 * (nt / 32) * 3 * sizeof(long long);
+    return b;
+}
+
+}  // namespace
+
+VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, int32_t prev_pitch, const uint8_t* prev_pyr,
+                         int64_t prev_pyr_stride, const uint8_t* next_frames, int64_t next_frame_stride, int32_t next_pitch,
+                         const uint8_t* next_pyr, int64_t next_pyr_stride, const vel_pyr_layout* layout, int32_t npairs,
+                         const float* prev_pts, int64_t pts_stride, int32_t npts, const vel_lk_params* params, float* next_pts,
+                         uint8_t* status, float* err, float* back_pts, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(prev_frames && next_frames && layout && prev_pts && params && next_pts && status && err,
+                  "vel_lk_track: NULL argument");
+    VEL_CHECK_ARG(npairs > 0 && npairs <= 65535, "vel_lk_track: npairs %d outside [1,65535]", npairs);
+    VEL_CHECK_ARG(npts >= 0, "vel_lk_track: npts < 0");
+    if (npts == 0) return VEL_OK;
+    const int ww = params->win_w, wh = params->win_h;
+    VEL_CHECK_ARG(ww >= 3 && wh >= 3 && ww <= 127 && wh <= 127, "vel_lk_track: window %dx%d outside [3,127]", ww, wh);
+    VEL_CHECK_ARG(layout->max_level >= 0 && layout->max_level < VEL_MAX_LEVELS, "vel_lk_track: bad layout");
+    VEL_CHECK_ARG(layout->width[0] > ww && layout->height[0] > wh,
+                  "vel_lk_track: image %dx%d must be larger than the window %dx%d", layout->width[0], layout->height[0], ww, wh);
+    VEL_CHECK_ARG(layout->max_level == 0 || (prev_pyr && next_pyr), "vel_lk_track: pyramid buffers required for max_level > 0");
+    VEL_CHECK_ARG(prev_pitch >= layout->width[0] && next_pitch >= layout->width[0], "vel_lk_track: pitch < width");
+
+    LkArgs A;
+    A.prev0 = prev_frames; A.prev_stride = prev_frame_stride; A.prev_pitch = prev_pitch;
+    A.prev_pyr = prev_pyr; A.prev_pyr_stride = prev_pyr_stride;
+    A.next0 = next_frames; A.next_stride = next_frame_stride; A.next_pitch = next_pitch;
+    A.next_pyr = next_pyr; A.next_pyr_stride = next_pyr_stride;
+    A.lv.max_level = layout->max_level;
+    for (int l = 0; l < VEL_MAX_LEVELS; ++l) {
+        A.lv.w[l] = layout->width[l]; A.lv.h[l] = layout->height[l]; A.lv.pitch[l] = layout->pitch[l]; A.lv.off[l] = layout->offset[l];
+    }
+    A.pts = prev_pts; A.pts_stride = pts_stride; A.npts = npts;
+    A.out = next_pts; A.status = status; A.err = err; A.back = back_pts;
+    A.win_w = ww; A.win_h = wh;
+    int mc = params->max_count; mc = mc < 0 ? 0 : (mc > 100 ? 100 : mc);
+    double eps = params->eps; eps = eps < 0. ? 0. : (eps > 10. ? 10. : eps);
+    A.max_count = mc;
+    A.eps2 = (float)(eps * eps);
+    A.min_eig = params->min_eig_threshold;
+    A.fbt = params->fb_threshold;
+
+    cudaStream_t st = (cudaStream_t)stream;
+    if (ww * wh <= 1024) {
+        constexpr int NT = 32, GROUPS = 8;
+        const size_t smem = GROUPS * group_smem_bytes(ww, wh, NT);
+        auto kern = lk_track_kernel<NT, GROUPS>;
+        if (smem > 48 * 1024) VEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((npts + GROUPS - 1) / GROUPS, npairs);
+        kern<<<grid, NT * GROUPS, smem, st>>>(A);
+    } else {
+        constexpr int NT = 128, GROUPS = 1;
+        const size_t smem = group_smem_bytes(ww, wh, NT);
+        VEL_CHECK_ARG(smem <= 227 * 1024, "vel_lk_track: window %dx%d needs %zu B of shared memory", ww, wh, smem);
+        auto kern = lk_track_kernel<NT, GROUPS>;
+        if (smem > 48 * 1024) VEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(npts, npairs);
+        kern<<<grid, NT, smem, st>>>(A);
+    }
+    VEL_LAUNCH_CHECK("lk_track_kernel");
+    return VEL_OK;
+}

@@ -1,0 +1,173 @@
+// K1: image pyramid (cv2.pyrDown chain) and the 1/4 nearest-neighbour decimation.
+//
+// Reference call sites: the pyramid cv2.calcOpticalFlowPyrLK builds internally (utils/KLT.py:45,48)
+// and cv2.resize(.., fx=fy=1/4, INTER_NEAREST) (utils/KLT.py:111,113).
+//
+// pyrDown semantics for CV_8UC1 (verified bit-exact against cv2 4.13 by the oracle tests):
+//   dst(x,y) = (sum_{i,j} k[i] k[j] src(2x-2+i, 2y-2+j) + 128) >> 8, k = [1 4 6 4 1],
+//   BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2).
+//
+// Streaming, HBM-bound: algorithmic bytes per level = src bytes read once + dst bytes written once.
+#include "common.cuh"
+
+namespace {
+
+// ---- vectorised interior kernel -------------------------------------------------------------
+// One CTA produces a TILE_W x TILE_H block of the destination.  The (2*TILE_W+4+pad) x (2*TILE_H+4)
+// source footprint is staged in shared memory with 16-byte loads, filtered horizontally into
+// uint16 rows (max 16*255 fits), then vertically; four output pixels are packed per 32-bit store.
+constexpr int TILE_W = 128;   // destination columns per CTA (multiple of 8)
+constexpr int TILE_H = 16;    // destination rows per CTA
+constexpr int SRC_ROWS = 2 * TILE_H + 3;          // rows 2*y0-2 .. 2*(y0+TILE_H-1)+2
+constexpr int SRC_COLS = 2 * TILE_W + 32;         // cols 2*x0-16 .. 2*x0+2*TILE_W+15 (16-byte aligned both ends)
+constexpr int PYR_THREADS = 256;
+
+__global__ void __launch_bounds__(PYR_THREADS)
+pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride, int sw, int sh, int spitch,
+                     uint8_t* __restrict__ dst_base, long long dst_stride, int dw, int dh, int dpitch)
+{
+    __shared__ __align__(16) uint8_t s_src[SRC_ROWS][SRC_COLS];
+    __shared__ __align__(16) uint16_t s_h[SRC_ROWS][TILE_W];
+
+    const uint8_t* __restrict__ src = src_base + (long long)blockIdx.z * src_stride;
+    uint8_t* __restrict__ dst = dst_base + (long long)blockIdx.z * dst_stride;
+    const int ox0 = blockIdx.x * TILE_W, oy0 = blockIdx.y * TILE_H;
+    const int sx0 = 2 * ox0 - 16, sy0 = 2 * oy0 - 2;
+    const int tid = threadIdx.x;
+
+    // interior tiles whose whole footprint is inside the image and 16-byte loadable take the vector path
+    const bool aligned = ((((uintptr_t)src) | (uintptr_t)spitch) & 15) == 0;
+    const bool interior = aligned && sx0 >= 0 && sy0 >= 0 && (sx0 + SRC_COLS) <= sw && (sy0 + SRC_ROWS) <= sh;
+    if (interior) {
+        constexpr int VEC_PER_ROW = SRC_COLS / 16;
+        for (int i = tid; i < SRC_ROWS * VEC_PER_ROW; i += PYR_THREADS) {
+            const int r = i / VEC_PER_ROW, c = i % VEC_PER_ROW;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(sy0 + r) * spitch + sx0) + c);
+            reinterpret_cast<uint4*>(&s_src[r][0])[c] = v;
+        }
+    } else {
+        for (int i = tid; i < SRC_ROWS * SRC_COLS; i += PYR_THREADS) {
+            const int r = i / SRC_COLS, c = i % SRC_COLS;
+            const int yy = reflect101(sy0 + r, sh), xx = reflect101(sx0 + c, sw);
+            s_src[r][c] = src[(long long)yy * spitch + xx];
+        }
+    }
+    __syncthreads();
+
+    // horizontal pass: each item = 4 adjacent outputs of one source row (bytes c = 8j+14 .. 8j+24)
+    for (int i = tid; i < SRC_ROWS * (TILE_W / 4); i += PYR_THREADS) {
+        const int r = i / (TILE_W / 4), j = i % (TILE_W / 4);
+        const uint2 a = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 8]);
+        const uint2 b = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 16]);
+        const unsigned c16 = s_src[r][8 * j + 24];
+        // names: bytes 6..16 relative to 8j+8
+        const unsigned p6 = (a.y >> 16) & 0xff, p7 = a.y >> 24;
+        const unsigned p8 = b.x & 0xff, p9 = (b.x >> 8) & 0xff, p10 = (b.x >> 16) & 0xff, p11 = b.x >> 24;
+        const unsigned p12 = b.y & 0xff, p13 = (b.y >> 8) & 0xff, p14 = (b.y >> 16) & 0xff, p15 = b.y >> 24;
+        const unsigned h0 = p6 + p10 + 4 * (p7 + p9) + 6 * p8;
+        const unsigned h1 = p8 + p12 + 4 * (p9 + p11) + 6 * p10;
+        const unsigned h2 = p10 + p14 + 4 * (p11 + p13) + 6 * p12;
+        const unsigned h3 = p12 + c16 + 4 * (p13 + p15) + 6 * p14;
+        *reinterpret_cast<uint2*>(&s_h[r][4 * j]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    }
+    __syncthreads();
+
+    // vertical pass: each item = 4 adjacent outputs of one destination row
+    for (int i = tid; i < TILE_H * (TILE_W / 4); i += PYR_THREADS) {
+        const int y = i / (TILE_W / 4), j = i % (TILE_W / 4);
+        const int oy = oy0 + y, ox = ox0 + 4 * j;
+        if (oy >= dh || ox >= dw) continue;
+        unsigned acc[4] = {0, 0, 0, 0};
+        const int kw[5] = {1, 4, 6, 4, 1};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            const uint2 h = *reinterpret_cast<const uint2*>(&s_h[2 * y + k][4 * j]);
+            acc[0] += kw[k] * (h.x & 0xffff);
+            acc[1] += kw[k] * (h.x >> 16);
+            acc[2] += kw[k] * (h.y & 0xffff);
+            acc[3] += kw[k] * (h.y >> 16);
+        }
+        const unsigned o0 = (acc[0] + 128) >> 8, o1 = (acc[1] + 128) >> 8, o2 = (acc[2] + 128) >> 8, o3 = (acc[3] + 128) >> 8;
+        uint8_t* d = dst + (long long)oy * dpitch + ox;
+        if (ox + 3 < dw && ((((uintptr_t)d) & 3) == 0)) {
+            *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+        } else {
+            d[0] = (uint8_t)o0;
+            if (ox + 1 < dw) d[1] = (uint8_t)o1;
+            if (ox + 2 < dw) d[2] = (uint8_t)o2;
+            if (ox + 3 < dw) d[3] = (uint8_t)o3;
+        }
+    }
+}
+
+__global__ void decimate4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst,
+                                 int dw, int dh, int dpitch)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= dw || y >= dh) return;
+    const int sx = min(4 * x, sw - 1), sy = min(4 * y, sh - 1);
+    dst[(long long)y * dpitch + x] = __ldg(src + (long long)sy * spitch + sx);
+}
+
+}  // namespace
+
+VEL_API int vel_pyr_layout_make(int32_t width, int32_t height, int32_t win_w, int32_t win_h, int32_t max_level,
+                                vel_pyr_layout* out)
+{
+    VEL_CHECK_ARG(out != nullptr, "vel_pyr_layout_make: out is NULL");
+    VEL_CHECK_ARG(width > 0 && height > 0 && win_w > 0 && win_h > 0, "vel_pyr_layout_make: bad size %dx%d win %dx%d", width,
+                  height, win_w, win_h);
+    VEL_CHECK_ARG(max_level >= 0 && max_level < VEL_MAX_LEVELS, "vel_pyr_layout_make: max_level %d outside [0,%d)", max_level,
+                  VEL_MAX_LEVELS);
+    int w = width, h = height, lvl = 0;
+    int64_t off = 0;
+    out->width[0] = w; out->height[0] = h; out->pitch[0] = 0; out->offset[0] = 0;
+    while (lvl < max_level) {
+        const int nw = (w + 1) / 2, nh = (h + 1) / 2;
+        if (nw <= win_w || nh <= win_h) break;
+        ++lvl;
+        w = nw; h = nh;
+        const int pitch = (w + 15) & ~15;
+        out->width[lvl] = w; out->height[lvl] = h; out->pitch[lvl] = pitch; out->offset[lvl] = off;
+        off += ((int64_t)pitch * h + 255) & ~(int64_t)255;
+    }
+    for (int l = lvl + 1; l < VEL_MAX_LEVELS; ++l) { out->width[l] = out->height[l] = out->pitch[l] = 0; out->offset[l] = 0; }
+    out->max_level = lvl;
+    out->bytes = off;
+    return VEL_OK;
+}
+
+VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t pitch, int32_t nframes,
+                           const vel_pyr_layout* L, uint8_t* pyr, int64_t pyr_stride, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(frames && L, "vel_pyramid_u8: NULL argument");
+    VEL_CHECK_ARG(nframes > 0 && nframes <= 65535, "vel_pyramid_u8: nframes %d outside [1,65535]", nframes);
+    VEL_CHECK_ARG(L->max_level >= 0 && L->max_level < VEL_MAX_LEVELS, "vel_pyramid_u8: bad layout");
+    VEL_CHECK_ARG(pitch >= L->width[0], "vel_pyramid_u8: pitch %d < width %d", pitch, L->width[0]);
+    if (L->max_level == 0) return VEL_OK;
+    VEL_CHECK_ARG(pyr != nullptr && pyr_stride >= L->bytes, "vel_pyramid_u8: pyramid buffer missing or stride too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int l = 1; l <= L->max_level; ++l) {
+        const uint8_t* src = l == 1 ? frames : pyr + L->offset[l - 1];
+        const long long sstride = l == 1 ? frame_stride : pyr_stride;
+        const int spitch = l == 1 ? pitch : L->pitch[l - 1];
+        dim3 grid((L->width[l] + TILE_W - 1) / TILE_W, (L->height[l] + TILE_H - 1) / TILE_H, nframes);
+        pyrdown_tiled_kernel<<<grid, PYR_THREADS, 0, st>>>(src, sstride, L->width[l - 1], L->height[l - 1], spitch,
+                                                          pyr + L->offset[l], pyr_stride, L->width[l], L->height[l],
+                                                          L->pitch[l]);
+        VEL_LAUNCH_CHECK("pyrdown_tiled_kernel");
+    }
+    return VEL_OK;
+}
+
+VEL_API int vel_decimate4_u8(const uint8_t* src, int32_t width, int32_t height, int32_t pitch, uint8_t* dst, int32_t dst_width,
+                             int32_t dst_height, int32_t dst_pitch, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(src && dst, "vel_decimate4_u8: NULL argument");
+    VEL_CHECK_ARG(width > 0 && height > 0 && dst_width > 0 && dst_height > 0 && dst_height <= 65535,
+                  "vel_decimate4_u8: bad size");
+    dim3 grid((dst_width + 255) / 256, dst_height);
+    decimate4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, width, height, pitch, dst, dst_width, dst_height, dst_pitch);
+    VEL_LAUNCH_CHECK("decimate4_kernel");
+    return VEL_OK;
+}

@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SFM speed-estimation hot path (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "C2"): synthetic 1080p frames, 4096 Harris tracks, pyramidal LK
+15x15, 3 pyramid levels, <=10 iterations, eps 0.1, forward-backward threshold 1.0 -- i.e. the
+reference call utils.KLT.cv2calcOpticalFlowPyrLK(im0, im1, p0, fbt=1.0, winSize=(15,15), maxLevel=2,
+criteria=(EPS|COUNT,10,0.1)) applied to every consecutive pair of a frame sequence.
+
+One STEP = one pass over a batch of PAIRS consecutive frame pairs (PAIRS+1 frames, ~270 MB > the
+126 MB L2, so every step streams its frames from HBM): K1 builds each frame's pyramid once, K2
+tracks all pairs forward+backward in one launch.  value = frames (pairs) per second, whole job.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, NPTS = 1080, 1920, 4096
+LK = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+FBT = 1.0
+PAIRS = 128            # frame pairs per step and per GPU
+UNIQUE_FRAMES = 24     # distinct rendered frames (one approach run of the generator, no depth reset inside); the batch tiles them
+SEED = 1234
+
+# Algorithmic bytes (restated in DESIGN.md): HW = H*W, Py = HW*(1 + 1/4 + 1/16)
+HW_B = H * W
+PY_B = HW_B + (HW_B // 4) + (HW_B // 16)
+PT_B = NPTS * (8 + 8 + 1 + 4)
+K1_BYTES_PER_FRAME = HW_B + (PY_B - HW_B)        # frame read once, levels >= 1 written once
+K2_BYTES_PER_PAIR_FB = 4 * PY_B + PT_B           # prev+next pyramids, forward and backward pass, point I/O
+SEQ_BYTES_PER_FRAME_FB = K1_BYTES_PER_FRAME + K2_BYTES_PER_PAIR_FB  # = 13,694,016 (SURVEY's sequence figure)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def make_frames(n_unique, seed):
+    from velocity_b200 import synth
+
+    frames, _ = synth.plane_sequence(n_unique, h=H, w=W, seed=seed)
+    pts = synth.harris_tracks(frames[0], NPTS)
+    return np.stack(frames), pts
+
+
+def tile_sequence(unique, n):
+    """n frames cycling forward/backward through the unique frames (every neighbour pair is a real
+    consecutive pair of the rendered sequence, so the per-pair work is representative)."""
+    u = unique.shape[0]
+    idx, i, d = [], 0, 1
+    for _ in range(n):
+        idx.append(i)
+        if i + d < 0 or i + d >= u:
+            d = -d
+        i += d
+    return idx
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle sampling during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_run(unique, pts, steps, warmup, sample_pairs):
+    """The reference's CPU implementation of the path on this host.  The reference's arithmetic is
+    cv2.calcOpticalFlowPyrLK (third-party, un-vendored); oracle/ holds a restatement of the wrapper
+    (oracle/klt_oracle.lk_forward_backward <- utils/KLT.py:37-51).  When opencv-python is importable
+    the third-party arithmetic is executed by cv2 itself -- literally what the reference runs, and
+    faster than the scalar C restatement, so the speed-up is not flattered; otherwise by
+    oracle/velocity_oracle.c (OpenMP, all cores)."""
+    try:
+        import cv2
+
+        cores = cv2.getNumThreads()
+
+        def one_pair(a, b):
+            p2, st, err = cv2.calcOpticalFlowPyrLK(a, b, pts, None, **LK)
+            v = st.ravel().astype(bool)
+            p1, st2, _ = cv2.calcOpticalFlowPyrLK(b, a, p2, None, **LK)
+            d = pts - p1
+            return p2, v & st2.ravel().astype(bool) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < np.float32(FBT))
+
+        backend = "opencv-python %s (cv2.calcOpticalFlowPyrLK fwd+bwd, %d threads)" % (cv2.__version__, cores)
+    except Exception:
+        from oracle import klt_oracle
+
+        cores = os.cpu_count()
+
+        def one_pair(a, b):
+            p2, v, _ = klt_oracle.lk_forward_backward(a, b, pts, fbt=FBT, **LK)
+            return p2, v
+
+        backend = "oracle/velocity_oracle.c (OpenMP, %d threads)" % cores
+    idx = tile_sequence(unique, sample_pairs + 1)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for k in range(sample_pairs):
+            one_pair(unique[idx[k]], unique[idx[k + 1]])
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per_step = float(np.mean(times))
+    return sample_pairs / per_step, per_step * 1e3, cores, backend
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    unique, pts = make_frames(4, SEED)
+    sample = 8
+    fps, ms, cores, backend = cpu_reference_run(unique, pts, args.steps, args.warmup, sample)
+    line = {
+        "impl": "reference", "metric": "SFM frames/sec @1080p, 4k tracks (KLT pyramidal LK fwd+bwd, 3 levels)",
+        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve",
+        "data": "synthetic",
+        "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
+                   "pairs_per_step": sample, "tracks": NPTS},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": "%d consecutive 1080p pairs per step on the host; %s" % (sample, backend)},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from velocity_b200.lk import FrameBatch, lk_params, track_pairs
+    from velocity_b200.sequence import SequenceTracker
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # every rank owns its own shard of PAIRS pairs (weak scaling, no data-path collective: KLT
+    # shards by frames); shards differ by seed
+    unique, pts_np = make_frames(UNIQUE_FRAMES, SEED + rank)
+    idx = tile_sequence(unique, PAIRS + 1)
+    frames_host = torch.from_numpy(unique[idx]).pin_memory()          # [PAIRS+1, H, W]
+    pts_host = torch.from_numpy(pts_np).pin_memory()
+    frames_dev = frames_host.to(dev)
+    pts_dev = pts_host.to(dev)
+    params = lk_params(fbt=FBT, **LK)
+    fb = FrameBatch(frames_dev, LK["winSize"], LK["maxLevel"])
+    l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        fb.build()
+        return track_pairs(fb, fb, pts_dev, params, 0, 1, PAIRS)
+
+    # ---- device-resident timing: `value` + per-kernel durations for the roofline -------------------
+    for _ in range(args.warmup):
+        step_resident()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    t_start = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for s in range(args.steps):
+        ev[s][0].record()
+        fb.build()
+        ev[s][1].record()
+        out = track_pairs(fb, fb, pts_dev, params, 0, 1, PAIRS)
+        ev[s][2].record()
+    t_end.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    total_ms = t_start.elapsed_time(t_end)
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    valid_frac = float(out[1].float().mean().item())
+
+    # ---- end-to-end timing through the public host-buffer API ----------------------------------------
+    chunk = 32
+    tracker = SequenceTracker(H, W, NPTS, chunk=chunk, fbt=FBT, **LK)
+    o_pts = torch.empty((PAIRS, NPTS, 2), dtype=torch.float32).pin_memory()
+    o_st = torch.empty((PAIRS, NPTS), dtype=torch.uint8).pin_memory()
+    o_err = torch.empty((PAIRS, NPTS), dtype=torch.float32).pin_memory()
+    for _ in range(max(1, args.warmup // 2)):
+        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        l2_flush.zero_()  # nothing of the previous step survives in L2 (frames come from the host anyway)
+        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_valid = float((o_st != 0).float().mean().item())
+
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms, k1_ms, k2_ms = (float(x) for x in times.tolist())
+
+    if rank == 0:
+        peaks, peak_kind = measured_peaks()
+        ms_per_step = total_ms / args.steps
+        value = world * PAIRS / (ms_per_step * 1e-3)
+        e2e_value = world * PAIRS / (e2e_ms / args.steps * 1e-3)
+        k2_gbs = PAIRS * K2_BYTES_PER_PAIR_FB / (k2_ms * 1e-3) / 1e9
+        k1_gbs = (PAIRS + 1) * K1_BYTES_PER_FRAME / (k1_ms * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("lk_track_kernel_bytes_per_launch")
+        cpu = None
+        if world == 1 or True:
+            try:
+                fps, ms, cores, backend = cpu_reference_run(unique[:4], pts_np, 3, 1, 4)
+                cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                       "sample": "4 consecutive 1080p pairs x 3 repeats on the host; %s" % backend}
+            except Exception as ex:  # pragma: no cover
+                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % ex}
+        line = {
+            "metric": "SFM frames/sec @1080p, 4k tracks (KLT pyramidal LK fwd+bwd, 3 levels)",
+            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
+            "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
+                       "pairs_per_step_per_gpu": PAIRS, "tracks": NPTS, "frames_resident_mb": (PAIRS + 1) * HW_B / 1e6,
+                       "l2_policy": "inputs (%d MB of frames per step) larger than L2; e2e additionally flushes L2" % ((PAIRS + 1) * HW_B // 1000000),
+                       "valid_fraction": valid_frac, "sharding": "frames, no collective"},
+            "roofline": {"bound": "hbm", "kernel": "lk_track_kernel (K2)", "achieved": k2_gbs, "peak": peaks["hbm_gbs"],
+                         "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
+                         "bytes_per_launch": PAIRS * K2_BYTES_PER_PAIR_FB, "ms_per_launch": k2_ms,
+                         "k1_pyramid": {"achieved": k1_gbs, "frac": k1_gbs / peaks["hbm_gbs"], "ms_per_step": k1_ms,
+                                        "bytes_per_step": (PAIRS + 1) * K1_BYTES_PER_FRAME},
+                         "sequence_model": {"bytes_per_frame": SEQ_BYTES_PER_FRAME_FB,
+                                            "achieved": PAIRS * SEQ_BYTES_PER_FRAME_FB / (ms_per_step * 1e-3) / 1e9}},
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "valid_fraction": e2e_valid, "chunk_frames": chunk},
+            "gpu_launches": args.steps * (LK["maxLevel"] + 1),
+            "clocks": clk,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

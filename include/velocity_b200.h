@@ -119,17 +119,29 @@ int vel_triangulate_2v(const double* A, const double* U, int32_t nf, int32_t nv,
 /* fcnNvintercept (utils/MSV.py:146-175): least-squares intersection of nf rays per point. */
 int vel_triangulate_nv(const double* A, const double* U, int32_t nf, int32_t nv, double* C0, vel_stream_t stream);
 
+/* fcnMSV1_t (utils/MSV.py:8-49): Levenberg-Marquardt on the LAST camera's translation x with the
+ * pairwise triangulation (vel_triangulate_2v) re-run inside every iteration; the whole loop runs
+ * in one persistent kernel.  A_fixed [nf-1][3] are the origins of cameras 0..nf-2, the last origin
+ * is -x; U [3][nf][ng]; z [ng][2] are the last frame's pixels.  Outputs x [3], b0 [ng][3] (the
+ * triangulated points relative to the last camera at the last evaluated iterate), iters (number of
+ * iterations, or -max_iter if the cap was hit). */
+int vel_msv1_t(const double* K, const double* A_fixed, const double* U, int32_t nf, int32_t ng, const double* z,
+               const double* x0, int32_t max_iter, double* x, double* b0, int32_t* iters, vel_stream_t stream);
+
 /* K7.  One Gauss-Newton linearisation of fcnNLS_batch (utils/NLS.py:186-250) in block form.
  * Parameters x = [points nt*3 | camera positions nc*3 | camera rpy nc*3] (camera 0 is fixed at
  * identity and not a parameter); z = observations [2][(nc+1)][nt] (all x then all y, track
  * fastest, utils/NLS.py:198-199).  Writes, for J = forward-difference Jacobian (1e-6):
  *   V  [nt][6]      upper triangle of the 3x3 point blocks of JtJ
  *   U  [nc][21]     upper triangle of the 6x6 camera blocks of JtJ (pos, rpy)
- *   W  [nc][nt][18] camera-point cross blocks (6x3, row-major)   (may be NULL)
+ *   W  [nc*6][nt*3] camera-point cross blocks as one row-major matrix: row 6*(c-1)+a (a = pos xyz,
+ *                   rpy xyz), column 3*i+b                       (may be NULL)
  *   g  [nt*3+nc*6]  Jt (z - zhat), in parameter order
  *   cost[1]         sum of squared residuals
- * cam_first/cam_count select the slice of cameras 1..nc this call (this rank) owns: V and the
- * point part of g then hold PARTIAL sums to be all-reduced across ranks. */
+ * Cameras are indexed 0..nc (0 = the fixed identity camera, which has measurements but no
+ * parameters).  cam_first/cam_count select the cameras this call (this rank) owns: it fills their
+ * rows of U/W/g and PARTIAL sums over them in V, the point part of g and cost, to be all-reduced
+ * across ranks.  U rows are indexed by camera-1. */
 int vel_ba_accumulate(const double* K, const double* x, const double* z, int32_t nt, int32_t nc, int32_t cam_first,
                       int32_t cam_count, double* V, double* U, double* W, double* g, double* cost, vel_stream_t stream);
 

@@ -1,0 +1,193 @@
+"""Drop-in for the reference's utils/NLS.py: same names, arguments, dtypes and printed messages.
+
+    estimateWorldCameraPose  utils/NLS.py:9-33
+    fzK / fzC                utils/NLS.py:71-86
+    fcnNLS_t                 utils/NLS.py:102-129   -> K5 vel_nls_t
+    fcnNLS_Rt                utils/NLS.py:133-183   -> K5 vel_nls_rt
+    fcnNLS_batch             utils/NLS.py:186-250   -> K7 vel_ba_accumulate + K8 vel_ba_solve
+
+The solvers run on the GPU in float64 with the reference's forward-difference Jacobians; only
+argument packing, the iteration printouts and the final float32 casts happen on the host.
+"""
+import ctypes as C
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from .common import addcol1, pscale, rms, world2image
+from .device import ptr, require_cuda, stream_ptr
+from .transforms import dcm2rpy, rpy2dcm
+
+
+def fzK(a, K):
+    return pscale(a @ K)
+
+
+def fzC(a, K, R, t=np.zeros((1, 3))):
+    return pscale(addcol1(a) @ (np.concatenate([R, t]) @ K))
+
+
+def _dev64(a):
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float64))).cuda()
+
+
+def nls_batch_device(K, p, pw, first, count, x0, dof):
+    """Batched K5 call on CUDA float64 tensors.  Returns (x [nprob,dof], iters [nprob] int32)."""
+    require_cuda()
+    nprob = first.shape[0]
+    x = torch.empty((nprob, dof), dtype=torch.float64, device=p.device)
+    iters = torch.empty((nprob,), dtype=torch.int32, device=p.device)
+    fn = _lib.lib().vel_nls_t if dof == 3 else _lib.lib().vel_nls_rt
+    _lib.check(fn(ptr(K), ptr(p), ptr(pw), ptr(first), ptr(count), nprob, ptr(x0), ptr(x), ptr(iters), stream_ptr()),
+               "vel_nls_t" if dof == 3 else "vel_nls_rt")
+    return x, iters
+
+
+def _single(K, p, pw, x, dof):
+    n = int(np.asarray(pw).shape[0])
+    first = torch.zeros(1, dtype=torch.int32, device="cuda")
+    count = torch.full((1,), n, dtype=torch.int32, device="cuda")
+    xd, it = nls_batch_device(_dev64(K), _dev64(p).reshape(-1, 2), _dev64(pw).reshape(-1, 3), first, count,
+                              _dev64(np.asarray(x, np.float64)[:dof]).reshape(1, dof), dof)
+    return xd.cpu().numpy()[0], int(it.item())
+
+
+def fcnNLS_t(K, p, pw, x):
+    """3-dof translation fit; returns float32 [3]."""
+    xs, it = _single(K, p, pw, x, 3)
+    if it < 0:
+        print("WARNING: fcnNLS_t() reaching max iterations!")
+    return xs.astype(np.float32)
+
+
+def fcnNLS_Rt(K, p, pw, x):
+    """6-dof fit; returns (R float32 3x3, t float32 [3])."""
+    xs, it = _single(K, p, pw, x, 6)
+    if it < 0:
+        print("WARNING: fcnNLS_Rt() reaching max iterations!")
+    return rpy2dcm(xs[:3]).astype(np.float32), xs[3:6].astype(np.float32)
+
+
+def estimateWorldCameraPose(K, p, p3, t=np.array([0, 0, 1]), R=np.eye(3), findR=False):
+    x0 = np.concatenate((dcm2rpy(R), t))
+    if findR is True:
+        R, t = fcnNLS_Rt(K.astype(float), p.astype(float), p3, x0)
+    else:
+        t = fcnNLS_t(K.astype(float), p.astype(float), p3, t)
+    p_proj = world2image(K, R, t, p3)
+    residuals = rms(p - p_proj)
+    return t, R, residuals, p_proj
+
+
+class BundleAdjuster:
+    """Device-resident state of one fcnNLS_batch problem (K7 + K8).  With torch.distributed
+    initialised and `shard=True`, cameras are split across ranks: each rank accumulates the blocks
+    of its own cameras, V / g_p / cost are all-reduced, the camera blocks (U, g_c, W rows) are
+    all-gathered, and every rank solves the same reduced system redundantly."""
+
+    def __init__(self, K, z, x0, nt, nc, shard=False):
+        require_cuda()
+        self.nt, self.nc = nt, nc
+        dev = torch.device("cuda", torch.cuda.current_device())
+        self.K = _dev64(K)
+        self.z = _dev64(z)
+        self.x = _dev64(x0).clone()
+        nx = 3 * nt + 6 * nc
+        self.V = torch.zeros((nt, 6), dtype=torch.float64, device=dev)
+        self.U = torch.zeros((max(nc, 1), 21), dtype=torch.float64, device=dev)
+        self.W = torch.zeros((max(6 * nc, 1), 3 * nt), dtype=torch.float64, device=dev)
+        self.g = torch.zeros((nx,), dtype=torch.float64, device=dev)
+        self.cost = torch.zeros((1,), dtype=torch.float64, device=dev)
+        self.rms_delta = torch.zeros((1,), dtype=torch.float64, device=dev)
+        L = _lib.lib()
+        nbytes = int(L.vel_ba_solve_workspace(nt, nc))
+        if nbytes == 0:
+            raise RuntimeError("vel_ba_solve_workspace failed: %s" % L.vel_last_error().decode())
+        self.work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+        self.rank, self.world = 0, 1
+        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+        # camera indices 0..nc split into `world` contiguous slices
+        bounds = [(nc + 1) * r // self.world for r in range(self.world + 1)]
+        self.slices = [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(self.world)]
+
+    def accumulate(self):
+        L = _lib.lib()
+        first, count = self.slices[self.rank]
+        _lib.check(L.vel_ba_accumulate(ptr(self.K), ptr(self.x), ptr(self.z), self.nt, self.nc, first, count, ptr(self.V),
+                                       ptr(self.U), ptr(self.W), ptr(self.g), ptr(self.cost), stream_ptr()), "vel_ba_accumulate")
+        if self.world > 1:
+            self._exchange()
+
+    def _exchange(self):
+        import torch.distributed as dist
+
+        nt, nc = self.nt, self.nc
+        # (1) all-reduce of the per-point partial sums (+ cost)
+        dist.all_reduce(self.V)
+        dist.all_reduce(self.g[:3 * nt])
+        dist.all_reduce(self.cost)
+        # (2) all-gather of the per-shard camera blocks: every rank broadcasts the rows it owns
+        for r, (first, count) in enumerate(self.slices):
+            lo = max(first, 1) - 1          # parameterised-camera index range [lo, hi)
+            hi = first + count - 1
+            if hi <= lo:
+                continue
+            dist.broadcast(self.U[lo:hi], src=r)
+            dist.broadcast(self.W[6 * lo:6 * hi], src=r)
+            dist.broadcast(self.g[3 * nt + 3 * lo:3 * nt + 3 * hi], src=r)
+            dist.broadcast(self.g[3 * nt + 3 * nc + 3 * lo:3 * nt + 3 * nc + 3 * hi], src=r)
+
+    def solve(self):
+        L = _lib.lib()
+        _lib.check(L.vel_ba_solve(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, ptr(self.x),
+                                  ptr(self.rms_delta), ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_solve")
+
+    def step(self):
+        """One LM iteration.  Returns (f = rms(z - zhat) before the update, rms(delta))."""
+        self.accumulate()
+        self.solve()
+        out = torch.stack([self.cost[0], self.rms_delta[0]]).cpu().numpy()
+        nz = 2 * self.nt * (self.nc + 1)
+        return float(np.sqrt(out[0] / nz)), float(out[1])
+
+
+def fcnNLS_batch(K, P, pw, cw):
+    """Bundle adjustment over tie points, camera positions and camera roll/pitch/yaw (camera 0
+    fixed).  Same update rule, iteration cap (10), stopping test and printouts as the reference;
+    returns (cw [nc+1,3], pw [nt,3]) float64."""
+    v = np.isfinite(P[4]).sum(1) == P.shape[2]
+    P, pw = P[:, v], pw[v]
+    _, nt, ncam = P.shape
+    nc = ncam - 1
+    if np.isnan(P[:2]).any():
+        raise ValueError("fcnNLS_batch: NaN pixel in a full-length track (the reference zeroes the residual but not the "
+                         "Jacobian row, utils/NLS.py:200-201,233 -- undefined behaviour, refused here)")
+    z = np.concatenate((P[0].T.ravel(), P[1].T.ravel())).astype(np.float64)  # [2][nc+1][nt]
+    x0 = np.concatenate((np.asarray(pw, np.float64), np.asarray(cw, np.float64)[1:], np.zeros((nc, 3)))).ravel()
+    ba = BundleAdjuster(np.asarray(K, float), z, x0, nt, nc)
+    max_iter = 10
+    i = 0
+    tic = time.time()
+    f = float("nan")
+    for i in range(max_iter):
+        tic = time.time()
+        f, xr = ba.step()
+        print(f"{i:g}: {time.time() - tic:.3f}s, f={f:g}, x={xr}")
+        if xr < 1e-7:
+            break
+    else:
+        print("WARNING: fcnNLS_batch() reaching max iterations!")
+    print(f"fcnNLS_batch done in {i:g} steps, {time.time() - tic:.3f}s, f={f:g}")
+    x = ba.x.cpu().numpy()
+    j = nt * 3
+    pw_out = x[:j].reshape(nt, 3)
+    cw_out = np.concatenate((np.zeros((1, 3)), x[j:j + nc * 3].reshape(nc, 3)), 0)
+    return cw_out, pw_out
+
+
+def fcnNLS_batch2(K, P, pw, cw):
+    raise NotImplementedError("fcnNLS_batch2 (utils/NLS.py:253-328, range/az/el parametrisation; never called by the "
+                              "reference) is not built yet -- see DESIGN.md 'Out of scope / next'")

@@ -51,6 +51,7 @@ SIGNATURES = {
     "vel_nls_rt": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "vel_triangulate_2v": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
     "vel_triangulate_nv": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "vel_msv1_t": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P, _I32, _P, _P, _P, _P]),
     "vel_ba_accumulate": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vel_ba_solve_workspace": (C.c_size_t, [_I32, _I32]),
     "vel_ba_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
@@ -59,8 +60,7 @@ SIGNATURES = {
 }
 
 # entry points declared in the header whose kernels have not landed yet (shrinks to empty)
-PENDING = {"vel_nls_t", "vel_nls_rt", "vel_triangulate_2v", "vel_triangulate_nv", "vel_ba_accumulate",
-           "vel_ba_solve_workspace", "vel_ba_solve", "vel_match_knn2_hamming256", "vel_match_knn2_l2"}
+PENDING = set()
 
 _lib = None
 

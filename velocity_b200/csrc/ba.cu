@@ -1,0 +1,502 @@
+// K7 / K8: bundle adjustment of fcnNLS_batch (utils/NLS.py:186-250) in block-sparse form.
+//
+// The reference builds a DENSE forward-difference Jacobian JT [nx][nz] by re-evaluating the whole
+// projection once per parameter (nx evaluations of nz measurements, 277 GB at the BASELINE size) and
+// inverts the dense nx x nx system.  Each measurement depends on one point (3 params) and one camera
+// (6 params: position, roll/pitch/yaw; camera 0 is fixed at identity), so JtJ has the block layout
+//      [ V  W^T ]   V = blockdiag(V_i 3x3),  U = blockdiag(U_j 6x6),  W_ji 6x3
+//      [ W  U   ]
+// K7 accumulates exactly the non-zero blocks, with the SAME forward-difference Jacobian entries
+// (perturb one parameter by 1e-6, re-project, subtract, divide) the reference computes, so the two
+// linear systems are identical up to float64 summation order.  K8 solves (JtJ + I) delta = Jt r by
+// Schur complement on the point blocks and applies x += 0.9 * delta (utils/NLS.py:234-235).
+//
+// Layouts:  x = [points nt*3 | camera positions nc*3 | camera rpy nc*3]  (utils/NLS.py:203)
+//           z = [2][nc+1][nt]  (all u then all v, camera-major, track fastest, :198-199)
+//           V [nt][6] upper triangles, U [nc][21] upper triangles (pos,rpy order),
+//           W [nc*6][nt*3] row-major (row 6*(c-1)+a, column 3*i+b), g [nt*3 + nc*6] in x order.
+// Cameras are indexed 0..nc (0 = the fixed one); a rank owning cameras [cam_first, cam_first +
+// cam_count) fills its rows of U/W/g_c and PARTIAL V/g_p/cost over its cameras (all-reduce across
+// ranks).
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr double JDX = 1e-6;
+constexpr int CAM_THREADS = 256;
+constexpr int PT_THREADS = 128;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ void rpy2dcm(const double* rpy, double* C)  // utils/transforms.py:7-23
+{
+    double sr, cr, sp, cp, sy, cy;
+    sincos(rpy[0], &sr, &cr);
+    sincos(rpy[1], &sp, &cp);
+    sincos(rpy[2], &sy, &cy);
+    C[0] = cp * cy; C[1] = sr * sp * cy - cr * sy; C[2] = cr * sp * cy + sr * sy;
+    C[3] = cp * sy; C[4] = sr * sp * sy + cr * cy; C[5] = cr * sp * sy - sr * cy;
+    C[6] = -sp;     C[7] = sr * cp;                C[8] = cr * cp;
+}
+
+__device__ __forceinline__ void project(const double* K, double ax, double ay, double az, double& u, double& v)
+{
+    const double q0 = ax * K[0] + ay * K[3] + az * K[6];
+    const double q1 = ax * K[1] + ay * K[4] + az * K[7];
+    const double q2 = ax * K[2] + ay * K[5] + az * K[8];
+    u = q0 / q2;
+    v = q1 / q2;
+}
+
+__device__ __forceinline__ void rot(const double* R, double X, double Y, double Z, double& ax, double& ay, double& az)
+{
+    ax = X * R[0] + Y * R[3] + Z * R[6];
+    ay = X * R[1] + Y * R[4] + Z * R[7];
+    az = X * R[2] + Y * R[5] + Z * R[8];
+}
+
+// per-camera constants for the point kernel: R0 (9) + pos (3); camera 0 = identity / zero
+__global__ void ba_cam_setup_kernel(const double* __restrict__ x, int nt, int nc, double* __restrict__ cams)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > nc) return;
+    double* o = cams + 12ll * c;
+    if (c == 0) {
+        o[0] = 1; o[1] = 0; o[2] = 0; o[3] = 0; o[4] = 1; o[5] = 0; o[6] = 0; o[7] = 0; o[8] = 1; o[9] = 0; o[10] = 0; o[11] = 0;
+        return;
+    }
+    const double* pos = x + 3ll * nt + 3ll * (c - 1);
+    const double* rpy = x + 3ll * nt + 3ll * nc + 3ll * (c - 1);
+    rpy2dcm(rpy, o);
+    o[9] = pos[0]; o[10] = pos[1]; o[11] = pos[2];
+}
+
+// Jacobian of one observation wrt its point: forward differences exactly as the reference forms them
+// (camera 0 projects the point itself: alist[0] = pw, utils/NLS.py:208)
+__device__ __forceinline__ void point_jacobian(const double* K, const double* R, const double* pos, bool fixed_cam, double X,
+                                               double Y, double Z, double& u0, double& v0, double (&ju)[3], double (&jv)[3])
+{
+    double ax, ay, az, u, v;
+    if (fixed_cam) {
+        project(K, X, Y, Z, u0, v0);
+        project(K, X + JDX, Y, Z, u, v); ju[0] = (u - u0) / JDX; jv[0] = (v - v0) / JDX;
+        project(K, X, Y + JDX, Z, u, v); ju[1] = (u - u0) / JDX; jv[1] = (v - v0) / JDX;
+        project(K, X, Y, Z + JDX, u, v); ju[2] = (u - u0) / JDX; jv[2] = (v - v0) / JDX;
+        return;
+    }
+    rot(R, X, Y, Z, ax, ay, az);
+    project(K, ax + pos[0], ay + pos[1], az + pos[2], u0, v0);
+    rot(R, X + JDX, Y, Z, ax, ay, az);
+    project(K, ax + pos[0], ay + pos[1], az + pos[2], u, v); ju[0] = (u - u0) / JDX; jv[0] = (v - v0) / JDX;
+    rot(R, X, Y + JDX, Z, ax, ay, az);
+    project(K, ax + pos[0], ay + pos[1], az + pos[2], u, v); ju[1] = (u - u0) / JDX; jv[1] = (v - v0) / JDX;
+    rot(R, X, Y, Z + JDX, ax, ay, az);
+    project(K, ax + pos[0], ay + pos[1], az + pos[2], u, v); ju[2] = (u - u0) / JDX; jv[2] = (v - v0) / JDX;
+}
+
+// ---- camera kernel: one CTA per parameterised camera ------------------------------------------------
+__global__ void __launch_bounds__(CAM_THREADS)
+ba_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z, int nt, int nc,
+                 int cam_first, double* __restrict__ U, double* __restrict__ W, double* __restrict__ g)
+{
+    constexpr int NACC = 21 + 6;
+    constexpr int NWARP = CAM_THREADS / 32;
+    __shared__ double sK[9], sR[4][9], sP[3];
+    __shared__ double sred[NWARP][NACC];
+    const int c = cam_first + blockIdx.x;  // camera index, >= 1
+    const int tid = threadIdx.x;
+    const double* pos = x + 3ll * nt + 3ll * (c - 1);
+    const double* rpy = x + 3ll * nt + 3ll * nc + 3ll * (c - 1);
+    if (tid < 9) sK[tid] = Kg[tid];
+    if (tid < 3) sP[tid] = pos[tid];
+    if (tid < 4) {
+        double r[3] = {rpy[0], rpy[1], rpy[2]};
+        if (tid > 0) r[tid - 1] = r[tid - 1] + JDX;
+        rpy2dcm(r, sR[tid]);
+    }
+    __syncthreads();
+    const double* zu = z + (long long)c * nt;
+    const double* zv = z + (long long)(nc + 1) * nt + (long long)c * nt;
+
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (int i = tid; i < nt; i += CAM_THREADS) {
+        const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
+        double u0, v0, pu[3], pv[3];
+        point_jacobian(sK, sR[0], sP, false, X, Y, Z, u0, v0, pu, pv);
+        double cu[6], cv[6], ax, ay, az, u, v;
+        rot(sR[0], X, Y, Z, ax, ay, az);
+        project(sK, ax + (sP[0] + JDX), ay + sP[1], az + sP[2], u, v); cu[0] = (u - u0) / JDX; cv[0] = (v - v0) / JDX;
+        project(sK, ax + sP[0], ay + (sP[1] + JDX), az + sP[2], u, v); cu[1] = (u - u0) / JDX; cv[1] = (v - v0) / JDX;
+        project(sK, ax + sP[0], ay + sP[1], az + (sP[2] + JDX), u, v); cu[2] = (u - u0) / JDX; cv[2] = (v - v0) / JDX;
+#pragma unroll
+        for (int m = 1; m < 4; ++m) {
+            rot(sR[m], X, Y, Z, ax, ay, az);
+            project(sK, ax + sP[0], ay + sP[1], az + sP[2], u, v);
+            cu[2 + m] = (u - u0) / JDX; cv[2 + m] = (v - v0) / JDX;
+        }
+        const double ru = zu[i] - u0, rv = zv[i] - v0;
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = r; q < 6; ++q) acc[k++] += cu[r] * cu[q] + cv[r] * cv[q];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[21 + r] += cu[r] * ru + cv[r] * rv;
+        if (W) {
+#pragma unroll
+            for (int a = 0; a < 6; ++a) {
+                double* w = W + ((long long)(6 * (c - 1) + a) * nt + i) * 3;
+                w[0] = cu[a] * pu[0] + cv[a] * pv[0];
+                w[1] = cu[a] * pu[1] + cv[a] * pv[1];
+                w[2] = cu[a] * pu[2] + cv[a] * pv[2];
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = warp_sum(acc[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) sred[tid >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double s = 0.0;
+        for (int w = 0; w < NWARP; ++w) s += sred[w][tid];
+        if (tid < 21) U[21ll * (c - 1) + tid] = s;
+        else {
+            const int r = tid - 21;  // g order: cam positions block, then cam rpy block
+            const long long idx = r < 3 ? 3ll * nt + 3ll * (c - 1) + r : 3ll * nt + 3ll * nc + 3ll * (c - 1) + (r - 3);
+            g[idx] = s;
+        }
+    }
+}
+
+// ---- point kernel: one thread per point, loops over this rank's cameras ---------------------------------
+__global__ void __launch_bounds__(PT_THREADS)
+ba_point_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z,
+                const double* __restrict__ cams, int nt, int nc, int cam_first, int cam_count, double* __restrict__ V,
+                double* __restrict__ g, double* __restrict__ cost_part)
+{
+    __shared__ double sK[9];
+    __shared__ double sred[PT_THREADS / 32];
+    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid;
+    if (tid < 9) sK[tid] = Kg[tid];
+    __syncthreads();
+    double cost = 0.0;
+    if (i < nt) {
+        const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
+        double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
+        for (int c = cam_first; c < cam_first + cam_count; ++c) {
+            const double* cm = cams + 12ll * c;
+            double u0, w0, ju[3], jv[3];
+            point_jacobian(sK, cm, cm + 9, c == 0, X, Y, Z, u0, w0, ju, jv);
+            const double ru = z[(long long)c * nt + i] - u0;
+            const double rv = z[(long long)(nc + 1) * nt + (long long)c * nt + i] - w0;
+            v00 += ju[0] * ju[0] + jv[0] * jv[0]; v01 += ju[0] * ju[1] + jv[0] * jv[1]; v02 += ju[0] * ju[2] + jv[0] * jv[2];
+            v11 += ju[1] * ju[1] + jv[1] * jv[1]; v12 += ju[1] * ju[2] + jv[1] * jv[2]; v22 += ju[2] * ju[2] + jv[2] * jv[2];
+            g0 += ju[0] * ru + jv[0] * rv; g1 += ju[1] * ru + jv[1] * rv; g2 += ju[2] * ru + jv[2] * rv;
+            cost += ru * ru + rv * rv;
+        }
+        double* v = V + 6ll * i;
+        v[0] = v00; v[1] = v01; v[2] = v02; v[3] = v11; v[4] = v12; v[5] = v22;
+        g[3ll * i] = g0; g[3ll * i + 1] = g1; g[3ll * i + 2] = g2;
+    }
+    cost = warp_sum(cost);
+    if ((tid & 31) == 0) sred[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w];
+        cost_part[blockIdx.x] = s;
+    }
+}
+
+__global__ void ba_cost_finalize_kernel(const double* __restrict__ part, int n, double* __restrict__ cost)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += part[k];
+        *cost = s;
+    }
+}
+
+// ---- solve ----------------------------------------------------------------------------------------------
+// per point: L_i = chol((V_i + I)^-1) so that W' = W * blockdiag(L_i) gives W' W'^T = W (V+I)^-1 W^T;
+// also y_i = (V_i + I)^-1 g_p,i
+__global__ void __launch_bounds__(PT_THREADS)
+ba_point_prep_kernel(const double* __restrict__ V, const double* __restrict__ g, int nt, double* __restrict__ Vinv,
+                     double* __restrict__ Lf, double* __restrict__ y)
+{
+    const int i = blockIdx.x * PT_THREADS + threadIdx.x;
+    if (i >= nt) return;
+    const double* v = V + 6ll * i;
+    const double m00 = v[0] + 1.0, m01 = v[1], m02 = v[2], m11 = v[3] + 1.0, m12 = v[4], m22 = v[5] + 1.0;
+    const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
+    const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
+    const double inv = 1.0 / (m00 * c00 + m01 * c01 + m02 * c02);
+    const double i00 = c00 * inv, i01 = c01 * inv, i02 = c02 * inv, i11 = c11 * inv, i12 = c12 * inv, i22 = c22 * inv;
+    double* o = Vinv + 6ll * i;
+    o[0] = i00; o[1] = i01; o[2] = i02; o[3] = i11; o[4] = i12; o[5] = i22;
+    // lower Cholesky factor of the (SPD) inverse
+    const double l00 = sqrt(i00), l10 = i01 / l00, l20 = i02 / l00;
+    const double l11 = sqrt(i11 - l10 * l10), l21 = (i12 - l20 * l10) / l11;
+    const double l22 = sqrt(i22 - l20 * l20 - l21 * l21);
+    double* l = Lf + 6ll * i;
+    l[0] = l00; l[1] = l10; l[2] = l11; l[3] = l20; l[4] = l21; l[5] = l22;
+    const double g0 = g[3ll * i], g1 = g[3ll * i + 1], g2 = g[3ll * i + 2];
+    y[3ll * i] = i00 * g0 + i01 * g1 + i02 * g2;
+    y[3ll * i + 1] = i01 * g0 + i11 * g1 + i12 * g2;
+    y[3ll * i + 2] = i02 * g0 + i12 * g1 + i22 * g2;
+}
+
+// W'[row][3i..3i+2] = W[row][3i..3i+2] * L_i   (row vector times lower-triangular 3x3)
+__global__ void __launch_bounds__(256)
+ba_scale_w_kernel(const double* __restrict__ W, const double* __restrict__ Lf, int nrows, int nt, double* __restrict__ Wp)
+{
+    const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (long long)nrows * nt) return;
+    const int i = (int)(idx % nt);
+    const double* w = W + idx * 3;
+    const double* l = Lf + 6ll * i;
+    const double w0 = w[0], w1 = w[1], w2 = w[2];
+    double* o = Wp + idx * 3;
+    o[0] = w0 * l[0] + w1 * l[1] + w2 * l[3];
+    o[1] = w1 * l[2] + w2 * l[4];
+    o[2] = w2 * l[5];
+}
+
+// S (col-major n6 x n6, full) = blockdiag(U_j + I); rhs = g_c
+__global__ void ba_init_s_kernel(const double* __restrict__ U, const double* __restrict__ g, int nt, int nc,
+                                 double* __restrict__ S, double* __restrict__ rhs)
+{
+    const int n6 = 6 * nc;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)n6 * n6) return;
+    const int r = (int)(idx % n6), c = (int)(idx / n6);
+    double v = 0.0;
+    if (r / 6 == c / 6) {
+        // S ordering is camera-major: row 6*j + a, a in (pos xyz, rpy xyz)
+        const int j = r / 6, a = r % 6, b = c % 6;
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        const int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);
+        v = U[21ll * j + k] + (a == b ? 1.0 : 0.0);
+    }
+    S[idx] = v;
+    if (c == 0) {
+        const int j = r / 6, a = r % 6;
+        rhs[r] = a < 3 ? g[3ll * nt + 3ll * j + a] : g[3ll * nt + 3ll * nc + 3ll * j + (a - 3)];
+    }
+}
+
+// delta_p,i = y_i - (V_i+I)^-1 t_i with t = W^T delta_c;  x += 0.9*delta;  partial sum of delta^2
+__global__ void __launch_bounds__(PT_THREADS)
+ba_update_kernel(const double* __restrict__ Vinv, const double* __restrict__ y, const double* __restrict__ t,
+                 const double* __restrict__ dc, int nt, int nc, double* __restrict__ x, double* __restrict__ ss_part)
+{
+    __shared__ double sred[PT_THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long i = (long long)blockIdx.x * PT_THREADS + tid;
+    double ss = 0.0;
+    if (i < nt) {
+        const double* v = Vinv + 6 * i;
+        const double t0 = t[3 * i], t1 = t[3 * i + 1], t2 = t[3 * i + 2];
+        const double d0 = y[3 * i] - (v[0] * t0 + v[1] * t1 + v[2] * t2);
+        const double d1 = y[3 * i + 1] - (v[1] * t0 + v[3] * t1 + v[4] * t2);
+        const double d2 = y[3 * i + 2] - (v[2] * t0 + v[4] * t1 + v[5] * t2);
+        x[3 * i] += 0.9 * d0; x[3 * i + 1] += 0.9 * d1; x[3 * i + 2] += 0.9 * d2;
+        ss = 0.81 * (d0 * d0 + d1 * d1 + d2 * d2);
+    } else if (i < nt + 6ll * nc) {
+        // camera part: dc is camera-major (6 per camera), x is [pos block | rpy block]
+        const int r = (int)(i - nt), j = r / 6, a = r % 6;
+        const double d = dc[r];
+        const long long xi = a < 3 ? 3ll * nt + 3ll * j + a : 3ll * nt + 3ll * nc + 3ll * j + (a - 3);
+        x[xi] += 0.9 * d;
+        ss = 0.81 * d * d;
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) sred[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w];
+        ss_part[blockIdx.x] = s;
+    }
+}
+
+__global__ void ba_rms_finalize_kernel(const double* __restrict__ part, int n, long long nx, double* __restrict__ rms)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) s += part[k];
+        *rms = sqrt(s / (double)nx);
+    }
+}
+
+struct Handles {
+    cublasHandle_t blas = nullptr;
+    cusolverDnHandle_t solver = nullptr;
+};
+
+Handles* handles()
+{
+    static thread_local Handles h;
+    if (!h.blas) {
+        if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { h.blas = nullptr; return nullptr; }
+        if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { h.solver = nullptr; return nullptr; }
+    }
+    return &h;
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+struct SolveLayout {
+    size_t off_wp, off_s, off_vinv, off_l, off_y, off_rhs, off_t, off_part, off_info, off_potrf, total;
+    int lwork;
+};
+
+bool solve_layout(int nt, int nc, SolveLayout* L, bool query_potrf)
+{
+    const size_t n6 = 6ull * nc, n3 = 3ull * nt;
+    size_t o = 0;
+    L->off_wp = o; o += align256(sizeof(double) * n6 * n3);
+    L->off_s = o; o += align256(sizeof(double) * n6 * n6);
+    L->off_vinv = o; o += align256(sizeof(double) * 6 * nt);
+    L->off_l = o; o += align256(sizeof(double) * 6 * nt);
+    L->off_y = o; o += align256(sizeof(double) * n3);
+    L->off_rhs = o; o += align256(sizeof(double) * (n6 + 8));
+    L->off_t = o; o += align256(sizeof(double) * n3);
+    L->off_part = o; o += align256(sizeof(double) * ((nt + n6) / PT_THREADS + 2));
+    L->off_info = o; o += 256;
+    L->lwork = 0;
+    if (query_potrf && nc > 0) {
+        Handles* h = handles();
+        if (!h) return false;
+        int lwork = 0;
+        if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, (int)n6, nullptr, (int)n6, &lwork) != CUSOLVER_STATUS_SUCCESS)
+            return false;
+        L->lwork = lwork;
+    }
+    L->off_potrf = o; o += align256(sizeof(double) * (size_t)(L->lwork > 0 ? L->lwork : 1));
+    L->total = o;
+    return true;
+}
+
+}  // namespace
+
+VEL_API int vel_ba_accumulate(const double* K, const double* x, const double* z, int32_t nt, int32_t nc, int32_t cam_first,
+                              int32_t cam_count, double* V, double* U, double* W, double* g, double* cost, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(K && x && z && V && U && g && cost, "vel_ba_accumulate: NULL argument");
+    VEL_CHECK_ARG(nt > 0 && nc >= 0, "vel_ba_accumulate: bad sizes nt=%d nc=%d", nt, nc);
+    VEL_CHECK_ARG(cam_first >= 0 && cam_count >= 0 && cam_first + cam_count <= nc + 1,
+                  "vel_ba_accumulate: camera slice [%d,%d) outside [0,%d]", cam_first, cam_first + cam_count, nc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    double* tmp = nullptr;
+    VEL_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * (12ull * (nc + 1) + pblocks), st));
+    double* cams = tmp;
+    double* cost_part = tmp + 12ull * (nc + 1);
+    ba_cam_setup_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(x, nt, nc, cams);
+    VEL_LAUNCH_CHECK("ba_cam_setup_kernel");
+    const int first_param = cam_first < 1 ? 1 : cam_first;
+    const int n_param = cam_first + cam_count - first_param;
+    if (n_param > 0) {
+        ba_camera_kernel<<<n_param, CAM_THREADS, 0, st>>>(K, x, z, nt, nc, first_param, U, W, g);
+        VEL_LAUNCH_CHECK("ba_camera_kernel");
+    }
+    ba_point_kernel<<<pblocks, PT_THREADS, 0, st>>>(K, x, z, cams, nt, nc, cam_first, cam_count, V, g, cost_part);
+    VEL_LAUNCH_CHECK("ba_point_kernel");
+    ba_cost_finalize_kernel<<<1, 32, 0, st>>>(cost_part, pblocks, cost);
+    VEL_LAUNCH_CHECK("ba_cost_finalize_kernel");
+    VEL_CUDA(cudaFreeAsync(tmp, st));
+    return VEL_OK;
+}
+
+VEL_API size_t vel_ba_solve_workspace(int32_t nt, int32_t nc)
+{
+    if (nt <= 0 || nc < 0) return 0;
+    SolveLayout L;
+    if (!solve_layout(nt, nc, &L, true)) { vel_set_error("vel_ba_solve_workspace: cuSOLVER/cuBLAS handle creation failed"); return 0; }
+    return L.total;
+}
+
+VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
+                         double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(V && g && x && rms_delta && work, "vel_ba_solve: NULL argument");
+    VEL_CHECK_ARG(nt > 0 && nc >= 0, "vel_ba_solve: bad sizes nt=%d nc=%d", nt, nc);
+    VEL_CHECK_ARG(nc == 0 || (U && W), "vel_ba_solve: U and W are required when nc > 0");
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc, &L, true), "vel_ba_solve: cuSOLVER/cuBLAS handle creation failed");
+    VEL_CHECK_ARG(work_bytes >= L.total, "vel_ba_solve: workspace %zu B < required %zu B", work_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wb = (char*)work;
+    double* Wp = (double*)(wb + L.off_wp);
+    double* S = (double*)(wb + L.off_s);
+    double* Vinv = (double*)(wb + L.off_vinv);
+    double* Lf = (double*)(wb + L.off_l);
+    double* y = (double*)(wb + L.off_y);
+    double* rhs = (double*)(wb + L.off_rhs);
+    double* t = (double*)(wb + L.off_t);
+    double* part = (double*)(wb + L.off_part);
+    int* info = (int*)(wb + L.off_info);
+    double* potrf_work = (double*)(wb + L.off_potrf);
+    const int n6 = 6 * nc, n3 = 3 * nt;
+    const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+
+    ba_point_prep_kernel<<<pblocks, PT_THREADS, 0, st>>>(V, g, nt, Vinv, Lf, y);
+    VEL_LAUNCH_CHECK("ba_point_prep_kernel");
+    if (nc > 0) {
+        Handles* h = handles();
+        VEL_CHECK_ARG(h != nullptr, "vel_ba_solve: cuBLAS/cuSOLVER handles unavailable");
+        cublasSetStream(h->blas, st);
+        cusolverDnSetStream(h->solver, st);
+        cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
+        const long long nel = (long long)n6 * nt;
+        ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, n6, nt, Wp);
+        VEL_LAUNCH_CHECK("ba_scale_w_kernel");
+        const long long ns = (long long)n6 * n6;
+        ba_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(U, g, nt, nc, S, rhs);
+        VEL_LAUNCH_CHECK("ba_init_s_kernel");
+        const double one = 1.0, neg = -1.0, zero = 0.0;
+        // row-major W [n6][n3] is the column-major matrix Wc [n3][n6] (lda = n3)
+        // S(lower) -= Wc'^T Wc'
+        if (cublasDsyrk(h->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, n6, n3, &neg, Wp, n3, &one, S, n6) != CUBLAS_STATUS_SUCCESS) {
+            vel_set_error("vel_ba_solve: cublasDsyrk failed");
+            return VEL_ERR_CUDA;
+        }
+        // rhs = g_c - W y   (W y = Wc^T y)
+        if (cublasDgemv(h->blas, CUBLAS_OP_T, n3, n6, &neg, W, n3, y, 1, &one, rhs, 1) != CUBLAS_STATUS_SUCCESS) {
+            vel_set_error("vel_ba_solve: cublasDgemv failed");
+            return VEL_ERR_CUDA;
+        }
+        if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, n6, S, n6, potrf_work, L.lwork, info) != CUSOLVER_STATUS_SUCCESS ||
+            cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, n6, 1, S, n6, rhs, n6, info) != CUSOLVER_STATUS_SUCCESS) {
+            vel_set_error("vel_ba_solve: cuSOLVER Cholesky failed");
+            return VEL_ERR_CUDA;
+        }
+        // t = W^T delta_c = Wc delta_c
+        if (cublasDgemv(h->blas, CUBLAS_OP_N, n3, n6, &one, W, n3, rhs, 1, &zero, t, 1) != CUBLAS_STATUS_SUCCESS) {
+            vel_set_error("vel_ba_solve: cublasDgemv failed");
+            return VEL_ERR_CUDA;
+        }
+    } else {
+        VEL_CUDA(cudaMemsetAsync(t, 0, sizeof(double) * n3, st));
+    }
+    const int ublocks = (nt + n6 + PT_THREADS - 1) / PT_THREADS;
+    ba_update_kernel<<<ublocks, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nc, x, part);
+    VEL_LAUNCH_CHECK("ba_update_kernel");
+    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + n6, rms_delta);
+    VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
+    return VEL_OK;
+}

@@ -33,6 +33,9 @@ FBT = 1.0
 PAIRS = 128            # frame pairs per step and per GPU
 UNIQUE_FRAMES = 24     # distinct rendered frames (one approach run of the generator, no depth reset inside); the batch tiles them
 SEED = 1234
+Z0_M = 40.0           # plane depth of the generator: >= 99% of the tracks pass the FB gate over the whole approach
+                      # (SURVEY 8(d) suggests 10 m, where 3 levels of 15x15 cannot follow the 37 px/frame corner flow
+                      # and only ~21% survive; use --z0 10 to reproduce that worst case)
 
 # Algorithmic bytes (restated in DESIGN.md): HW = H*W, Py = HW*(1 + 1/4 + 1/16)
 HW_B = H * W
@@ -54,7 +57,7 @@ def measured_peaks():
 def make_frames(n_unique, seed):
     from velocity_b200 import synth
 
-    frames, _ = synth.plane_sequence(n_unique, h=H, w=W, seed=seed)
+    frames, _ = synth.plane_sequence(n_unique, h=H, w=W, seed=seed, Z0=Z0_M)
     pts = synth.harris_tracks(frames[0], NPTS)
     return np.stack(frames), pts
 
@@ -166,7 +169,7 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve",
         "data": "synthetic",
         "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
-                   "pairs_per_step": sample, "tracks": NPTS},
+                   "pairs_per_step": sample, "tracks": NPTS, "plane_depth_m": Z0_M},
         "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
                          "sample": "%d consecutive 1080p pairs per step on the host; %s" % (sample, backend)},
         "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -289,7 +292,7 @@ def run_ours(args):
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
             "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
-                       "pairs_per_step_per_gpu": PAIRS, "tracks": NPTS, "frames_resident_mb": (PAIRS + 1) * HW_B / 1e6,
+                       "pairs_per_step_per_gpu": PAIRS, "tracks": NPTS, "plane_depth_m": Z0_M, "frames_resident_mb": (PAIRS + 1) * HW_B / 1e6,
                        "l2_policy": "inputs (%d MB of frames per step) larger than L2; e2e additionally flushes L2" % ((PAIRS + 1) * HW_B // 1000000),
                        "valid_fraction": valid_frac, "sharding": "frames, no collective"},
             "roofline": {"bound": "hbm", "kernel": "lk_track_kernel (K2)", "achieved": k2_gbs, "peak": peaks["hbm_gbs"],
@@ -311,12 +314,15 @@ def run_ours(args):
 
 
 def main():
+    global Z0_M
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--z0", type=float, default=Z0_M, help="plane depth (m) of the synthetic generator")
     args = ap.parse_args()
+    Z0_M = args.z0
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)

@@ -10,7 +10,8 @@ from velocity_b200 import synth  # noqa: E402
 from velocity_b200.lk import FrameBatch, lk_params, track_pairs  # noqa: E402
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 32
-frames, _ = synth.plane_sequence(B + 1, seed=1234)
+Z0 = float(sys.argv[2]) if len(sys.argv) > 2 else 40.0
+frames, _ = synth.plane_sequence(B + 1, seed=1234, Z0=Z0)
 pts = torch.from_numpy(synth.harris_tracks(frames[0], 4096)).cuda()
 dev = torch.from_numpy(np.stack(frames)).cuda()
 for name, lk, fbt in [("c2_fwd", dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1)), None),

@@ -374,13 +374,22 @@ struct W15Patch {
     int I[8], gx[8], gy[8];
 };
 
+// single-overshoot REFLECT_101 clamped into range (far corners of the staged region can overshoot
+// twice on 16-pixel-wide top levels; those entries are never used but must stay in bounds)
+__device__ __forceinline__ unsigned reflect_safe(int i, int n)
+{
+    i = i < 0 ? -i : i;
+    i = i >= n ? 2 * n - 2 - i : i;
+    return (unsigned)max(0, min(i, n - 1));
+}
+
 // the lane's 9 J bytes of the 16x16 footprint at integer position (inx, iny); 32-bit offsets from the
 // (warp-uniform) level base keep the address arithmetic to one add per load
 __device__ __forceinline__ void w15_gather(const Img& J, int inx, int iny, int h, int c, int (&jv)[9])
 {
     const bool inside = inx >= 0 && iny >= 0 && inx + 15 < J.w && iny + 15 < J.h;
+    const unsigned pitch = (unsigned)J.pitch;
     if (inside) {
-        const unsigned pitch = (unsigned)J.pitch;
         const unsigned off = (unsigned)(iny + 8 * h) * pitch + (unsigned)(inx + c);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
@@ -388,11 +397,11 @@ __device__ __forceinline__ void w15_gather(const Img& J, int inx, int iny, int h
             jv[k] = (int)__ldg(J.p + (off + rr * pitch));
         }
     } else {
-        const unsigned xx = (unsigned)reflect101(inx + c, J.w);
+        const unsigned xx = reflect_safe(inx + c, J.w);
 #pragma unroll
         for (int k = 0; k < 9; ++k) {
             const int rr = min(8 * h + k, 15);
-            jv[k] = (int)__ldg(J.p + ((unsigned)reflect101(iny + rr, J.h) * (unsigned)J.pitch + xx));
+            jv[k] = (int)__ldg(J.p + (reflect_safe(iny + rr, J.h) * pitch + xx));
         }
     }
 }
@@ -408,198 +417,11 @@ __device__ __forceinline__ void w15_diff(const int (&jv)[9], const Weights& w, c
     }
 }
 
-__device__ void track_point_w15(const LkArgs& A, const uint8_t* I0, int I0_pitch, const uint8_t* Ipyr, const uint8_t* J0,
-                                int J0_pitch, const uint8_t* Jpyr, float px, float py, float& out_x, float& out_y,
-                                int& out_status, float& out_err, uint8_t* sreg, int lane)
-{
-    const int h = lane >> 4, c = lane & 15;
-    const float half = 7.0f;
-    const float FLT_SCALE = 1.f / 1048576.f;
-    int status = 1;
-    float err = 0.f;
-    float next_x = 0.f, next_y = 0.f;
-
-    for (int level = A.lv.max_level; level >= 0; --level) {
-        Img I, J;
-        I.w = J.w = A.lv.w[level];
-        I.h = J.h = A.lv.h[level];
-        if (level == 0) { I.p = I0; I.pitch = I0_pitch; J.p = J0; J.pitch = J0_pitch; }
-        else { I.p = Ipyr + A.lv.off[level]; J.p = Jpyr + A.lv.off[level]; I.pitch = J.pitch = A.lv.pitch[level]; }
-
-        const float scale = 1.f / (float)(1 << level);
-        float prev_x = fmul(px, scale), prev_y = fmul(py, scale);
-        float nx, ny;
-        if (level == A.lv.max_level) { nx = prev_x; ny = prev_y; }
-        else { nx = fmul(next_x, 2.f); ny = fmul(next_y, 2.f); }
-        next_x = nx; next_y = ny;
-
-        prev_x = fsub(prev_x, half); prev_y = fsub(prev_y, half);
-        const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
-        if (ipx < -W15 || ipx >= I.w || ipy < -W15 || ipy >= I.h) {
-            if (level == 0) { status = 0; err = 0.f; }
-            continue;
-        }
-        Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
-
-        // ---- stage the 18x18 region (rows ipy-1.., cols ipx-1..) in shared memory ----------------------
-        const int rx0 = ipx - 1, ry0 = ipy - 1;
-        const bool interior = rx0 >= 0 && ry0 >= 0 && rx0 + 17 < I.w && ry0 + 17 < I.h;
-        __syncwarp();
-        if (interior) {
-            const unsigned pitch = (unsigned)I.pitch;
-            const unsigned base = (unsigned)ry0 * pitch + (unsigned)rx0;
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                const unsigned row = 2 * q + h;
-                sreg[row * W15_REGION_PITCH + c] = __ldg(I.p + (base + row * pitch + c));
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int k = lane + 32 * q;
-                if (k < 36) {
-                    const unsigned row = k >> 1, col = 16 + (k & 1);
-                    sreg[row * W15_REGION_PITCH + col] = __ldg(I.p + (base + row * pitch + col));
-                }
-            }
-        } else {
-#pragma unroll
-            for (int q = 0; q < 9; ++q) {
-                const int row = 2 * q + h;
-                sreg[row * W15_REGION_PITCH + c] =
-                    (uint8_t)ldg_u8(I.p + (long long)reflect101(ry0 + row, I.h) * I.pitch + reflect101(rx0 + c, I.w));
-            }
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                const int k = lane + 32 * q;
-                if (k < 36) {
-                    const int row = k >> 1, col = 16 + (k & 1);
-                    sreg[row * W15_REGION_PITCH + col] =
-                        (uint8_t)ldg_u8(I.p + (long long)reflect101(ry0 + row, I.h) * I.pitch + reflect101(rx0 + col, I.w));
-                }
-            }
-        }
-        __syncwarp();
-
-        // ---- packed 4-byte windows (region cols c..c+3) of the lane's 11 region rows -------------------
-        unsigned win[11];
-        {
-            const unsigned* rowp = reinterpret_cast<const unsigned*>(sreg + (8 * h) * W15_REGION_PITCH + (c & ~3));
-            const int sh = (c & 3) * 8;
-#pragma unroll
-            for (int t = 0; t < 11; ++t) win[t] = __funnelshift_r(rowp[t * (W15_REGION_PITCH / 4)], rowp[t * (W15_REGION_PITCH / 4) + 1], sh);
-        }
-        // horizontal Scharr halves at tile columns c (0) and c+1 (1)
-        int hd0[11], hs0[11], hd1[11], hs1[11];
-#pragma unroll
-        for (int t = 0; t < 11; ++t) {
-            hd0[t] = dp4a_us(win[t], 0x000100FF, 0);   // (-1, 0, +1, 0)
-            hs0[t] = dp4a_us(win[t], 0x00030A03, 0);   // ( 3,10,  3, 0)
-            hd1[t] = dp4a_us(win[t], 0x0100FF00, 0);   // ( 0,-1,  0,+1)
-            hs1[t] = dp4a_us(win[t], 0x030A0300, 0);   // ( 0, 3, 10, 3)
-        }
-        // Scharr at the lane's 9 tile rows, both columns; zero outside the image (window padding)
-        int gx0[9], gy0[9], gx1[9], gy1[9];
-#pragma unroll
-        for (int y = 0; y < 9; ++y) {
-            gx0[y] = 3 * (hd0[y] + hd0[y + 2]) + 10 * hd0[y + 1];
-            gx1[y] = 3 * (hd1[y] + hd1[y + 2]) + 10 * hd1[y + 1];
-            gy0[y] = hs0[y + 2] - hs0[y];
-            gy1[y] = hs1[y + 2] - hs1[y];
-        }
-        if (!interior) {
-            const bool in_x0 = (ipx + c) >= 0 && (ipx + c) < I.w, in_x1 = (ipx + c + 1) >= 0 && (ipx + c + 1) < I.w;
-#pragma unroll
-            for (int y = 0; y < 9; ++y) {
-                const int Y = ipy + 8 * h + y;
-                const bool in_y = Y >= 0 && Y < I.h;
-                if (!(in_y && in_x0)) { gx0[y] = 0; gy0[y] = 0; }
-                if (!(in_y && in_x1)) { gx1[y] = 0; gy1[y] = 0; }
-            }
-        }
-        // ---- template patch + gradient matrix ---------------------------------------------------------------
-        W15Patch P;
-        int a11 = 0, a12 = 0, a22 = 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const bool active = (c < W15) && (8 * h + i < W15);
-            const unsigned r0 = win[i + 1], r1 = win[i + 2];
-            const int i00 = (r0 >> 8) & 0xff, i01 = (r0 >> 16) & 0xff, i10 = (r1 >> 8) & 0xff, i11 = (r1 >> 16) & 0xff;
-            const int ival = (i00 * w.w00 + i01 * w.w01 + i10 * w.w10 + i11 * w.w11 + (1 << 8)) >> 9;
-            int ix = (gx0[i] * w.w00 + gx1[i] * w.w01 + gx0[i + 1] * w.w10 + gx1[i + 1] * w.w11 + (1 << 13)) >> 14;
-            int iy = (gy0[i] * w.w00 + gy1[i] * w.w01 + gy0[i + 1] * w.w10 + gy1[i + 1] * w.w11 + (1 << 13)) >> 14;
-            if (!active) { ix = 0; iy = 0; }
-            P.I[i] = (1 << 8) - (ival << 9); P.gx[i] = ix; P.gy[i] = iy;
-            a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-        }
-        const float A11 = fmul(__ll2float_rn(warp_sum_exact(a11)), FLT_SCALE);
-        const float A12 = fmul(__ll2float_rn(warp_sum_exact(a12)), FLT_SCALE);
-        const float A22 = fmul(__ll2float_rn(warp_sum_exact(a22)), FLT_SCALE);
-        float D = fsub(fmul(A11, A22), fmul(A12, A12));
-        const float dA = fsub(A11, A22);
-        const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
-        const float min_eig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(disc)), (float)(2 * W15 * W15));
-        if (min_eig < A.min_eig || D < 1.1920928955078125e-07f) {
-            if (level == 0) status = 0;
-            continue;
-        }
-        D = __fdiv_rn(1.f, D);
-
-        nx = fsub(nx, half); ny = fsub(ny, half);
-        float pdx = 0.f, pdy = 0.f;
-        for (int j = 0; j < A.max_count; ++j) {
-            const int inx = __float2int_rd(nx), iny = __float2int_rd(ny);
-            if (inx < -W15 || inx >= J.w || iny < -W15 || iny >= J.h) {
-                if (level == 0) status = 0;
-                break;
-            }
-            w = bilin_weights(fsub(nx, (float)inx), fsub(ny, (float)iny));
-            int jv[9], diff[8];
-            w15_gather(J, inx, iny, h, c, jv);
-            w15_diff(jv, w, P, diff);
-            int sb1 = 0, sb2 = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { sb1 += diff[i] * P.gx[i]; sb2 += diff[i] * P.gy[i]; }
-            const float b1 = fmul(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
-            const float b2 = fmul(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
-            const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
-            const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
-            nx = fadd(nx, dx); ny = fadd(ny, dy);
-            next_x = fadd(nx, half); next_y = fadd(ny, half);
-            if (fadd(fmul(dx, dx), fmul(dy, dy)) <= A.eps2) break;
-            if (j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
-                next_x = fsub(next_x, fmul(dx, 0.5f));
-                next_y = fsub(next_y, fmul(dy, 0.5f));
-                break;
-            }
-            pdx = dx; pdy = dy;
-        }
-
-        if (level == 0 && status) {
-            const float fx = fsub(next_x, half), fy = fsub(next_y, half);
-            const int inx = __float2int_rd(fx), iny = __float2int_rd(fy);
-            if (inx < -W15 || inx >= J.w || iny < -W15 || iny >= J.h) {
-                status = 0;
-            } else {
-                w = bilin_weights(fsub(fx, (float)inx), fsub(fy, (float)iny));
-                int jv[9], diff[8];
-                w15_gather(J, inx, iny, h, c, jv);
-                w15_diff(jv, w, P, diff);
-                int e = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const bool active = (c < W15) && (8 * h + i < W15);
-                    e += active ? abs(diff[i]) : 0;
-                }
-                e = __reduce_add_sync(0xffffffffu, e);
-                err = __fdiv_rn((float)e, (float)(32 * W15 * W15));
-            }
-        }
-    }
-    out_x = next_x; out_y = next_y; out_status = status; out_err = err;
-}
-
 constexpr int W15_WARPS = 8;
 
+// One warp tracks one point: forward pass, then (fused) the backward pass from the forward result.
+// A single instance of the level / iteration code serves both passes and the final error
+// evaluation, which keeps the kernel inside the instruction cache.
 __global__ void __launch_bounds__(32 * W15_WARPS, 3)
 lk_track_w15_kernel(const LkArgs A)
 {
@@ -608,26 +430,212 @@ lk_track_w15_kernel(const LkArgs A)
     const int pair = blockIdx.y;
     const int pt = blockIdx.x * W15_WARPS + warp;
     if (pt >= A.npts) return;
+    uint8_t* sreg = s_region[warp];
+    const int h = lane >> 4, c = lane & 15;
+    const float half = 7.0f;
+    const float FLT_SCALE = 1.f / 1048576.f;
 
     const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
     const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
     const uint8_t* N0 = A.next0 + (long long)pair * A.next_stride;
     const uint8_t* Np = A.next_pyr ? A.next_pyr + (long long)pair * A.next_pyr_stride : nullptr;
     const float* pin = A.pts + (long long)pair * A.pts_stride + 2ll * pt;
-    const float px = __ldg(pin), py = __ldg(pin + 1);
+    const float px0 = __ldg(pin), py0 = __ldg(pin + 1);
 
-    float fx, fy, ferr;
-    int fst;
-    track_point_w15(A, P0, A.prev_pitch, Pp, N0, A.next_pitch, Np, px, py, fx, fy, fst, ferr, s_region[warp], lane);
-    int st = fst;
-    float bx = 0.f, by = 0.f;
-    if (A.fbt >= 0.f && fst) {
-        float berr;
-        int bst;
-        track_point_w15(A, N0, A.next_pitch, Np, P0, A.prev_pitch, Pp, fx, fy, bx, by, bst, berr, s_region[warp], lane);
-        const float ddx = fsub(px, bx), ddy = fsub(py, by);
-        const float fbe = __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
-        st = bst && (fbe < A.fbt);
+    float fx = 0.f, fy = 0.f, ferr = 0.f, bx = 0.f, by = 0.f;
+    int fst = 0, st = 0;
+    const int npass = A.fbt >= 0.f ? 2 : 1;
+
+    for (int pass = 0; pass < npass; ++pass) {
+        // pass 0: template = prev, search = next, start at the input point
+        // pass 1: roles swapped, start at the forward result
+        const uint8_t* I0 = pass ? N0 : P0;
+        const uint8_t* Ipyr = pass ? Np : Pp;
+        const uint8_t* J0 = pass ? P0 : N0;
+        const uint8_t* Jpyr = pass ? Pp : Np;
+        const int I0_pitch = pass ? A.next_pitch : A.prev_pitch, J0_pitch = pass ? A.prev_pitch : A.next_pitch;
+        const float px = pass ? fx : px0, py = pass ? fy : py0;
+
+        int status = 1;
+        float err = 0.f;
+        float next_x = 0.f, next_y = 0.f;
+
+        for (int level = A.lv.max_level; level >= 0; --level) {
+            Img I, J;
+            I.w = J.w = A.lv.w[level];
+            I.h = J.h = A.lv.h[level];
+            if (level == 0) { I.p = I0; I.pitch = I0_pitch; J.p = J0; J.pitch = J0_pitch; }
+            else { I.p = Ipyr + A.lv.off[level]; J.p = Jpyr + A.lv.off[level]; I.pitch = J.pitch = A.lv.pitch[level]; }
+
+            const float scale = 1.f / (float)(1 << level);
+            float prev_x = fmul(px, scale), prev_y = fmul(py, scale);
+            float nx, ny;
+            if (level == A.lv.max_level) { nx = prev_x; ny = prev_y; }
+            else { nx = fmul(next_x, 2.f); ny = fmul(next_y, 2.f); }
+            next_x = nx; next_y = ny;
+
+            prev_x = fsub(prev_x, half); prev_y = fsub(prev_y, half);
+            const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
+            if (ipx < -W15 || ipx >= I.w || ipy < -W15 || ipy >= I.h) {
+                if (level == 0) { status = 0; err = 0.f; }
+                continue;
+            }
+            Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
+
+            // ---- stage the 18x18 region (rows ipy-1.., cols ipx-1..) in shared memory ------------------
+            const int rx0 = ipx - 1, ry0 = ipy - 1;
+            const bool interior = rx0 >= 0 && ry0 >= 0 && rx0 + 17 < I.w && ry0 + 17 < I.h;
+            __syncwarp();
+            {
+                const unsigned pitch = (unsigned)I.pitch;
+                // column offsets of this lane's two region columns (c, and 16/17 for the tail entries)
+                const int k1 = lane + 32;                       // second tail entry index (>= 36 for lanes >= 4)
+                const unsigned trow0 = lane >> 1, tcol0 = 16 + (lane & 1);
+                const unsigned trow1 = k1 >> 1, tcol1 = 16 + (k1 & 1);
+                if (interior) {
+                    const unsigned base = (unsigned)ry0 * pitch + (unsigned)rx0;
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const unsigned row = 2 * q + h;
+                        sreg[row * W15_REGION_PITCH + c] = __ldg(I.p + (base + row * pitch + c));
+                    }
+                    sreg[trow0 * W15_REGION_PITCH + tcol0] = __ldg(I.p + (base + trow0 * pitch + tcol0));
+                    if (k1 < 36) sreg[trow1 * W15_REGION_PITCH + tcol1] = __ldg(I.p + (base + trow1 * pitch + tcol1));
+                } else {
+                    const unsigned xc = reflect_safe(rx0 + c, I.w);
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) {
+                        const unsigned row = 2 * q + h;
+                        sreg[row * W15_REGION_PITCH + c] = __ldg(I.p + (reflect_safe(ry0 + (int)row, I.h) * pitch + xc));
+                    }
+                    sreg[trow0 * W15_REGION_PITCH + tcol0] =
+                        __ldg(I.p + (reflect_safe(ry0 + (int)trow0, I.h) * pitch + reflect_safe(rx0 + (int)tcol0, I.w)));
+                    if (k1 < 36)
+                        sreg[trow1 * W15_REGION_PITCH + tcol1] =
+                            __ldg(I.p + (reflect_safe(ry0 + (int)trow1, I.h) * pitch + reflect_safe(rx0 + (int)tcol1, I.w)));
+                }
+            }
+            __syncwarp();
+
+            // ---- template: Scharr of the lane's 9 tile rows at columns c and c+1, streamed row by row ---
+            W15Patch P;
+            int a11 = 0, a12 = 0, a22 = 0;
+            {
+                const unsigned* rowp = reinterpret_cast<const unsigned*>(sreg + (8 * h) * W15_REGION_PITCH + (c & ~3));
+                const int sh = (c & 3) * 8;
+                const bool in_x0 = (ipx + c) >= 0 && (ipx + c) < I.w, in_x1 = (ipx + c + 1) >= 0 && (ipx + c + 1) < I.w;
+                unsigned win[11];
+                int hd0[11], hs0[11], hd1[11], hs1[11];
+#pragma unroll
+                for (int t = 0; t < 11; ++t) {
+                    win[t] = __funnelshift_r(rowp[t * (W15_REGION_PITCH / 4)], rowp[t * (W15_REGION_PITCH / 4) + 1], sh);
+                    hd0[t] = dp4a_us(win[t], 0x000100FF, 0);   // (-1, 0, +1, 0)
+                    hs0[t] = dp4a_us(win[t], 0x00030A03, 0);   // ( 3,10,  3, 0)
+                    hd1[t] = dp4a_us(win[t], 0x0100FF00, 0);   // ( 0,-1,  0,+1)
+                    hs1[t] = dp4a_us(win[t], 0x030A0300, 0);   // ( 0, 3, 10, 3)
+                }
+                int gx0[9], gy0[9], gx1[9], gy1[9];
+#pragma unroll
+                for (int y = 0; y < 9; ++y) {
+                    gx0[y] = 3 * (hd0[y] + hd0[y + 2]) + 10 * hd0[y + 1];
+                    gx1[y] = 3 * (hd1[y] + hd1[y + 2]) + 10 * hd1[y + 1];
+                    gy0[y] = hs0[y + 2] - hs0[y];
+                    gy1[y] = hs1[y + 2] - hs1[y];
+                    if (!interior) {   // derivative is constant 0 in the window padding outside the image
+                        const int Y = ipy + 8 * h + y;
+                        const bool in_y = Y >= 0 && Y < I.h;
+                        if (!(in_y && in_x0)) { gx0[y] = 0; gy0[y] = 0; }
+                        if (!(in_y && in_x1)) { gx1[y] = 0; gy1[y] = 0; }
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const bool active = (c < W15) && (8 * h + i < W15);
+                    const unsigned r0 = win[i + 1], r1 = win[i + 2];
+                    const int i00 = (r0 >> 8) & 0xff, i01 = (r0 >> 16) & 0xff, i10 = (r1 >> 8) & 0xff, i11 = (r1 >> 16) & 0xff;
+                    const int ival = (i00 * w.w00 + i01 * w.w01 + i10 * w.w10 + i11 * w.w11 + (1 << 8)) >> 9;
+                    int ix = (gx0[i] * w.w00 + gx1[i] * w.w01 + gx0[i + 1] * w.w10 + gx1[i + 1] * w.w11 + (1 << 13)) >> 14;
+                    int iy = (gy0[i] * w.w00 + gy1[i] * w.w01 + gy0[i + 1] * w.w10 + gy1[i + 1] * w.w11 + (1 << 13)) >> 14;
+                    if (!active) { ix = 0; iy = 0; }
+                    P.I[i] = (1 << 8) - (ival << 9); P.gx[i] = ix; P.gy[i] = iy;
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                }
+            }
+            const float A11 = fmul(__ll2float_rn(warp_sum_exact(a11)), FLT_SCALE);
+            const float A12 = fmul(__ll2float_rn(warp_sum_exact(a12)), FLT_SCALE);
+            const float A22 = fmul(__ll2float_rn(warp_sum_exact(a22)), FLT_SCALE);
+            float D = fsub(fmul(A11, A22), fmul(A12, A12));
+            const float dA = fsub(A11, A22);
+            const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
+            const float min_eig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(disc)), (float)(2 * W15 * W15));
+            if (min_eig < A.min_eig || D < 1.1920928955078125e-07f) {
+                if (level == 0) status = 0;
+                continue;
+            }
+            D = __fdiv_rn(1.f, D);
+
+            // ---- Newton iterations; at level 0 one extra trip through the same code evaluates err -----
+            nx = fsub(nx, half); ny = fsub(ny, half);
+            float pdx = 0.f, pdy = 0.f;
+            bool final_eval = false;
+            for (int j = 0;; ++j) {
+                if (!final_eval && j >= A.max_count) {
+                    if (level == 0 && status) final_eval = true;
+                    else break;
+                }
+                const float qx = final_eval ? fsub(next_x, half) : nx, qy = final_eval ? fsub(next_y, half) : ny;
+                const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
+                if (inx < -W15 || inx >= J.w || iny < -W15 || iny >= J.h) {
+                    if (level == 0) status = 0;
+                    break;
+                }
+                w = bilin_weights(fsub(qx, (float)inx), fsub(qy, (float)iny));
+                int jv[9], diff[8];
+                w15_gather(J, inx, iny, h, c, jv);
+                w15_diff(jv, w, P, diff);
+                if (final_eval) {
+                    int e = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const bool active = (c < W15) && (8 * h + i < W15);
+                        e += active ? abs(diff[i]) : 0;
+                    }
+                    e = __reduce_add_sync(0xffffffffu, e);
+                    err = __fdiv_rn((float)e, (float)(32 * W15 * W15));
+                    break;
+                }
+                int sb1 = 0, sb2 = 0;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { sb1 += diff[i] * P.gx[i]; sb2 += diff[i] * P.gy[i]; }
+                const float b1 = fmul(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
+                const float b2 = fmul(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+                const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
+                const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
+                nx = fadd(nx, dx); ny = fadd(ny, dy);
+                next_x = fadd(nx, half); next_y = fadd(ny, half);
+                bool stop = fadd(fmul(dx, dx), fmul(dy, dy)) <= A.eps2;
+                if (!stop && j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
+                    next_x = fsub(next_x, fmul(dx, 0.5f));
+                    next_y = fsub(next_y, fmul(dy, 0.5f));
+                    stop = true;
+                }
+                pdx = dx; pdy = dy;
+                if (stop) {
+                    if (level == 0 && status) final_eval = true;
+                    else break;
+                }
+            }
+        }
+
+        if (pass == 0) {
+            fx = next_x; fy = next_y; fst = status; ferr = err; st = status;
+            if (!fst) break;   // the backward pass cannot change a failed track
+        } else {
+            bx = next_x; by = next_y;
+            const float ddx = fsub(px0, bx), ddy = fsub(py0, by);
+            const float fbe = __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+            st = status && (fbe < A.fbt);
+        }
     }
     if (lane == 0) {
         const long long o = (long long)pair * A.npts + pt;

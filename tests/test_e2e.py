@@ -1,0 +1,89 @@
+"""End-to-end parity on the reference's real clips (SURVEY.md 8(c).3 pins, regenerated into
+tests/golden/e2e_vidExample.npz by running the reference): per-frame track counts identical,
+per-frame speeds within 1 % (north_star), summary speed/residual to the printed precision.
+
+The frames are video-derived and too large to commit: tools/make_refdata.py writes them to the
+git-ignored tests/_refdata/ (which still travels to the GPU box); tests skip when it is absent.
+
+  * CPU (not gpu): velocity_b200.pipeline's frame loop driven by the ORACLE modules -- pins the
+    oracle end to end and checks the host logic of the loop.
+  * GPU (-m gpu): the same loop on the CUDA path.
+"""
+import os
+import types
+
+import numpy as np
+import pytest
+
+from util import golden
+
+REFDATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_refdata")
+CLIPS = ["IMG_4134", "IMG_4119"]
+
+
+def load_clip(name):
+    path = os.path.join(REFDATA, name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/_refdata/%s.npz not present (run tools/make_refdata.py where /root/reference exists)" % name)
+    return np.load(path)
+
+
+def check_against_pins(name, out):
+    g = golden("e2e_vidExample")
+    tab = g[name + "_table"]            # columns: image procTime tracks metric dt time dx distance speed
+    assert np.array_equal(out["tracks"], tab[:, 2].astype(int)), "per-frame track counts differ"
+    speed_ref, speed = tab[1:, 8], out["S"][1:, 8]
+    assert np.abs(speed - speed_ref).max() <= 0.01 * speed_ref.max() + 0.05      # table is printed with 1 decimal
+    summary = str(g[name + "_summary"])
+    ours = "Speed = %.2f +/- %.2f km/h\nRes = %.3f pixels" % (out["speed_mean"], out["speed_std"], out["res_mean"])
+    ref_speed = float(summary.split("=")[1].split("+/-")[0])
+    ref_std = float(summary.split("+/-")[1].split("km/h")[0])
+    ref_res = float(summary.split("Res =")[1].split("pixels")[0])
+    # north_star: recovered speed within 1 % of the reference; observed: 0.03 % (cv2 accumulates the LK
+    # normal equations in float32 SIMD lanes, this build exactly -- a rare stop-criterion flip moves a
+    # point by < 1e-2 px, which RANSAC and the pose fit then carry forward)
+    assert abs(out["speed_mean"] - ref_speed) <= 0.0025 * ref_speed, (ours, summary)
+    assert abs(out["speed_std"] - ref_std) <= 0.05 and abs(out["res_mean"] - ref_res) <= 0.01, (ours, summary)
+    return ours, summary
+
+
+def oracle_modules():
+    from oracle import klt_oracle, sfm_oracle
+    from velocity_b200.common import rms, world2image
+
+    def estimateWorldCameraPose(K, p, p3, t=np.array([0, 0, 1]), R=np.eye(3), findR=False):
+        x0 = np.concatenate((sfm_oracle.dcm_euler(R), t))
+        if findR:
+            R, t, _ = sfm_oracle.solve_pose(K.astype(float), p.astype(float), p3, x0)
+        else:
+            t, _ = sfm_oracle.solve_translation(K.astype(float), p.astype(float), p3, t)
+        proj = world2image(K, R, t, p3)
+        return t, R, rms(p - proj), proj
+
+    def fcnMSV1_t(K, P, B, vg, ii):
+        x, b0, _ = sfm_oracle.solve_last_translation(K, P, B, vg, ii)
+        return x, b0
+
+    klt = types.SimpleNamespace(KLTmain=klt_oracle.klt_main)
+    nls = types.SimpleNamespace(estimateWorldCameraPose=estimateWorldCameraPose)
+    msv = types.SimpleNamespace(fcnMSV1_t=fcnMSV1_t)
+    return klt, nls, msv
+
+
+@pytest.mark.parametrize("name", CLIPS)
+def test_e2e_oracle_reproduces_reference(name):
+    from velocity_b200 import pipeline
+
+    d = load_clip(name)
+    out = pipeline.run_speed_estimation(list(d["frames"]), d["q"], d["K"], d["times"], verbose=False, modules=oracle_modules())
+    check_against_pins(name, out)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", CLIPS)
+def test_e2e_gpu_reproduces_reference(name):
+    from velocity_b200 import pipeline
+
+    d = load_clip(name)
+    out = pipeline.run_speed_estimation(list(d["frames"]), d["q"], d["K"], d["times"], verbose=False)
+    check_against_pins(name, out)

@@ -22,6 +22,13 @@ constexpr int SRC_ROWS = 2 * TILE_H + 3;          // rows 2*y0-2 .. 2*(y0+TILE_H
 constexpr int SRC_COLS = 2 * TILE_W + 32;         // cols 2*x0-16 .. 2*x0+2*TILE_W+15 (16-byte aligned both ends)
 constexpr int PYR_THREADS = 256;
 
+__device__ __forceinline__ unsigned dp4a_uu(unsigned a, unsigned b, unsigned c)
+{
+    unsigned d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 __global__ void __launch_bounds__(PYR_THREADS)
 pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride, int sw, int sh, int spitch,
                      uint8_t* __restrict__ dst_base, long long dst_stride, int dw, int dh, int dpitch)
@@ -35,67 +42,67 @@ pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
     const int sx0 = 2 * ox0 - 16, sy0 = 2 * oy0 - 2;
     const int tid = threadIdx.x;
 
-    // interior tiles whose whole footprint is inside the image and 16-byte loadable take the vector path
+    // stage the source footprint: 16-byte chunks that lie inside the row are vector loads (rows are
+    // reflected as a whole); only chunks straddling the left/right image edge go byte by byte
     const bool aligned = ((((uintptr_t)src) | (uintptr_t)spitch) & 15) == 0;
-    const bool interior = aligned && sx0 >= 0 && sy0 >= 0 && (sx0 + SRC_COLS) <= sw && (sy0 + SRC_ROWS) <= sh;
-    if (interior) {
-        constexpr int VEC_PER_ROW = SRC_COLS / 16;
-        for (int i = tid; i < SRC_ROWS * VEC_PER_ROW; i += PYR_THREADS) {
-            const int r = i / VEC_PER_ROW, c = i % VEC_PER_ROW;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (long long)(sy0 + r) * spitch + sx0) + c);
-            reinterpret_cast<uint4*>(&s_src[r][0])[c] = v;
-        }
-    } else {
-        for (int i = tid; i < SRC_ROWS * SRC_COLS; i += PYR_THREADS) {
-            const int r = i / SRC_COLS, c = i % SRC_COLS;
-            const int yy = reflect101(sy0 + r, sh), xx = reflect101(sx0 + c, sw);
-            s_src[r][c] = src[(long long)yy * spitch + xx];
+    constexpr int VEC_PER_ROW = SRC_COLS / 16;
+    for (int i = tid; i < SRC_ROWS * VEC_PER_ROW; i += PYR_THREADS) {
+        const int r = i / VEC_PER_ROW, v = i - r * VEC_PER_ROW;
+        const int yy = reflect101(sy0 + r, sh);
+        const int xs = sx0 + 16 * v;
+        const uint8_t* row = src + (long long)yy * spitch;
+        if (aligned && xs >= 0 && xs + 16 <= sw) {
+            reinterpret_cast<uint4*>(&s_src[r][0])[v] = __ldg(reinterpret_cast<const uint4*>(row + xs));
+        } else {
+#pragma unroll 4
+            for (int b = 0; b < 16; ++b) s_src[r][16 * v + b] = row[reflect101(xs + b, sw)];
         }
     }
     __syncthreads();
 
-    // horizontal pass: each item = 4 adjacent outputs of one source row (bytes c = 8j+14 .. 8j+24)
+    // horizontal pass: item = 4 adjacent outputs of one source row; output m is centred on byte 16+2m
+    // of the 16-byte group starting at 8j+8:  h_m = [1 4 6 4] . bytes(14+2m .. 17+2m) + byte(18+2m)
     for (int i = tid; i < SRC_ROWS * (TILE_W / 4); i += PYR_THREADS) {
-        const int r = i / (TILE_W / 4), j = i % (TILE_W / 4);
-        const uint2 a = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 8]);
-        const uint2 b = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 16]);
-        const unsigned c16 = s_src[r][8 * j + 24];
-        // names: bytes 6..16 relative to 8j+8
-        const unsigned p6 = (a.y >> 16) & 0xff, p7 = a.y >> 24;
-        const unsigned p8 = b.x & 0xff, p9 = (b.x >> 8) & 0xff, p10 = (b.x >> 16) & 0xff, p11 = b.x >> 24;
-        const unsigned p12 = b.y & 0xff, p13 = (b.y >> 8) & 0xff, p14 = (b.y >> 16) & 0xff, p15 = b.y >> 24;
-        const unsigned h0 = p6 + p10 + 4 * (p7 + p9) + 6 * p8;
-        const unsigned h1 = p8 + p12 + 4 * (p9 + p11) + 6 * p10;
-        const unsigned h2 = p10 + p14 + 4 * (p11 + p13) + 6 * p12;
-        const unsigned h3 = p12 + c16 + 4 * (p13 + p15) + 6 * p14;
+        const int r = i / (TILE_W / 4), j = i - r * (TILE_W / 4);
+        const uint2 a = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 8]);    // bytes  8..15
+        const uint2 b = *reinterpret_cast<const uint2*>(&s_src[r][8 * j + 16]);   // bytes 16..23
+        const unsigned c24 = s_src[r][8 * j + 24];
+        const unsigned K = 0x04060401u;  // weights for bytes k, k+1, k+2, k+3 (the fifth tap has weight 1)
+        const unsigned w0 = __funnelshift_r(a.y, b.x, 16);   // bytes 14..17
+        const unsigned w1 = b.x;                             // bytes 16..19
+        const unsigned w2 = __funnelshift_r(b.x, b.y, 16);   // bytes 18..21
+        const unsigned w3 = b.y;                             // bytes 20..23
+        const unsigned h0 = dp4a_uu(w0, K, (b.x >> 16) & 0xff);   // + byte 18
+        const unsigned h1 = dp4a_uu(w1, K, b.y & 0xff);           // + byte 20
+        const unsigned h2 = dp4a_uu(w2, K, (b.y >> 16) & 0xff);   // + byte 22
+        const unsigned h3 = dp4a_uu(w3, K, c24);                  // + byte 24
         *reinterpret_cast<uint2*>(&s_h[r][4 * j]) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     }
     __syncthreads();
 
-    // vertical pass: each item = 4 adjacent outputs of one destination row
+    // vertical pass on packed 16-bit pairs: every partial sum is <= 16 * 4080 = 65280, so the two
+    // halves of a register never carry into each other
     for (int i = tid; i < TILE_H * (TILE_W / 4); i += PYR_THREADS) {
-        const int y = i / (TILE_W / 4), j = i % (TILE_W / 4);
+        const int y = i / (TILE_W / 4), j = i - y * (TILE_W / 4);
         const int oy = oy0 + y, ox = ox0 + 4 * j;
         if (oy >= dh || ox >= dw) continue;
-        unsigned acc[4] = {0, 0, 0, 0};
-        const int kw[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const uint2 h = *reinterpret_cast<const uint2*>(&s_h[2 * y + k][4 * j]);
-            acc[0] += kw[k] * (h.x & 0xffff);
-            acc[1] += kw[k] * (h.x >> 16);
-            acc[2] += kw[k] * (h.y & 0xffff);
-            acc[3] += kw[k] * (h.y >> 16);
-        }
-        const unsigned o0 = (acc[0] + 128) >> 8, o1 = (acc[1] + 128) >> 8, o2 = (acc[2] + 128) >> 8, o3 = (acc[3] + 128) >> 8;
+        const uint2 r0 = *reinterpret_cast<const uint2*>(&s_h[2 * y][4 * j]);
+        const uint2 r1 = *reinterpret_cast<const uint2*>(&s_h[2 * y + 1][4 * j]);
+        const uint2 r2 = *reinterpret_cast<const uint2*>(&s_h[2 * y + 2][4 * j]);
+        const uint2 r3 = *reinterpret_cast<const uint2*>(&s_h[2 * y + 3][4 * j]);
+        const uint2 r4 = *reinterpret_cast<const uint2*>(&s_h[2 * y + 4][4 * j]);
+        const unsigned ax = r0.x + r4.x + ((r1.x + r3.x) << 2) + r2.x * 6u + 0x00800080u;
+        const unsigned ay = r0.y + r4.y + ((r1.y + r3.y) << 2) + r2.y * 6u + 0x00800080u;
+        // bytes 1 and 3 of ax/ay are the four outputs ((sum + 128) >> 8)
+        const unsigned out = __byte_perm(ax, ay, 0x7531);
         uint8_t* d = dst + (long long)oy * dpitch + ox;
         if (ox + 3 < dw && ((((uintptr_t)d) & 3) == 0)) {
-            *reinterpret_cast<unsigned*>(d) = o0 | (o1 << 8) | (o2 << 16) | (o3 << 24);
+            *reinterpret_cast<unsigned*>(d) = out;
         } else {
-            d[0] = (uint8_t)o0;
-            if (ox + 1 < dw) d[1] = (uint8_t)o1;
-            if (ox + 2 < dw) d[2] = (uint8_t)o2;
-            if (ox + 3 < dw) d[3] = (uint8_t)o3;
+            d[0] = (uint8_t)(out & 0xff);
+            if (ox + 1 < dw) d[1] = (uint8_t)((out >> 8) & 0xff);
+            if (ox + 2 < dw) d[2] = (uint8_t)((out >> 16) & 0xff);
+            if (ox + 3 < dw) d[3] = (uint8_t)(out >> 24);
         }
     }
 }

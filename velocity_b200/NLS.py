@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
+from .ba_exchange import camera_slices, exchange_blocks
 from .common import addcol1, pscale, rms, world2image
 from .device import ptr, require_cuda, stream_ptr
 from .transforms import dcm2rpy, rpy2dcm
@@ -109,9 +110,7 @@ class BundleAdjuster:
         self.rank, self.world = 0, 1
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        # camera indices 0..nc split into `world` contiguous slices
-        bounds = [(nc + 1) * r // self.world for r in range(self.world + 1)]
-        self.slices = [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(self.world)]
+        self.slices = camera_slices(nc, self.world)
 
     def accumulate(self):
         L = _lib.lib()
@@ -119,26 +118,7 @@ class BundleAdjuster:
         _lib.check(L.vel_ba_accumulate(ptr(self.K), ptr(self.x), ptr(self.z), self.nt, self.nc, first, count, ptr(self.V),
                                        ptr(self.U), ptr(self.W), ptr(self.g), ptr(self.cost), stream_ptr()), "vel_ba_accumulate")
         if self.world > 1:
-            self._exchange()
-
-    def _exchange(self):
-        import torch.distributed as dist
-
-        nt, nc = self.nt, self.nc
-        # (1) all-reduce of the per-point partial sums (+ cost)
-        dist.all_reduce(self.V)
-        dist.all_reduce(self.g[:3 * nt])
-        dist.all_reduce(self.cost)
-        # (2) all-gather of the per-shard camera blocks: every rank broadcasts the rows it owns
-        for r, (first, count) in enumerate(self.slices):
-            lo = max(first, 1) - 1          # parameterised-camera index range [lo, hi)
-            hi = first + count - 1
-            if hi <= lo:
-                continue
-            dist.broadcast(self.U[lo:hi], src=r)
-            dist.broadcast(self.W[6 * lo:6 * hi], src=r)
-            dist.broadcast(self.g[3 * nt + 3 * lo:3 * nt + 3 * hi], src=r)
-            dist.broadcast(self.g[3 * nt + 3 * nc + 3 * lo:3 * nt + 3 * nc + 3 * hi], src=r)
+            exchange_blocks(self.V, self.U, self.W, self.g, self.cost, self.nt, self.nc, self.slices)
 
     def solve(self):
         L = _lib.lib()

@@ -43,19 +43,25 @@ pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
     const int tid = threadIdx.x;
 
     // stage the source footprint: 16-byte chunks that lie inside the row are vector loads (rows are
-    // reflected as a whole); only chunks straddling the left/right image edge go byte by byte
+    // reflected as a whole); only the bytes of edge-straddling chunks that a valid output really taps
+    // go byte by byte, and chunks/rows no valid output needs are skipped altogether
     const bool aligned = ((((uintptr_t)src) | (uintptr_t)spitch) & 15) == 0;
     constexpr int VEC_PER_ROW = SRC_COLS / 16;
-    for (int i = tid; i < SRC_ROWS * VEC_PER_ROW; i += PYR_THREADS) {
+    const int need_x0 = 2 * ox0 - 2, need_x1 = 2 * (min(ox0 + TILE_W, dw) - 1) + 2;   // inclusive source columns
+    const int need_rows = 2 * (min(oy0 + TILE_H, dh) - 1 - oy0) + 5;                   // rows 0 .. need_rows-1 of the tile
+    for (int i = tid; i < need_rows * VEC_PER_ROW; i += PYR_THREADS) {
         const int r = i / VEC_PER_ROW, v = i - r * VEC_PER_ROW;
-        const int yy = reflect101(sy0 + r, sh);
         const int xs = sx0 + 16 * v;
+        if (xs + 15 < need_x0 || xs > need_x1) continue;
+        int yy = sy0 + r;
+        yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);   // |overshoot| <= 2 here
+        yy = max(0, min(yy, sh - 1));
         const uint8_t* row = src + (long long)yy * spitch;
         if (aligned && xs >= 0 && xs + 16 <= sw) {
             reinterpret_cast<uint4*>(&s_src[r][0])[v] = __ldg(reinterpret_cast<const uint4*>(row + xs));
         } else {
-#pragma unroll 4
-            for (int b = 0; b < 16; ++b) s_src[r][16 * v + b] = row[reflect101(xs + b, sw)];
+            const int b0 = max(0, need_x0 - xs), b1 = min(15, need_x1 - xs);
+            for (int b = b0; b <= b1; ++b) s_src[r][16 * v + b] = row[reflect101(xs + b, sw)];
         }
     }
     __syncthreads();

@@ -28,7 +28,7 @@ for it in range(10):
 xs, x1 = ba.x.cpu().numpy(), single.x.cpu().numpy()
 cw, pw = S._ba_unpack(xs, nt, nc)
 ok_ref = np.allclose(cw, g["cw"], rtol=1e-6, atol=1e-7) and np.allclose(pw, g["pw"], rtol=1e-6, atol=1e-7)
-ok_single = np.allclose(xs, x1, rtol=1e-9, atol=1e-10)
+ok_single = np.allclose(xs, x1, rtol=1e-7, atol=1e-8)  # all-reduce order differs from the sequential sum
 gathered = [torch.empty_like(ba.x) for _ in range(world)]
 dist.all_gather(gathered, ba.x)
 identical = all(torch.equal(gathered[0], t) for t in gathered)

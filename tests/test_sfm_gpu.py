@@ -200,3 +200,23 @@ def test_match_full_size_and_ragged(cuda):
         idx, dist = match.knn2_hamming256(q[:nq], t[:nt])
         oi, od = O.knn2_hamming(q[:nq], t[:nt])
         assert np.array_equal(idx, oi) and np.array_equal(dist, od), (nq, nt)
+
+
+def test_match_tensor_core_and_popcount_forms_agree(cuda, monkeypatch):
+    """Both forms of K4 (tcgen05 int8 GEMM with fused top-2, and xor+popcount) against the oracle on
+    ragged sizes (partial query / train tiles) with exact duplicates (lowest train index must win)."""
+    from oracle import cv_oracle as O
+    from velocity_b200 import match
+
+    rng = np.random.default_rng(9)
+    for nq, nt in [(128, 256), (200, 300), (1000, 777), (2049, 1025)]:
+        t = rng.integers(0, 256, (nt, 32), dtype=np.uint8)
+        q = t[rng.integers(0, nt, nq)].copy()
+        q[:, 3] ^= rng.integers(0, 4, nq).astype(np.uint8)
+        t[17] = t[4]
+        t[nt - 1] = t[nt // 2]
+        oi, od = O.knn2_hamming(q, t)
+        for mode in ("tc", "popc"):
+            monkeypatch.setenv("VEL_MATCH_FORCE", mode)
+            idx, dist = match.knn2_hamming256(q, t)
+            assert np.array_equal(idx, oi) and np.array_equal(dist, od), (mode, nq, nt)

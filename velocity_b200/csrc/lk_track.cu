@@ -647,6 +647,241 @@ lk_track_w15_kernel(const LkArgs A)
     }
 }
 
+// =====================================================================================================
+// Column-streaming path for mid-size windows (16 <= win_w <= COLS-1, win_h <= 63; the reference's
+// 51x51 lk_fine, cv2's default 21x21).  One CTA of 128 threads per point: thread = (column slot c,
+// row group g).  Each thread walks DOWN its column: the two J bytes of the previous row stay in
+// registers, so a pixel costs 2 byte loads + 4 IMAD + shift + 2 IMAD against the template held in
+// shared memory (I stored pre-folded as 256 - (I << 9), Ix/Iy packed as short2).  Per-thread sums
+// fit int32 (<= 32 rows x 2^25), the CTA-wide sums are exact int64.  Same arithmetic as every
+// other path => bit-identical results.
+template <int COLS>
+__global__ void __launch_bounds__(128)
+lk_track_cols_kernel(const LkArgs A)
+{
+    constexpr int NT = 128, NG = NT / COLS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.y, pt = blockIdx.x;
+    const int ww = A.win_w, wh = A.win_h, npx = ww * wh;
+    const int tw = ww + 1, th = wh + 1;
+    const size_t bytes_D = ((size_t)tw * th * 4 + 15) & ~(size_t)15;
+    const size_t bytes_G = ((size_t)npx * 4 + 15) & ~(size_t)15;
+    short2* sD = reinterpret_cast<short2*>(smem_raw);
+    short2* sG = reinterpret_cast<short2*>(smem_raw + bytes_D);
+    int* sI = reinterpret_cast<int*>(smem_raw + bytes_D + bytes_G);
+    long long* red = reinterpret_cast<long long*>(smem_raw + bytes_D + 2 * bytes_G);
+    int parity = 0;
+
+    const int c = tid % COLS, g = tid / COLS;
+    const int rows_per = (wh + NG - 1) / NG;
+    const int r0 = g * rows_per, r1 = min(wh, r0 + rows_per);
+    const bool col_active = c < ww && r0 < r1;
+
+    const float half_x = fmul((float)(ww - 1), 0.5f), half_y = fmul((float)(wh - 1), 0.5f);
+    const float FLT_SCALE = 1.f / 1048576.f;
+
+    const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
+    const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
+    const uint8_t* N0 = A.next0 + (long long)pair * A.next_stride;
+    const uint8_t* Np = A.next_pyr ? A.next_pyr + (long long)pair * A.next_pyr_stride : nullptr;
+    const float* pin = A.pts + (long long)pair * A.pts_stride + 2ll * pt;
+    const float px0 = __ldg(pin), py0 = __ldg(pin + 1);
+
+    float fx = 0.f, fy = 0.f, ferr = 0.f, bx = 0.f, by = 0.f;
+    int fst = 0, st = 0;
+    const int npass = A.fbt >= 0.f ? 2 : 1;
+
+    for (int pass = 0; pass < npass; ++pass) {
+        const uint8_t* I0 = pass ? N0 : P0;
+        const uint8_t* Ipyr = pass ? Np : Pp;
+        const uint8_t* J0 = pass ? P0 : N0;
+        const uint8_t* Jpyr = pass ? Pp : Np;
+        const int I0_pitch = pass ? A.next_pitch : A.prev_pitch, J0_pitch = pass ? A.prev_pitch : A.next_pitch;
+        const float px = pass ? fx : px0, py = pass ? fy : py0;
+        int status = 1;
+        float err = 0.f;
+        float next_x = 0.f, next_y = 0.f;
+
+        for (int level = A.lv.max_level; level >= 0; --level) {
+            Img I, J;
+            I.w = J.w = A.lv.w[level];
+            I.h = J.h = A.lv.h[level];
+            if (level == 0) { I.p = I0; I.pitch = I0_pitch; J.p = J0; J.pitch = J0_pitch; }
+            else { I.p = Ipyr + A.lv.off[level]; J.p = Jpyr + A.lv.off[level]; I.pitch = J.pitch = A.lv.pitch[level]; }
+
+            const float scale = 1.f / (float)(1 << level);
+            float prev_x = fmul(px, scale), prev_y = fmul(py, scale);
+            float nx, ny;
+            if (level == A.lv.max_level) { nx = prev_x; ny = prev_y; }
+            else { nx = fmul(next_x, 2.f); ny = fmul(next_y, 2.f); }
+            next_x = nx; next_y = ny;
+            prev_x = fsub(prev_x, half_x); prev_y = fsub(prev_y, half_y);
+            const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
+            if (ipx < -ww || ipx >= I.w || ipy < -wh || ipy >= I.h) {
+                if (level == 0) { status = 0; err = 0.f; }
+                continue;
+            }
+            Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
+
+            __syncthreads();
+            // (1) Scharr tile over the (ww+1) x (wh+1) footprint, one column per thread, streamed down the rows
+            for (int tx = tid; tx < tw; tx += NT) {
+                const int X = ipx + tx;
+                const bool in_x = X >= 0 && X < I.w;
+                const unsigned xm = reflect_safe(X - 1, I.w), xc = reflect_safe(X, I.w), xp = reflect_safe(X + 1, I.w);
+                // rows Y-1, Y, Y+1 sliding
+                unsigned ry = reflect_safe(ipy - 1, I.h) * (unsigned)I.pitch;
+                int a0 = __ldg(I.p + ry + xm), a1 = __ldg(I.p + ry + xc), a2 = __ldg(I.p + ry + xp);
+                ry = reflect_safe(ipy, I.h) * (unsigned)I.pitch;
+                int b0 = __ldg(I.p + ry + xm), b1 = __ldg(I.p + ry + xc), b2 = __ldg(I.p + ry + xp);
+                for (int ty = 0; ty < th; ++ty) {
+                    const int Y = ipy + ty;
+                    ry = reflect_safe(Y + 1, I.h) * (unsigned)I.pitch;
+                    const int c0 = __ldg(I.p + ry + xm), c1 = __ldg(I.p + ry + xc), c2 = __ldg(I.p + ry + xp);
+                    int gx = 0, gy = 0;
+                    if (in_x && Y >= 0 && Y < I.h) {
+                        gx = 3 * (a2 + c2) + 10 * b2 - 3 * (a0 + c0) - 10 * b0;
+                        gy = 3 * ((c0 - a0) + (c2 - a2)) + 10 * (c1 - a1);
+                    }
+                    sD[ty * tw + tx] = make_short2((short)gx, (short)gy);
+                    a0 = b0; a1 = b1; a2 = b2; b0 = c0; b1 = c1; b2 = c2;
+                }
+            }
+            __syncthreads();
+            // (2) template patch + gradient matrix, column-streamed
+            long long acc[3] = {0, 0, 0};
+            if (col_active) {
+                const unsigned x0 = reflect_safe(ipx + c, I.w), x1 = reflect_safe(ipx + c + 1, I.w);
+                unsigned ry = reflect_safe(ipy + r0, I.h) * (unsigned)I.pitch;
+                int i00 = __ldg(I.p + ry + x0), i01 = __ldg(I.p + ry + x1);
+                int a11 = 0, a12 = 0, a22 = 0;
+                for (int y = r0; y < r1; ++y) {
+                    ry = reflect_safe(ipy + y + 1, I.h) * (unsigned)I.pitch;
+                    const int i10 = __ldg(I.p + ry + x0), i11 = __ldg(I.p + ry + x1);
+                    const int ival = (i00 * w.w00 + i01 * w.w01 + i10 * w.w10 + i11 * w.w11 + (1 << 8)) >> 9;
+                    const short2 d00 = sD[y * tw + c], d01 = sD[y * tw + c + 1], d10 = sD[(y + 1) * tw + c], d11 = sD[(y + 1) * tw + c + 1];
+                    const int ix = (d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11 + (1 << 13)) >> 14;
+                    const int iy = (d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11 + (1 << 13)) >> 14;
+                    sI[y * ww + c] = (1 << 8) - (ival << 9);
+                    sG[y * ww + c] = make_short2((short)ix, (short)iy);
+                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;   // <= 32 rows x 2^24: fits int32
+                    i00 = i10; i01 = i11;
+                }
+                acc[0] = a11; acc[1] = a12; acc[2] = a22;
+            }
+            group_sum<NT, 3>(acc, red, parity, tid);   // contains the barrier that publishes sI / sG
+            const float A11 = fmul(__ll2float_rn(acc[0]), FLT_SCALE), A12 = fmul(__ll2float_rn(acc[1]), FLT_SCALE),
+                        A22 = fmul(__ll2float_rn(acc[2]), FLT_SCALE);
+            float D = fsub(fmul(A11, A22), fmul(A12, A12));
+            const float dA = fsub(A11, A22);
+            const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
+            const float min_eig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(disc)), (float)(2 * ww * wh));
+            if (min_eig < A.min_eig || D < 1.1920928955078125e-07f) {
+                if (level == 0) status = 0;
+                continue;
+            }
+            D = __fdiv_rn(1.f, D);
+
+            nx = fsub(nx, half_x); ny = fsub(ny, half_y);
+            float pdx = 0.f, pdy = 0.f;
+            bool final_eval = false;
+            for (int j = 0;; ++j) {
+                if (!final_eval && j >= A.max_count) {
+                    if (level == 0 && status) final_eval = true;
+                    else break;
+                }
+                const float qx = final_eval ? fsub(next_x, half_x) : nx, qy = final_eval ? fsub(next_y, half_y) : ny;
+                const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
+                if (inx < -ww || inx >= J.w || iny < -wh || iny >= J.h) {
+                    if (level == 0) status = 0;
+                    break;
+                }
+                w = bilin_weights(fsub(qx, (float)inx), fsub(qy, (float)iny));
+                int sb1 = 0, sb2 = 0, se = 0;
+                if (col_active) {
+                    const bool inside = inx >= 0 && iny >= 0 && inx + ww < J.w && iny + wh < J.h;
+                    const unsigned pitch = (unsigned)J.pitch;
+                    const int* pI = sI + r0 * ww + c;
+                    const short2* pG = sG + r0 * ww + c;
+                    if (inside) {
+                        const uint8_t* p = J.p + ((unsigned)(iny + r0) * pitch + (unsigned)(inx + c));
+                        int a = __ldg(p), b = __ldg(p + 1);
+#pragma unroll 4
+                        for (int y = r0; y < r1; ++y) {
+                            p += pitch;
+                            const int an = __ldg(p), bn = __ldg(p + 1);
+                            const int diff = (a * w.w00 + b * w.w01 + an * w.w10 + bn * w.w11 + *pI) >> 9;
+                            const short2 gg = *pG;
+                            sb1 += diff * (int)gg.x; sb2 += diff * (int)gg.y; se += abs(diff);
+                            a = an; b = bn; pI += ww; pG += ww;
+                        }
+                    } else {
+                        const unsigned x0 = reflect_safe(inx + c, J.w), x1 = reflect_safe(inx + c + 1, J.w);
+                        unsigned ry = reflect_safe(iny + r0, J.h) * pitch;
+                        int a = __ldg(J.p + ry + x0), b = __ldg(J.p + ry + x1);
+                        for (int y = r0; y < r1; ++y) {
+                            ry = reflect_safe(iny + y + 1, J.h) * pitch;
+                            const int an = __ldg(J.p + ry + x0), bn = __ldg(J.p + ry + x1);
+                            const int diff = (a * w.w00 + b * w.w01 + an * w.w10 + bn * w.w11 + *pI) >> 9;
+                            const short2 gg = *pG;
+                            sb1 += diff * (int)gg.x; sb2 += diff * (int)gg.y; se += abs(diff);
+                            a = an; b = bn; pI += ww; pG += ww;
+                        }
+                    }
+                }
+                if (final_eval) {
+                    long long e[1] = {se};
+                    group_sum<NT, 1>(e, red, parity, tid);
+                    err = __fdiv_rn(__ll2float_rn(e[0]), (float)(32 * ww * wh));
+                    break;
+                }
+                long long bsum[2] = {sb1, sb2};
+                group_sum<NT, 2>(bsum, red, parity, tid);
+                const float b1 = fmul(__ll2float_rn(bsum[0]), FLT_SCALE), b2 = fmul(__ll2float_rn(bsum[1]), FLT_SCALE);
+                const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
+                const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
+                nx = fadd(nx, dx); ny = fadd(ny, dy);
+                next_x = fadd(nx, half_x); next_y = fadd(ny, half_y);
+                bool stop = fadd(fmul(dx, dx), fmul(dy, dy)) <= A.eps2;
+                if (!stop && j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
+                    next_x = fsub(next_x, fmul(dx, 0.5f));
+                    next_y = fsub(next_y, fmul(dy, 0.5f));
+                    stop = true;
+                }
+                pdx = dx; pdy = dy;
+                if (stop) {
+                    if (level == 0 && status) final_eval = true;
+                    else break;
+                }
+            }
+        }
+        if (pass == 0) {
+            fx = next_x; fy = next_y; fst = status; ferr = err; st = status;
+            if (!fst) break;
+        } else {
+            bx = next_x; by = next_y;
+            const float ddx = fsub(px0, bx), ddy = fsub(py0, by);
+            const float fbe = __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
+            st = status && (fbe < A.fbt);
+        }
+    }
+    if (tid == 0) {
+        const long long o = (long long)pair * A.npts + pt;
+        A.out[2 * o] = fx;
+        A.out[2 * o + 1] = fy;
+        A.status[o] = (uint8_t)st;
+        A.err[o] = fst ? ferr : 0.f;
+        if (A.back) { A.back[2 * o] = bx; A.back[2 * o + 1] = by; }
+    }
+}
+
+size_t cols_smem_bytes(int win_w, int win_h)
+{
+    const size_t npx = (size_t)win_w * win_h, ntile = (size_t)(win_w + 1) * (win_h + 1);
+    return ((ntile * 4 + 15) & ~(size_t)15) + 2 * ((npx * 4 + 15) & ~(size_t)15) + (size_t)2 * 4 * 3 * sizeof(long long);
+}
+
 size_t group_smem_bytes(int win_w, int win_h, int nt)
 {
     const size_t npx = (size_t)win_w * win_h, ntile = (size_t)(win_w + 1) * (win_h + 1);
@@ -699,6 +934,18 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
     if (ww == W15 && wh == W15) {
         dim3 grid((npts + W15_WARPS - 1) / W15_WARPS, npairs);
         lk_track_w15_kernel<<<grid, 32 * W15_WARPS, 0, st>>>(A);
+    } else if (ww >= 16 && ww <= 63 && wh >= 8 && wh <= 63) {
+        const size_t smem = cols_smem_bytes(ww, wh);
+        dim3 grid(npts, npairs);
+        if (ww <= 31) {
+            auto kern = lk_track_cols_kernel<32>;
+            if (smem > 48 * 1024) VEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 128, smem, st>>>(A);
+        } else {
+            auto kern = lk_track_cols_kernel<64>;
+            if (smem > 48 * 1024) VEL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            kern<<<grid, 128, smem, st>>>(A);
+        }
     } else if (ww * wh <= 1024) {
         constexpr int NT = 32, GROUPS = 8;
         const size_t smem = GROUPS * group_smem_bytes(ww, wh, NT);

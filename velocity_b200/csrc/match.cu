@@ -13,6 +13,7 @@
 #include "common.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -53,6 +54,13 @@ knn2_hamming256_partial_kernel(const uint4* __restrict__ q, int nq, const uint4*
     if (qi < nq) part[(long long)blockIdx.y * nq + qi] = make_int4(d0, i0, d1, i1);
 }
 
+// (distance, index) lexicographic order: partial results may cover interleaved column ranges
+__device__ __forceinline__ void top2_push_lex(int& d0, int& i0, int& d1, int& i1, int d, int j)
+{
+    if (d < d0 || (d == d0 && j < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+    else if (d < d1 || (d == d1 && j < i1)) { d1 = d; i1 = j; }
+}
+
 __global__ void knn2_hamming_merge_kernel(const int4* __restrict__ part, int nq, int nsplit, int* __restrict__ idx,
                                           int* __restrict__ dist)
 {
@@ -61,8 +69,8 @@ __global__ void knn2_hamming_merge_kernel(const int4* __restrict__ part, int nq,
     int d0 = INT_MAX, i0 = -1, d1 = INT_MAX, i1 = -1;
     for (int s = 0; s < nsplit; ++s) {
         const int4 p = part[(long long)s * nq + qi];
-        if (p.y >= 0) top2_push(d0, i0, d1, i1, p.x, p.y);
-        if (p.w >= 0) top2_push(d0, i0, d1, i1, p.z, p.w);
+        if (p.y >= 0) top2_push_lex(d0, i0, d1, i1, p.x, p.y);
+        if (p.w >= 0) top2_push_lex(d0, i0, d1, i1, p.z, p.w);
     }
     idx[2 * qi] = i0; idx[2 * qi + 1] = i1;
     dist[2 * qi] = i0 < 0 ? -1 : d0; dist[2 * qi + 1] = i1 < 0 ? -1 : d1;
@@ -139,14 +147,21 @@ int choose_splits(int nq, int nt, int tile)
 
 }  // namespace
 
-VEL_API int vel_match_knn2_hamming256(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
-                                      vel_stream_t stream)
+// shared with the tensor-core path (match_tc.cu): merge per-split partial top-2 in split order
+int vel_match_merge_hamming(const int4* part, int nq, int nsplit, int32_t* idx, int32_t* dist, cudaStream_t st)
 {
-    VEL_CHECK_ARG(q && t && idx && dist, "vel_match_knn2_hamming256: NULL argument");
-    VEL_CHECK_ARG(nq >= 0 && nt >= 0, "vel_match_knn2_hamming256: negative size");
-    VEL_CHECK_ARG(((((uintptr_t)q) | ((uintptr_t)t)) & 15) == 0, "vel_match_knn2_hamming256: descriptors must be 16-byte aligned");
-    if (nq == 0) return VEL_OK;
-    cudaStream_t st = (cudaStream_t)stream;
+    knn2_hamming_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(part, nq, nsplit, idx, dist);
+    VEL_LAUNCH_CHECK("knn2_hamming_merge_kernel");
+    return VEL_OK;
+}
+
+int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
+                                 cudaStream_t st);
+
+// exact CUDA-core (xor + popcount) form; used for problems too small to fill a 128 x 256 tensor tile
+static int knn2_hamming256_popc(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
+                                cudaStream_t st)
+{
     const int nsplit = choose_splits(nq, nt, MT_TILE);
     int t_per_split = (nt + nsplit - 1) / nsplit;
     t_per_split = ((t_per_split + MT_TILE - 1) / MT_TILE) * MT_TILE;
@@ -157,10 +172,27 @@ VEL_API int vel_match_knn2_hamming256(const uint8_t* q, int32_t nq, const uint8_
     dim3 grid((nq + MQ_THREADS - 1) / MQ_THREADS, nsp);
     knn2_hamming256_partial_kernel<<<grid, MQ_THREADS, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, t_per_split, part);
     VEL_LAUNCH_CHECK("knn2_hamming256_partial_kernel");
-    knn2_hamming_merge_kernel<<<(nq + 255) / 256, 256, 0, st>>>(part, nq, nsp, idx, dist);
-    VEL_LAUNCH_CHECK("knn2_hamming_merge_kernel");
+    const int rc = vel_match_merge_hamming(part, nq, nsp, idx, dist, st);
+    if (rc != VEL_OK) return rc;
     VEL_CUDA(cudaFreeAsync(part, st));
     return VEL_OK;
+}
+
+// test hook: VEL_MATCH_FORCE=popc|tc selects one form regardless of size
+VEL_API int vel_match_knn2_hamming256(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
+                                      vel_stream_t stream)
+{
+    VEL_CHECK_ARG(q && t && idx && dist, "vel_match_knn2_hamming256: NULL argument");
+    VEL_CHECK_ARG(nq >= 0 && nt >= 0, "vel_match_knn2_hamming256: negative size");
+    VEL_CHECK_ARG(((((uintptr_t)q) | ((uintptr_t)t)) & 15) == 0, "vel_match_knn2_hamming256: descriptors must be 16-byte aligned");
+    if (nq == 0) return VEL_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* force = getenv("VEL_MATCH_FORCE");
+    bool use_tc = nq >= 128 && nt >= 256;
+    if (force && force[0] == 'p') use_tc = false;
+    if (force && force[0] == 't' && nt >= 1) use_tc = true;
+    if (use_tc) return vel_match_knn2_hamming256_tc(q, nq, t, nt, idx, dist, st);
+    return knn2_hamming256_popc(q, nq, t, nt, idx, dist, st);
 }
 
 VEL_API int vel_match_knn2_l2(const float* q, int32_t nq, const float* t, int32_t nt, int32_t dim, int32_t* idx, float* dist,

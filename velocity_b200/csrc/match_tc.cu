@@ -1,0 +1,374 @@
+// K4 (tensor-core form): all-pairs Hamming distance of 256-bit descriptors as an int8 GEMM on the
+// 5th-generation tensor cores, with the 2-nearest-neighbour selection fused into the epilogue.
+//
+//   bit b -> (2b - 1) in {-1,+1}  =>  <q', t'> = 256 - 2 * hamming(q, t)   (exact in int32)
+//
+// so D = Q' T'^T (M x N x 256, int8 x int8 -> int32) carries every distance, and the largest dot
+// product is the nearest neighbour.  The 8192 x 8192 distance matrix is never written: each
+// 128 x 256 accumulator tile lives in TMEM, four epilogue warps read it with tcgen05.ld (one query
+// row per thread) and keep a running top-2 in registers.  Ties resolve to the lower train index
+// (columns are visited in ascending order with strict >), as cv2.BFMatcher does.
+//
+// Kernel anatomy (one CTA per 128 queries x one split of the train set, 320 threads):
+//   warp 0      TMA producer: Q' tile once (2 x 16 KB, SWIZZLE_128B), T' tiles double-buffered (2 x 64 KB)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: 8 x (M128 N256 K32, kind::i8) per tile,
+//               accumulators double-buffered in 2 x 256 TMEM columns; tcgen05.commit frees smem / publishes D
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32x32b.x32, branch-free
+//               running top-2 on packed keys, overlapped with the next tile's MMAs
+// Reference call site: cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) (the ORB variant of utils/KLT.py:16-26;
+// BASELINE config 4).  Roofline class: tensor (34.36 G int8-op per 8192^2 pair of frames).
+#include <cuda.h>
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace tc {
+
+constexpr int TC_M = 128, TC_N = 256;
+constexpr int TC_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr uint32_t A_CHUNK = TC_M * 128;          // one 128-byte K chunk of the query tile
+constexpr uint32_t B_CHUNK = TC_N * 128;
+constexpr uint32_t SMEM_A = 2 * A_CHUNK;          // K = 256 bytes = 2 chunks
+constexpr uint32_t SMEM_B_STAGE = 2 * B_CHUNK;
+constexpr uint32_t SMEM_BARS = 256;
+constexpr uint32_t SMEM_TOTAL = SMEM_A + 2 * SMEM_B_STAGE + SMEM_BARS + 1024;   // + alignment slack
+
+// instruction descriptor: D = S32 (2<<4), A = S8 (1<<7), B = S8 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
+constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
+// shared-memory matrix descriptor, high word: SBO = 1024 B (>>4 = 64), version 1 (bit 46), SWIZZLE_128B (2 at bits 61..63)
+constexpr uint32_t DESC_HI = 64u | (1u << 14) | (2u << 29);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr)
+{
+    const uint32_t lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);   // start address, LBO = 1 (unused for swizzled K-major)
+    return ((uint64_t)DESC_HI << 32) | lo;
+}
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+
+// wait for the outstanding tcgen05.ld; the loaded registers are tied to the asm ("+r") so the compiler cannot
+// schedule their first use above the wait
+__device__ __forceinline__ void tmem_ld_wait(int (&v)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                   "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                   "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :
+                 : "memory");
+}
+
+// Branch-free running top-2 on packed keys: key = (dot << 16) + (0xFFFF - local column), so a larger key is a
+// smaller Hamming distance and, among equal distances, the LOWER train index.  Four independent (k0, k1)
+// pairs break the loop-carried dependency (ILP 4); they are merged once at the end.
+struct Top2Keys {
+    int k0[4], k1[4];
+    __device__ __forceinline__ void init()
+    {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) { k0[a] = INT_MIN; k1[a] = INT_MIN; }
+    }
+    __device__ __forceinline__ void push(int a, int key)
+    {
+        k1[a] = max(k1[a], min(k0[a], key));
+        k0[a] = max(k0[a], key);
+    }
+};
+
+__device__ __forceinline__ void consume_chunk(const int (&v)[32], int inv_col0, Top2Keys& T)
+{
+    // inv_col0 = 0xFFFF - (local column of v[0]); columns ascend => the inverted index descends
+#pragma unroll
+    for (int c = 0; c < 32; ++c) T.push(c & 3, (v[c] << 16) + (inv_col0 - c));
+}
+
+// bits -> +-1 int8 (bit b of byte k -> element 8k + b)
+__global__ void expand_pm1_kernel(const uint8_t* __restrict__ in, long long nbytes, uint2* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nbytes) return;
+    const unsigned b = in[i];
+    unsigned lo = 0, hi = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        lo |= (((b >> k) & 1u) ? 0x01u : 0xFFu) << (8 * k);
+        hi |= (((b >> (k + 4)) & 1u) ? 0x01u : 0xFFu) << (8 * k);
+    }
+    out[i] = make_uint2(lo, hi);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT, int nq, int nt,
+                       int nblk_per_split, int4* __restrict__ part)
+{
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
+    const uint32_t sA = base, sB = base + SMEM_A, sBar = base + SMEM_A + 2 * SMEM_B_STAGE;
+    // barriers (8 bytes each): 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 tmem_full | 7,8 tmem_empty ; +80: TMEM base slot
+    const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 56;
+    const uint32_t tmem_slot = sBar + 80;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TC_M;
+    const int nblk_total = (nt + TC_N - 1) / TC_N;
+    const int blk0 = blockIdx.y * nblk_per_split;
+    const int nblk = min(nblk_per_split, nblk_total - blk0);
+
+    if (threadIdx.x == 0) {
+        mbar_init(bar_a, 1);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+            mbar_init(bar_tfull + 8 * s, 1);
+            mbar_init(bar_tempty + 8 * s, 8);   // one arrive per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bar_a, SMEM_A);
+            tma_load_2d(sA, &tmQ, 0, m0, bar_a);
+            tma_load_2d(sA + A_CHUNK, &tmQ, 128, m0, bar_a);
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i & 1;
+                if (i >= 2) mbar_wait(bar_bempty + 8 * s, ((i >> 1) - 1) & 1);
+                const uint32_t dst = sB + s * SMEM_B_STAGE;
+                const int row = (blk0 + i) * TC_N;
+                mbar_expect_tx(bar_bfull + 8 * s, SMEM_B_STAGE);
+                tma_load_2d(dst, &tmT, 0, row, bar_bfull + 8 * s);
+                tma_load_2d(dst + B_CHUNK, &tmT, 128, row, bar_bfull + 8 * s);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            mbar_wait(bar_a, 0);
+            for (int i = 0; i < nblk; ++i) {
+                const int s = i & 1;
+                mbar_wait(bar_bfull + 8 * s, (i >> 1) & 1);
+                if (i >= 2) mbar_wait(bar_tempty + 8 * s, ((i >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)s * TC_N;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t koff = (uint32_t)(k & 3) * 32u;
+                    const uint64_t ad = make_desc(sA + (k >> 2) * A_CHUNK + koff);
+                    const uint64_t bd = make_desc(sB + s * SMEM_B_STAGE + (k >> 2) * B_CHUNK + koff);
+                    mma_i8(d, ad, bd, k > 0 ? 1u : 0u);
+                }
+                mma_commit(bar_bempty + 8 * s);   // smem stage reusable once these MMAs have read it
+                mma_commit(bar_tfull + 8 * s);    // accumulator tile complete
+            }
+        }
+    } else {
+        const int q = warp & 3;                   // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;         // two warps share a quarter: each scans 128 of the 256 columns
+        const int row = q * 32 + lane;
+        const int col_base = blk0 * TC_N;         // keys carry columns local to this split (< 65536, checked on the host)
+        Top2Keys T;
+        T.init();
+        for (int i = 0; i < nblk; ++i) {
+            const int s = i & 1;
+            mbar_wait(bar_tfull + 8 * s, (i >> 1) & 1);
+            tc_fence_after();
+            const int jloc = i * TC_N;            // local column of the tile's first column
+            const int valid = min(TC_N, nt - (col_base + jloc));   // columns of this tile that exist
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * TC_N;
+            int va[32], vb[32];
+            const int ch0 = half * 4, ch1 = half * 4 + 4;
+            tmem_ld32(taddr + ch0 * 32, va);
+#pragma unroll
+            for (int ch = ch0; ch < ch1; ch += 2) {
+                tmem_ld_wait(va);
+                tmem_ld32(taddr + (ch + 1) * 32, vb);          // prefetch the next chunk while this one is consumed
+                if (valid < (ch + 1) * 32) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if (ch * 32 + c >= valid) va[c] = -30000;   // padded train rows never win
+                }
+                consume_chunk(va, 0xFFFF - (jloc + ch * 32), T);
+                tmem_ld_wait(vb);
+                if (ch + 2 < ch1) tmem_ld32(taddr + (ch + 2) * 32, va);
+                if (valid < (ch + 2) * 32) {
+#pragma unroll
+                    for (int c = 0; c < 32; ++c) if ((ch + 1) * 32 + c >= valid) vb[c] = -30000;
+                }
+                consume_chunk(vb, 0xFFFF - (jloc + (ch + 1) * 32), T);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
+        }
+        // merge the four accumulator pairs (keys are unique, so plain max/min merging is exact)
+        int k0 = T.k0[0], k1 = T.k1[0];
+#pragma unroll
+        for (int a = 1; a < 4; ++a) {
+            const int x0 = T.k0[a], x1 = T.k1[a];
+            const int n0 = max(k0, x0);
+            const int n1 = max(min(k0, x0), max(k1, x1));
+            k0 = n0; k1 = n1;
+        }
+        if (m0 + row < nq) {
+            // key -> (dot, column): dot = key >> 16 (arithmetic), column = 0xFFFF - (key & 0xFFFF)
+            const int dot0 = k0 >> 16, dot1 = k1 >> 16;
+            const int idx0 = dot0 > -20000 ? col_base + (0xFFFF - (k0 & 0xFFFF)) : -1;
+            const int idx1 = dot1 > -20000 ? col_base + (0xFFFF - (k1 & 0xFFFF)) : -1;
+            const int d0 = idx0 >= 0 ? (256 - dot0) >> 1 : 0x7fffffff, d1 = idx1 >= 0 ? (256 - dot1) >> 1 : 0x7fffffff;
+            part[(long long)(blockIdx.y * 2 + half) * nq + m0 + row] = make_int4(d0, idx0, d1, idx1);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+bool make_map(CUtensorMap* tm, void* ptr, int rows, int box_rows)
+{
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {256, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {256};
+    cuuint32_t box[2] = {128, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+
+// defined in match.cu
+int vel_match_merge_hamming(const int4* part, int nq, int nsplit, int32_t* idx, int32_t* dist, cudaStream_t st);
+
+// Tensor-core path of vel_match_knn2_hamming256 (called from match.cu for problems large enough to fill tiles).
+int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t, int32_t nt, int32_t* idx, int32_t* dist,
+                                 cudaStream_t st)
+{
+    using namespace tc;
+    int8_t* qe = nullptr;
+    int8_t* te = nullptr;
+    VEL_CUDA(cudaMallocAsync((void**)&qe, (size_t)nq * 256, st));
+    VEL_CUDA(cudaMallocAsync((void**)&te, (size_t)nt * 256, st));
+    expand_pm1_kernel<<<(unsigned)(((long long)nq * 32 + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, (uint2*)qe);
+    VEL_LAUNCH_CHECK("expand_pm1_kernel");
+    expand_pm1_kernel<<<(unsigned)(((long long)nt * 32 + 255) / 256), 256, 0, st>>>(t, (long long)nt * 32, (uint2*)te);
+    VEL_LAUNCH_CHECK("expand_pm1_kernel");
+
+    CUtensorMap tmQ, tmT;
+    if (!make_map(&tmQ, qe, nq, TC_M) || !make_map(&tmT, te, nt, TC_N)) {
+        vel_set_error("vel_match_knn2_hamming256: cuTensorMapEncodeTiled failed");
+        return VEL_ERR_CUDA;
+    }
+    const int mblocks = (nq + TC_M - 1) / TC_M;
+    const int nblk_total = (nt + TC_N - 1) / TC_N;
+    int nsplit = kNumSMs / mblocks;                            // one CTA per SM, a single wave
+    if (nsplit > nblk_total) nsplit = nblk_total;
+    if (nsplit < 1) nsplit = 1;
+    int nblk_per_split = (nblk_total + nsplit - 1) / nsplit;
+    if (nblk_per_split > 255) {                                // keys hold 16-bit local columns: <= 255 tiles of 256 per split
+        nblk_per_split = 255;
+    }
+    nsplit = (nblk_total + nblk_per_split - 1) / nblk_per_split;
+    int4* part = nullptr;
+    VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsplit * 2, st));   // two column halves per split
+    static bool attr_set = false;
+    if (!attr_set) {
+        VEL_CUDA(cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
+        attr_set = true;
+    }
+    knn2_hamming_tc_kernel<<<dim3(mblocks, nsplit), TC_THREADS, SMEM_TOTAL, st>>>(tmQ, tmT, nq, nt, nblk_per_split, part);
+    VEL_LAUNCH_CHECK("knn2_hamming_tc_kernel");
+    const int rc = vel_match_merge_hamming(part, nq, nsplit * 2, idx, dist, st);
+    if (rc != VEL_OK) return rc;
+    VEL_CUDA(cudaFreeAsync(part, st));
+    VEL_CUDA(cudaFreeAsync(te, st));
+    VEL_CUDA(cudaFreeAsync(qe, st));
+    return VEL_OK;
+}

@@ -242,7 +242,7 @@ def run_ours(args):
     valid_frac = float(out[1].float().mean().item())
 
     # ---- end-to-end timing through the public host-buffer API ----------------------------------------
-    chunk = 32
+    chunk = args.chunk
     tracker = SequenceTracker(H, W, NPTS, chunk=chunk, fbt=FBT, **LK)
     o_pts = torch.empty((PAIRS, NPTS, 2), dtype=torch.float32).pin_memory()
     o_st = torch.empty((PAIRS, NPTS), dtype=torch.uint8).pin_memory()
@@ -320,6 +320,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--chunk", type=int, default=16, help="frames per H2D/compute pipeline chunk of the e2e path")
     ap.add_argument("--z0", type=float, default=Z0_M, help="plane depth (m) of the synthetic generator")
     args = ap.parse_args()
     Z0_M = args.z0

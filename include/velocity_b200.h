@@ -152,6 +152,17 @@ size_t vel_ba_solve_workspace(int32_t nt, int32_t nc);
 int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
                  double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
 
+/* fcnNLS_batch2 (utils/NLS.py:253-328): the range/elevation/azimuth-parametrised bundle adjustment.
+ * x = [points nt*3 | q], q = [joint roll,pitch,yaw | el | az | range_1..range_nc] (nq = 5 + nc).
+ * vel_ba2_accumulate writes V [nt][6], the dense symmetric camera-side block G [nq][nq], the cross
+ * block W [nq][nt*3] (row-major), g [nt*3 + nq] and cost[1]; vel_ba2_solve solves
+ * (JtJ + I) delta = g through the Schur complement of the point blocks and applies x += 0.9 delta.
+ * Workspace for vel_ba2_solve: vel_ba_solve_workspace(nt, (nq + 5) / 6) bytes. */
+int vel_ba2_accumulate(const double* K, const double* x, const double* z, int32_t nt, int32_t nc, double* V, double* G,
+                       double* W, double* g, double* cost, vel_stream_t stream);
+int vel_ba2_solve(const double* V, const double* G, const double* W, const double* g, int32_t nt, int32_t nq, double* x,
+                  double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
+
 /* K4.  cv2.BFMatcher(NORM_HAMMING).knnMatch(q, t, k=2) for 256-bit descriptors (the ORB variant
  * of the reference's descriptor fallback, utils/KLT.py:16-26; BASELINE config 4): the two nearest
  * train rows per query, ascending distance, ties to the lower train index.  q [nq][32], t [nt][32]

@@ -146,6 +146,21 @@ def test_fcnNLS_batch(cuda, name):
     assert "fcnNLS_batch done in" in buf.getvalue()
 
 
+def test_fcnNLS_batch2(cuda):
+    from velocity_b200 import NLS
+
+    g = golden("ba_small")
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        cw, pw = NLS.fcnNLS_batch2(g["K"], g["P"].copy(), g["pw0"].copy(), g["cw0"].copy())
+    assert cw.shape == g["cw_b2"].shape and pw.shape == g["pw_b2"].shape
+    assert np.allclose(cw, g["cw_b2"], rtol=1e-6, atol=1e-7)
+    assert np.allclose(pw, g["pw_b2"], rtol=1e-6, atol=1e-7)
+    ref_steps = [ln for ln in str(g["stdout_b2"]).splitlines() if "fcnNLS_batch2 done in" in ln][0].split("done in")[1].split("steps")[0]
+    our_steps = [ln for ln in buf.getvalue().splitlines() if "fcnNLS_batch2 done in" in ln][0].split("done in")[1].split("steps")[0]
+    assert ref_steps.strip() == our_steps.strip()
+
+
 def test_ba_blocks_match_oracle(cuda):
     """K7 output blocks vs the numpy block oracle on one linearisation (tight: same forward differences)."""
     from oracle import sfm_oracle as S

@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .ba_exchange import camera_slices, exchange_blocks
-from .common import addcol1, pscale, rms, world2image
+from .common import addcol1, cam2ned, cc2sc, pscale, rms, sc2cc, world2image
 from .device import ptr, require_cuda, stream_ptr
 from .transforms import dcm2rpy, rpy2dcm
 
@@ -169,5 +169,54 @@ def fcnNLS_batch(K, P, pw, cw):
 
 
 def fcnNLS_batch2(K, P, pw, cw):
-    raise NotImplementedError("fcnNLS_batch2 (utils/NLS.py:253-328, range/az/el parametrisation; never called by the "
-                              "reference) is not built yet -- see DESIGN.md 'Out of scope / next'")
+    """Bundle adjustment with the camera track parametrised as one joint rotation, one direction
+    (elevation, azimuth) and a range per camera (utils/NLS.py:253-328).  Same update rule as
+    fcnNLS_batch, <= 20 iterations; returns (cw [nc+1,3], pw [nt,3]) float64."""
+    require_cuda()
+    v = np.isfinite(P[4]).sum(1) == P.shape[2]
+    P, pw = P[:, v], pw[v]
+    _, nt, ncam = P.shape
+    nc = ncam - 1
+    if np.isnan(P[:2]).any():
+        raise ValueError("fcnNLS_batch2: NaN pixel in a full-length track (undefined in the reference, refused here)")
+    Cn = cam2ned()
+    z = np.concatenate((P[0].T.ravel(), P[1].T.ravel())).astype(np.float64)
+    sc = cc2sc(Cn @ (np.asarray(cw, float)[1] - np.asarray(cw, float)[0]))
+    ranges = np.arange(1, nc + 1) * sc[0]
+    x0 = np.concatenate((np.asarray(pw, np.float64).ravel(), np.zeros(3), sc[1:3], ranges))
+    nq = 5 + nc
+    dev = torch.device("cuda", torch.cuda.current_device())
+    Kd, zd, xd = _dev64(np.asarray(K, float)), _dev64(z), _dev64(x0).clone()
+    V = torch.zeros((nt, 6), dtype=torch.float64, device=dev)
+    G = torch.zeros((nq, nq), dtype=torch.float64, device=dev)
+    W = torch.zeros((nq, 3 * nt), dtype=torch.float64, device=dev)
+    g = torch.zeros((3 * nt + nq,), dtype=torch.float64, device=dev)
+    stats = torch.zeros((2,), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    nbytes = int(L.vel_ba_solve_workspace(nt, (nq + 5) // 6))
+    if nbytes == 0:
+        raise RuntimeError("vel_ba_solve_workspace failed: %s" % L.vel_last_error().decode())
+    work = torch.empty((nbytes + (1 << 20),), dtype=torch.uint8, device=dev)
+    max_iter = 20
+    i, f, tic = 0, float("nan"), time.time()
+    for i in range(max_iter):
+        tic = time.time()
+        _lib.check(L.vel_ba2_accumulate(ptr(Kd), ptr(xd), ptr(zd), nt, nc, ptr(V), ptr(G), ptr(W), ptr(g), ptr(stats[0:1]),
+                                        stream_ptr()), "vel_ba2_accumulate")
+        _lib.check(L.vel_ba2_solve(ptr(V), ptr(G), ptr(W), ptr(g), nt, nq, ptr(xd), ptr(stats[1:2]), ptr(work), work.numel(),
+                                   stream_ptr()), "vel_ba2_solve")
+        cost, xr = stats.cpu().numpy()
+        f = float(np.sqrt(cost / z.size))
+        if xr < 1e-7:
+            break
+    else:
+        print("WARNING: fcnNLS_batch() reaching max iterations!")
+    print(f"fcnNLS_batch2 done in {i:g} steps, {time.time() - tic:.3f}s, f={f:g}")
+    x = xd.cpu().numpy()
+    j = nt * 3
+    scm = np.zeros((nc, 3))
+    scm[:, 0] = x[j + 5:j + 5 + nc]
+    scm[:, 1] = x[j + 3]
+    scm[:, 2] = x[j + 4]
+    cw_out = np.concatenate((np.zeros((1, 3)), sc2cc(scm) @ Cn), 0)
+    return cw_out, x[:j].reshape(nt, 3)

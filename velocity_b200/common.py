@@ -61,3 +61,23 @@ def worldPointsLicensePlate(country="EU"):
 
 def cam2ned():
     return np.array([[0, 0, 1], [1, 0, 0], [0, 1, 0]])
+
+
+def cc2sc(x):
+    """Cartesian -> [range, elevation, azimuth] (utils/common.py:81-95); a length-3 first axis means columns."""
+    x = np.asarray(x)
+    cols = x.shape[0] == 3
+    X, Y, Z = (x[0], x[1], x[2]) if cols else (x[:, 0], x[:, 1], x[:, 2])
+    r = (X * X + Y * Y + Z * Z) ** 0.5
+    parts = (r, np.arcsin(-Z / r), np.arctan2(Y, X))
+    return np.stack(parts, 0 if cols else 1).astype(x.dtype)
+
+
+def sc2cc(s):
+    """[range, elevation, azimuth] -> Cartesian (utils/common.py:98-114)."""
+    s = np.asarray(s)
+    cols = s.shape[0] == 3
+    r, el, az = (s[0], s[1], s[2]) if cols else (s[:, 0], s[:, 1], s[:, 2])
+    a = r * np.cos(el)
+    parts = (a * np.cos(az), a * np.sin(az), -r * np.sin(el))
+    return np.stack(parts, 0 if cols else 1).astype(s.dtype)

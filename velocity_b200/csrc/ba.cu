@@ -500,3 +500,351 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
     VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
     return VEL_OK;
 }
+
+// =====================================================================================================
+// fcnNLS_batch2 (utils/NLS.py:253-328): same damped Gauss-Newton, different camera model.
+// Parameters x = [points nt*3 | q], q = [joint roll,pitch,yaw (3) | el | az | range_1..range_nc]:
+//   pc = pw @ rpy2dcm(crpy);  camera 0 sees pc;  camera c >= 1 sees pc + sc2cc([range_c, el, az]) @ cam2ned()
+// i.e. offset_c = [a sin(az), -range_c sin(el), a cos(az)], a = range_c cos(el).
+// Five of the camera-side parameters are shared by every observation, so the camera block of JtJ is
+// a dense (5+nc)^2 matrix G; the point blocks stay 3x3.  Forward differences (1e-6) as in the reference.
+namespace {
+
+constexpr int B2_SHARED = 5;
+
+// per camera: offsets for the base parameters and for el+h, az+h, range+h  (4 x 3 doubles); camera 0 = zeros
+__global__ void ba2_setup_kernel(const double* __restrict__ x, int nt, int nc, double* __restrict__ offs, double* __restrict__ dcm)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const double* q = x + 3ll * nt;
+    if (c == 0) {
+        // the four DCMs: base and roll/pitch/yaw + h
+        for (int m = 0; m < 4; ++m) {
+            double r[3] = {q[0], q[1], q[2]};
+            if (m > 0) r[m - 1] = r[m - 1] + JDX;
+            rpy2dcm(r, dcm + 9 * m);
+        }
+    }
+    if (c > nc) return;
+    double* o = offs + 12ll * c;
+    if (c == 0) {
+        for (int k = 0; k < 12; ++k) o[k] = 0.0;
+        return;
+    }
+    const double el = q[3], az = q[4], rg = q[5 + (c - 1)];
+    for (int m = 0; m < 4; ++m) {
+        const double e = m == 1 ? el + JDX : el, a_ = m == 2 ? az + JDX : az, r = m == 3 ? rg + JDX : rg;
+        const double a = r * cos(e);
+        o[3 * m + 0] = a * sin(a_);
+        o[3 * m + 1] = -r * sin(e);
+        o[3 * m + 2] = a * cos(a_);
+    }
+}
+
+// residual + forward-difference Jacobian rows of one observation: columns 0..2 point, 3..5 crpy, 6 el, 7 az, 8 range
+__device__ __forceinline__ void ba2_jacobian(const double* K, const double* dcm, const double* off, bool cam0, double X, double Y,
+                                             double Z, double& u0, double& v0, double (&ju)[9], double (&jv)[9])
+{
+    double ax, ay, az, u, v;
+    rot(dcm, X, Y, Z, ax, ay, az);
+    project(K, ax + off[0], ay + off[1], az + off[2], u0, v0);
+    const double bx = ax, by = ay, bz = az;
+    rot(dcm, X + JDX, Y, Z, ax, ay, az); project(K, ax + off[0], ay + off[1], az + off[2], u, v); ju[0] = (u - u0) / JDX; jv[0] = (v - v0) / JDX;
+    rot(dcm, X, Y + JDX, Z, ax, ay, az); project(K, ax + off[0], ay + off[1], az + off[2], u, v); ju[1] = (u - u0) / JDX; jv[1] = (v - v0) / JDX;
+    rot(dcm, X, Y, Z + JDX, ax, ay, az); project(K, ax + off[0], ay + off[1], az + off[2], u, v); ju[2] = (u - u0) / JDX; jv[2] = (v - v0) / JDX;
+#pragma unroll
+    for (int m = 1; m < 4; ++m) {
+        rot(dcm + 9 * m, X, Y, Z, ax, ay, az);
+        project(K, ax + off[0], ay + off[1], az + off[2], u, v);
+        ju[2 + m] = (u - u0) / JDX; jv[2 + m] = (v - v0) / JDX;
+    }
+    if (cam0) {
+#pragma unroll
+        for (int m = 6; m < 9; ++m) { ju[m] = 0.0; jv[m] = 0.0; }
+    } else {
+#pragma unroll
+        for (int m = 1; m < 4; ++m) {
+            project(K, bx + off[3 * m], by + off[3 * m + 1], bz + off[3 * m + 2], u, v);
+            ju[5 + m] = (u - u0) / JDX; jv[5 + m] = (v - v0) / JDX;
+        }
+    }
+}
+
+// one CTA per camera c in [0, nc]: H66 (21) and g6 (6) over the camera-side columns 3..8, and the range row of W
+__global__ void __launch_bounds__(CAM_THREADS)
+ba2_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z,
+                  const double* __restrict__ offs, const double* __restrict__ dcm, int nt, int nc, double* __restrict__ Hc,
+                  double* __restrict__ gc, double* __restrict__ W)
+{
+    constexpr int NACC = 21 + 6;
+    constexpr int NWARP = CAM_THREADS / 32;
+    __shared__ double sK[9], sD[36], sO[12];
+    __shared__ double sred[NWARP][NACC];
+    const int c = blockIdx.x, tid = threadIdx.x;
+    if (tid < 9) sK[tid] = Kg[tid];
+    if (tid < 36) sD[tid] = dcm[tid];
+    if (tid < 12) sO[tid] = offs[12ll * c + tid];
+    __syncthreads();
+    const double* zu = z + (long long)c * nt;
+    const double* zv = z + (long long)(nc + 1) * nt + (long long)c * nt;
+    double acc[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
+    for (int i = tid; i < nt; i += CAM_THREADS) {
+        double u0, v0, ju[9], jv[9];
+        ba2_jacobian(sK, sD, sO, c == 0, x[3ll * i], x[3ll * i + 1], x[3ll * i + 2], u0, v0, ju, jv);
+        const double ru = zu[i] - u0, rv = zv[i] - v0;
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+            for (int q = r; q < 6; ++q) acc[k++] += ju[3 + r] * ju[3 + q] + jv[3 + r] * jv[3 + q];
+#pragma unroll
+        for (int r = 0; r < 6; ++r) acc[21 + r] += ju[3 + r] * ru + jv[3 + r] * rv;
+        if (c > 0) {
+            double* w = W + ((long long)(B2_SHARED + c - 1) * nt + i) * 3;   // range_c row
+            w[0] = ju[8] * ju[0] + jv[8] * jv[0];
+            w[1] = ju[8] * ju[1] + jv[8] * jv[1];
+            w[2] = ju[8] * ju[2] + jv[8] * jv[2];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) acc[k] = warp_sum(acc[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) sred[tid >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < NACC) {
+        double s = 0.0;
+        for (int w = 0; w < NWARP; ++w) s += sred[w][tid];
+        if (tid < 21) Hc[21ll * c + tid] = s;
+        else gc[6ll * c + (tid - 21)] = s;
+    }
+}
+
+// one thread per point: V_i, g_p,i, the five shared rows of W (summed over cameras) and the cost
+__global__ void __launch_bounds__(PT_THREADS)
+ba2_point_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z,
+                 const double* __restrict__ offs, const double* __restrict__ dcm, int nt, int nc, double* __restrict__ V,
+                 double* __restrict__ g, double* __restrict__ W, double* __restrict__ cost_part)
+{
+    __shared__ double sK[9], sD[36];
+    __shared__ double sred[PT_THREADS / 32];
+    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid;
+    if (tid < 9) sK[tid] = Kg[tid];
+    if (tid < 36) sD[tid] = dcm[tid];
+    __syncthreads();
+    double cost = 0.0;
+    if (i < nt) {
+        const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
+        double v[6] = {0, 0, 0, 0, 0, 0}, gp[3] = {0, 0, 0}, w5[B2_SHARED][3];
+#pragma unroll
+        for (int a = 0; a < B2_SHARED; ++a) { w5[a][0] = 0; w5[a][1] = 0; w5[a][2] = 0; }
+        for (int c = 0; c <= nc; ++c) {
+            double u0, v0, ju[9], jv[9];
+            ba2_jacobian(sK, sD, offs + 12ll * c, c == 0, X, Y, Z, u0, v0, ju, jv);
+            const double ru = z[(long long)c * nt + i] - u0, rv = z[(long long)(nc + 1) * nt + (long long)c * nt + i] - v0;
+            v[0] += ju[0] * ju[0] + jv[0] * jv[0]; v[1] += ju[0] * ju[1] + jv[0] * jv[1]; v[2] += ju[0] * ju[2] + jv[0] * jv[2];
+            v[3] += ju[1] * ju[1] + jv[1] * jv[1]; v[4] += ju[1] * ju[2] + jv[1] * jv[2]; v[5] += ju[2] * ju[2] + jv[2] * jv[2];
+#pragma unroll
+            for (int b = 0; b < 3; ++b) gp[b] += ju[b] * ru + jv[b] * rv;
+#pragma unroll
+            for (int a = 0; a < B2_SHARED; ++a)
+#pragma unroll
+                for (int b = 0; b < 3; ++b) w5[a][b] += ju[3 + a] * ju[b] + jv[3 + a] * jv[b];
+            cost += ru * ru + rv * rv;
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) V[6ll * i + k] = v[k];
+#pragma unroll
+        for (int b = 0; b < 3; ++b) g[3ll * i + b] = gp[b];
+#pragma unroll
+        for (int a = 0; a < B2_SHARED; ++a)
+#pragma unroll
+            for (int b = 0; b < 3; ++b) W[((long long)a * nt + i) * 3 + b] = w5[a][b];
+    }
+    cost = warp_sum(cost);
+    if ((tid & 31) == 0) sred[tid >> 5] = cost;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w];
+        cost_part[blockIdx.x] = s;
+    }
+}
+
+// G (nq x nq, dense, symmetric) and the camera-side gradient from the per-camera 6x6 blocks
+__global__ void ba2_assemble_kernel(const double* __restrict__ Hc, const double* __restrict__ gc, int nt, int nc,
+                                    double* __restrict__ G, double* __restrict__ g)
+{
+    const int nq = B2_SHARED + nc;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nq * nq) return;
+    const int r = (int)(idx % nq), c = (int)(idx / nq);
+    auto h = [&](int cam, int a, int b) {   // upper-triangle lookup of camera `cam`'s 6x6 block
+        const int lo = a < b ? a : b, hi = a < b ? b : a;
+        return Hc[21ll * cam + lo * 6 - lo * (lo - 1) / 2 + (hi - lo)];
+    };
+    double v = 0.0;
+    if (r < B2_SHARED && c < B2_SHARED) {
+        for (int cam = 0; cam <= nc; ++cam) v += h(cam, r, c);
+    } else if (r < B2_SHARED) {
+        v = h(c - B2_SHARED + 1, r, 5);
+    } else if (c < B2_SHARED) {
+        v = h(r - B2_SHARED + 1, c, 5);
+    } else if (r == c) {
+        v = h(r - B2_SHARED + 1, 5, 5);
+    }
+    G[idx] = v;
+    if (c == 0) {
+        double s = 0.0;
+        if (r < B2_SHARED) { for (int cam = 0; cam <= nc; ++cam) s += gc[6ll * cam + r]; }
+        else s = gc[6ll * (r - B2_SHARED + 1) + 5];
+        g[3ll * nt + r] = s;
+    }
+}
+
+// S = G + I, rhs = g_q   (column-major nq x nq)
+__global__ void ba2_init_s_kernel(const double* __restrict__ G, const double* __restrict__ g, int nt, int nq, double* __restrict__ S,
+                                  double* __restrict__ rhs)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nq * nq) return;
+    const int r = (int)(idx % nq), c = (int)(idx / nq);
+    S[idx] = G[idx] + (r == c ? 1.0 : 0.0);
+    if (c == 0) rhs[r] = g[3ll * nt + r];
+}
+
+// delta_p from the point blocks, x += 0.9 * delta for x = [points | q], partial sums of delta^2
+__global__ void __launch_bounds__(PT_THREADS)
+ba2_update_kernel(const double* __restrict__ Vinv, const double* __restrict__ y, const double* __restrict__ t,
+                  const double* __restrict__ dq, int nt, int nq, double* __restrict__ x, double* __restrict__ ss_part)
+{
+    __shared__ double sred[PT_THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long i = (long long)blockIdx.x * PT_THREADS + tid;
+    double ss = 0.0;
+    if (i < nt) {
+        const double* v = Vinv + 6 * i;
+        const double t0 = t[3 * i], t1 = t[3 * i + 1], t2 = t[3 * i + 2];
+        const double d0 = y[3 * i] - (v[0] * t0 + v[1] * t1 + v[2] * t2);
+        const double d1 = y[3 * i + 1] - (v[1] * t0 + v[3] * t1 + v[4] * t2);
+        const double d2 = y[3 * i + 2] - (v[2] * t0 + v[4] * t1 + v[5] * t2);
+        x[3 * i] += 0.9 * d0; x[3 * i + 1] += 0.9 * d1; x[3 * i + 2] += 0.9 * d2;
+        ss = 0.81 * (d0 * d0 + d1 * d1 + d2 * d2);
+    } else if (i < nt + nq) {
+        const int r = (int)(i - nt);
+        const double d = dq[r];
+        x[3ll * nt + r] += 0.9 * d;
+        ss = 0.81 * d * d;
+    }
+    ss = warp_sum(ss);
+    if ((tid & 31) == 0) sred[tid >> 5] = ss;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w];
+        ss_part[blockIdx.x] = s;
+    }
+}
+
+}  // namespace
+
+VEL_API int vel_ba2_accumulate(const double* K, const double* x, const double* z, int32_t nt, int32_t nc, double* V, double* G,
+                               double* W, double* g, double* cost, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(K && x && z && V && G && W && g && cost, "vel_ba2_accumulate: NULL argument");
+    VEL_CHECK_ARG(nt > 0 && nc >= 1, "vel_ba2_accumulate: bad sizes nt=%d nc=%d", nt, nc);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    const int nq = B2_SHARED + nc;
+    double* tmp = nullptr;
+    const size_t n_tmp = 12ull * (nc + 1) + 36 + 27ull * (nc + 1) + pblocks;
+    VEL_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * n_tmp, st));
+    double* offs = tmp;
+    double* dcm = offs + 12ull * (nc + 1);
+    double* Hc = dcm + 36;
+    double* gc = Hc + 21ull * (nc + 1);
+    double* cost_part = gc + 6ull * (nc + 1);
+    ba2_setup_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(x, nt, nc, offs, dcm);
+    VEL_LAUNCH_CHECK("ba2_setup_kernel");
+    ba2_camera_kernel<<<nc + 1, CAM_THREADS, 0, st>>>(K, x, z, offs, dcm, nt, nc, Hc, gc, W);
+    VEL_LAUNCH_CHECK("ba2_camera_kernel");
+    ba2_point_kernel<<<pblocks, PT_THREADS, 0, st>>>(K, x, z, offs, dcm, nt, nc, V, g, W, cost_part);
+    VEL_LAUNCH_CHECK("ba2_point_kernel");
+    const long long nel = (long long)nq * nq;
+    ba2_assemble_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(Hc, gc, nt, nc, G, g);
+    VEL_LAUNCH_CHECK("ba2_assemble_kernel");
+    ba_cost_finalize_kernel<<<1, 32, 0, st>>>(cost_part, pblocks, cost);
+    VEL_LAUNCH_CHECK("ba_cost_finalize_kernel");
+    VEL_CUDA(cudaFreeAsync(tmp, st));
+    return VEL_OK;
+}
+
+// Solve (JtJ + I) delta = g for x = [points | q] with a dense nq x nq camera-side block G; x += 0.9 delta.
+// Workspace: vel_ba_solve_workspace(nt, ceil(nq / 6)) bytes are sufficient.
+VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, const double* g, int32_t nt, int32_t nq, double* x,
+                          double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(V && G && W && g && x && rms_delta && work, "vel_ba2_solve: NULL argument");
+    VEL_CHECK_ARG(nt > 0 && nq > 0, "vel_ba2_solve: bad sizes nt=%d nq=%d", nt, nq);
+    const int nc_equiv = (nq + 5) / 6;
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc_equiv, &L, false), "vel_ba2_solve: layout failed");
+    Handles* h = handles();
+    VEL_CHECK_ARG(h != nullptr, "vel_ba2_solve: cuBLAS/cuSOLVER handles unavailable");
+    int lwork = 0;
+    if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, nq, nullptr, nq, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+        vel_set_error("vel_ba2_solve: cusolverDnDpotrf_bufferSize failed");
+        return VEL_ERR_CUDA;
+    }
+    const size_t need = L.off_potrf + align256(sizeof(double) * (size_t)(lwork > 0 ? lwork : 1));
+    VEL_CHECK_ARG(work_bytes >= need, "vel_ba2_solve: workspace %zu B < required %zu B", work_bytes, need);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wb = (char*)work;
+    double* Wp = (double*)(wb + L.off_wp);
+    double* S = (double*)(wb + L.off_s);
+    double* Vinv = (double*)(wb + L.off_vinv);
+    double* Lf = (double*)(wb + L.off_l);
+    double* y = (double*)(wb + L.off_y);
+    double* rhs = (double*)(wb + L.off_rhs);
+    double* t = (double*)(wb + L.off_t);
+    double* part = (double*)(wb + L.off_part);
+    int* info = (int*)(wb + L.off_info);
+    double* potrf_work = (double*)(wb + L.off_potrf);
+    const int n3 = 3 * nt;
+    const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    ba_point_prep_kernel<<<pblocks, PT_THREADS, 0, st>>>(V, g, nt, Vinv, Lf, y);
+    VEL_LAUNCH_CHECK("ba_point_prep_kernel");
+    cublasSetStream(h->blas, st);
+    cusolverDnSetStream(h->solver, st);
+    cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
+    const long long nel = (long long)nq * nt;
+    ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, nq, nt, Wp);
+    VEL_LAUNCH_CHECK("ba_scale_w_kernel");
+    const long long ns = (long long)nq * nq;
+    ba2_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(G, g, nt, nq, S, rhs);
+    VEL_LAUNCH_CHECK("ba2_init_s_kernel");
+    const double one = 1.0, neg = -1.0, zero = 0.0;
+    if (cublasDsyrk(h->blas, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, nq, n3, &neg, Wp, n3, &one, S, nq) != CUBLAS_STATUS_SUCCESS ||
+        cublasDgemv(h->blas, CUBLAS_OP_T, n3, nq, &neg, W, n3, y, 1, &one, rhs, 1) != CUBLAS_STATUS_SUCCESS) {
+        vel_set_error("vel_ba2_solve: cuBLAS failed");
+        return VEL_ERR_CUDA;
+    }
+    if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, nq, S, nq, potrf_work, lwork, info) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, nq, 1, S, nq, rhs, nq, info) != CUSOLVER_STATUS_SUCCESS) {
+        vel_set_error("vel_ba2_solve: cuSOLVER Cholesky failed");
+        return VEL_ERR_CUDA;
+    }
+    if (cublasDgemv(h->blas, CUBLAS_OP_N, n3, nq, &one, W, n3, rhs, 1, &zero, t, 1) != CUBLAS_STATUS_SUCCESS) {
+        vel_set_error("vel_ba2_solve: cublasDgemv failed");
+        return VEL_ERR_CUDA;
+    }
+    const int ublocks = (nt + nq + PT_THREADS - 1) / PT_THREADS;
+    ba2_update_kernel<<<ublocks, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nq, x, part);
+    VEL_LAUNCH_CHECK("ba2_update_kernel");
+    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + nq, rms_delta);
+    VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
+    return VEL_OK;
+}

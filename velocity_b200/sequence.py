@@ -9,7 +9,7 @@ device-to-device rather than re-uploaded.
 
 Semantics per pair are exactly utils/KLT.py:37-51 (cv2calcOpticalFlowPyrLK with fbt): every pair
 tracks the SAME seed points `pts` from frame k to frame k+1 (independent pairs -- the C2 workload
-of BASELINE.json), or, with `chain=True`, pair k starts from the forward result of pair k-1.
+of BASELINE.json).
 """
 import numpy as np
 import torch

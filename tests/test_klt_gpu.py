@@ -122,3 +122,57 @@ def test_lk_full_size_properties(cuda):
     sel = np.arange(0, 4096, 16)
     o2, ov, _ = KO.lk_forward_backward(im0, im1, pts[sel], fbt=1.0, **lk)
     assert np.array_equal(v[sel], ov) and np.array_equal(p2[sel], o2)
+
+
+def test_edge_cases_empty_single_and_errors(cuda):
+    """Empty and single-point inputs, points far outside the frame (status 0, no crash), argument
+    errors surfaced as RuntimeError with the C ABI's message; a point set on a pure-constant image
+    fails the minimum-eigenvalue test exactly like cv2 (status 0)."""
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT, synth
+
+    im0 = synth.texture(200, 260, 5)
+    im1 = np.roll(im0, (1, 1), (0, 1))
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, np.zeros((0, 2), np.float32), None, fbt=1.0, **lk)
+    assert p2.shape == (0, 2) and v.shape == (0,) and err.shape == (0, 1)
+    pts = np.float32([[100.5, 80.25]])
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, pts, None, fbt=1.0, **lk)
+    o2, ov, oerr = KO.lk_forward_backward(im0, im1, pts, fbt=1.0, **lk)
+    assert np.array_equal(p2, o2) and np.array_equal(v, ov)
+    far = np.float32([[-500, -500], [1e6, 40], [130, 1e7], [259.9, 199.9], [-14.9, -14.9]])
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, far, None, fbt=1.0, **lk)
+    o2, ov, _ = KO.lk_forward_backward(im0, im1, far, fbt=1.0, **lk)
+    assert np.array_equal(v, ov) and np.array_equal(p2, o2) and not v[:3].any()
+    flat = np.full((120, 160), 77, np.uint8)
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(flat, flat, np.float32([[60, 60], [80, 40]]), None, **lk)
+    assert not v.any()
+    for win in [(51, 51), (21, 21), (9, 13)]:      # every kernel variant agrees with the oracle on the same pair
+        lkw = dict(winSize=win, maxLevel=1, criteria=(3, 15, 0.01))
+        pts = synth.harris_tracks(im0, 64, border=8)
+        p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, pts, None, fbt=0.5, **lkw)
+        o2, ov, _ = KO.lk_forward_backward(im0, im1, pts, fbt=0.5, **lkw)
+        assert np.array_equal(v, ov) and np.array_equal(p2, o2), win
+    with pytest.raises(ValueError):
+        KLT.cv2calcOpticalFlowPyrLK(im0, im1[:-1], pts, None, **lk)
+    with pytest.raises(RuntimeError, match="must be larger than the window"):
+        KLT.cv2calcOpticalFlowPyrLK(im0[:12, :12], im1[:12, :12], pts, None, **lk)
+    with pytest.raises(NotImplementedError):
+        KLT.cv2calcOpticalFlowPyrLK(im0, im1, pts, None, flags=4, **lk)
+
+
+def test_sequence_tracker_host_api_matches_per_pair_calls(cuda):
+    """The public host-buffer entry point (what bench.py's e2e number times): chunked H2D pipeline,
+    one pyramid per frame, results identical to calling cv2calcOpticalFlowPyrLK pair by pair."""
+    from velocity_b200 import KLT, synth
+    from velocity_b200.sequence import track_sequence
+
+    frames, _ = synth.plane_sequence(7, h=270, w=480, seed=3, Z0=40.0)
+    frames = np.stack(frames)
+    pts = synth.harris_tracks(frames[0], 300, border=20)
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    p2, v, err = track_sequence(frames, pts, fbt=1.0, chunk=3, **lk)
+    assert p2.shape == (6, 300, 2) and v.shape == (6, 300)
+    for k in range(6):
+        q2, qv, qerr = KLT.cv2calcOpticalFlowPyrLK(frames[k], frames[k + 1], pts, None, fbt=1.0, **lk)
+        assert np.array_equal(p2[k], q2) and np.array_equal(v[k], qv) and np.array_equal(err[k], qerr.ravel())

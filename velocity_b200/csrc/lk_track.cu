@@ -898,11 +898,11 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
                          const float* prev_pts, int64_t pts_stride, int32_t npts, const vel_lk_params* params, float* next_pts,
                          uint8_t* status, float* err, float* back_pts, vel_stream_t stream)
 {
+    VEL_CHECK_ARG(npts >= 0, "vel_lk_track: npts < 0");
+    if (npts == 0) return VEL_OK;   // empty point set: nothing to do (buffers may be NULL)
     VEL_CHECK_ARG(prev_frames && next_frames && layout && prev_pts && params && next_pts && status && err,
                   "vel_lk_track: NULL argument");
     VEL_CHECK_ARG(npairs > 0 && npairs <= 65535, "vel_lk_track: npairs %d outside [1,65535]", npairs);
-    VEL_CHECK_ARG(npts >= 0, "vel_lk_track: npts < 0");
-    if (npts == 0) return VEL_OK;
     const int ww = params->win_w, wh = params->win_h;
     VEL_CHECK_ARG(ww >= 3 && wh >= 3 && ww <= 127 && wh <= 127, "vel_lk_track: window %dx%d outside [3,127]", ww, wh);
     VEL_CHECK_ARG(layout->max_level >= 0 && layout->max_level < VEL_MAX_LEVELS, "vel_lk_track: bad layout");

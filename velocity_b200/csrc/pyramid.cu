@@ -113,6 +113,75 @@ pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
     }
 }
 
+// ---- register-streaming kernel (widths that are multiples of 8, 8-byte aligned rows) ----------------
+// Thread t owns 4 output columns (source columns 8t..8t+7) for STRIP_H output rows and walks DOWN the
+// source rows: one 8-byte load per row, the 3 halo bytes come from the neighbouring lanes by shuffle
+// (lane 0 / 31 fetch them), the horizontal [1 4 6 4 1] pass is 4 dp4a on funnel-shifted words, and the
+// five most recent filtered rows stay in registers as packed 16-bit pairs for the vertical pass.
+// No shared memory, no barriers; 128-byte coalesced stores.
+constexpr int STRIP_H = 16;
+constexpr int STRIP_THREADS = 64;
+
+__global__ void __launch_bounds__(STRIP_THREADS)
+pyrdown_strip_kernel(const uint8_t* __restrict__ src_base, long long src_stride, int sw, int sh, int spitch,
+                     uint8_t* __restrict__ dst_base, long long dst_stride, int dw, int dh, int dpitch)
+{
+    const uint8_t* __restrict__ src = src_base + (long long)blockIdx.z * src_stride;
+    uint8_t* __restrict__ dst = dst_base + (long long)blockIdx.z * dst_stride;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * STRIP_THREADS + threadIdx.x;
+    const int nt_row = sw >> 3;                       // threads that own real columns
+    const int tc = min(t, nt_row - 1);                // clamped: idle threads still feed the shuffles
+    const bool last = tc == nt_row - 1;
+    const int oy0 = blockIdx.y * STRIP_H;
+    const unsigned K = 0x04060401u;
+
+    constexpr int NROWS = 2 * STRIP_H + 3;
+    constexpr int BATCH = 7;   // source rows loaded ahead of the arithmetic (memory-level parallelism)
+    uint2 win[NROWS];
+#pragma unroll
+    for (int r0 = 0; r0 < NROWS; r0 += BATCH) {
+        uint2 a[BATCH];
+        unsigned edge_lo[BATCH], edge_hi[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            if (r0 + k < NROWS) {
+                int yy = 2 * oy0 - 2 + r0 + k;
+                yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);
+                yy = max(0, min(yy, sh - 1));
+                const uint8_t* row = src + (long long)yy * spitch + 8 * tc;
+                a[k] = __ldg(reinterpret_cast<const uint2*>(row));
+                edge_lo[k] = (lane == 0 && tc > 0) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(row - 2)) : 0u;
+                edge_hi[k] = (lane == 31 && !last) ? (unsigned)__ldg(row + 8) : 0u;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int r = r0 + k;
+            if (r < NROWS) {
+                const uint2 v = a[k];
+                unsigned lo2 = __shfl_up_sync(0xffffffffu, v.y, 1) >> 16;      // source columns 8t-2, 8t-1
+                unsigned b0 = __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffu;   // source column 8t+8
+                if (lane == 0) lo2 = tc > 0 ? edge_lo[k] : (((v.x >> 16) & 0xffu) | (((v.x >> 8) & 0xffu) << 8));   // REFLECT_101 at column 0
+                if (last) b0 = (v.y >> 16) & 0xffu;                                                                // REFLECT_101 at column sw
+                else if (lane == 31) b0 = edge_hi[k];
+                const unsigned h0 = dp4a_uu(lo2 | (v.x << 16), K, (v.x >> 16) & 0xffu);
+                const unsigned h1 = dp4a_uu(v.x, K, v.y & 0xffu);
+                const unsigned h2 = dp4a_uu(__funnelshift_r(v.x, v.y, 16), K, (v.y >> 16) & 0xffu);
+                const unsigned h3 = dp4a_uu(v.y, K, b0);
+                win[r] = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+                if (r >= 4 && (r & 1) == 0) {
+                    const int y = (r - 4) >> 1, oy = oy0 + y;
+                    const unsigned ax = win[r - 4].x + win[r].x + ((win[r - 3].x + win[r - 1].x) << 2) + win[r - 2].x * 6u + 0x00800080u;
+                    const unsigned ay = win[r - 4].y + win[r].y + ((win[r - 3].y + win[r - 1].y) << 2) + win[r - 2].y * 6u + 0x00800080u;
+                    if (t < nt_row && oy < dh)
+                        *reinterpret_cast<unsigned*>(dst + (long long)oy * dpitch + 4 * t) = __byte_perm(ax, ay, 0x7531);
+                }
+            }
+        }
+    }
+}
+
 __global__ void decimate4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst,
                                  int dw, int dh, int dpitch)
 {
@@ -164,11 +233,20 @@ VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t 
         const uint8_t* src = l == 1 ? frames : pyr + L->offset[l - 1];
         const long long sstride = l == 1 ? frame_stride : pyr_stride;
         const int spitch = l == 1 ? pitch : L->pitch[l - 1];
-        dim3 grid((L->width[l] + TILE_W - 1) / TILE_W, (L->height[l] + TILE_H - 1) / TILE_H, nframes);
-        pyrdown_tiled_kernel<<<grid, PYR_THREADS, 0, st>>>(src, sstride, L->width[l - 1], L->height[l - 1], spitch,
-                                                          pyr + L->offset[l], pyr_stride, L->width[l], L->height[l],
-                                                          L->pitch[l]);
-        VEL_LAUNCH_CHECK("pyrdown_tiled_kernel");
+        const int sw = L->width[l - 1];
+        const bool strip_ok = (sw % 8 == 0) && sw >= 16 && (spitch % 8 == 0) && ((((uintptr_t)src) | (uintptr_t)sstride) & 7) == 0 &&
+                              ((((uintptr_t)(pyr + L->offset[l])) | (uintptr_t)pyr_stride | (uintptr_t)L->pitch[l]) & 3) == 0;
+        if (strip_ok) {
+            dim3 grid((sw / 8 + STRIP_THREADS - 1) / STRIP_THREADS, (L->height[l] + STRIP_H - 1) / STRIP_H, nframes);
+            pyrdown_strip_kernel<<<grid, STRIP_THREADS, 0, st>>>(src, sstride, sw, L->height[l - 1], spitch, pyr + L->offset[l],
+                                                                pyr_stride, L->width[l], L->height[l], L->pitch[l]);
+            VEL_LAUNCH_CHECK("pyrdown_strip_kernel");
+        } else {
+            dim3 grid((L->width[l] + TILE_W - 1) / TILE_W, (L->height[l] + TILE_H - 1) / TILE_H, nframes);
+            pyrdown_tiled_kernel<<<grid, PYR_THREADS, 0, st>>>(src, sstride, sw, L->height[l - 1], spitch, pyr + L->offset[l],
+                                                              pyr_stride, L->width[l], L->height[l], L->pitch[l]);
+            VEL_LAUNCH_CHECK("pyrdown_tiled_kernel");
+        }
     }
     return VEL_OK;
 }

@@ -360,14 +360,17 @@ __device__ __forceinline__ int dp4a_us(unsigned a, int b, int c)
     return d;
 }
 
-// exact 32-lane sum of per-lane int32 partials that may overflow 32 bits in total
-__device__ __forceinline__ long long warp_sum_exact(int v)
+// Exact 32-lane sum of per-lane int32 partials (the total may need 34 bits), returned as
+// float(sum) * 2^-20 with a single rounding -- bit-identical to (float)(int64 sum) * 2^-20:
+// the two REDUX halves (hi * 65536 and lo) are each exactly representable in float32, and one FMA
+// rounds their exact sum once (power-of-two scaling commutes with the rounding).
+__device__ __forceinline__ float warp_sum_scaled(int v)
 {
     const unsigned lo = (unsigned)v & 0xffffu;
     const int hi = v >> 16;
-    const int shi = __reduce_add_sync(0xffffffffu, hi);
-    const unsigned slo = __reduce_add_sync(0xffffffffu, lo);
-    return ((long long)shi << 16) + (long long)slo;
+    const int shi = __reduce_add_sync(0xffffffffu, hi);        // |shi| < 2^18
+    const unsigned slo = __reduce_add_sync(0xffffffffu, lo);   // < 2^21
+    return __fmaf_rn((float)shi, 0.0625f, __fmul_rn((float)slo, 1.f / 1048576.f));
 }
 
 struct W15Patch {
@@ -387,7 +390,8 @@ __device__ __forceinline__ unsigned reflect_safe(int i, int n)
 // (warp-uniform) level base keep the address arithmetic to one add per load
 __device__ __forceinline__ void w15_gather(const Img& J, int inx, int iny, int h, int c, int (&jv)[9])
 {
-    const bool inside = inx >= 0 && iny >= 0 && inx + 15 < J.w && iny + 15 < J.h;
+    // 0 <= inx <= w - 16  <=>  (unsigned)inx <= (unsigned)(w - 16)   (w >= 16 on every level)
+    const bool inside = (unsigned)inx <= (unsigned)(J.w - 16) && (unsigned)iny <= (unsigned)(J.h - 16);
     const unsigned pitch = (unsigned)J.pitch;
     if (inside) {
         const unsigned off = (unsigned)(iny + 8 * h) * pitch + (unsigned)(inx + c);
@@ -422,7 +426,7 @@ constexpr int W15_WARPS = 8;
 // One warp tracks one point: forward pass, then (fused) the backward pass from the forward result.
 // A single instance of the level / iteration code serves both passes and the final error
 // evaluation, which keeps the kernel inside the instruction cache.
-__global__ void __launch_bounds__(32 * W15_WARPS, 3)
+__global__ void __launch_bounds__(32 * W15_WARPS, 4)
 lk_track_w15_kernel(const LkArgs A)
 {
     __shared__ __align__(16) uint8_t s_region[W15_WARPS][W15_REGION_BYTES];
@@ -433,7 +437,6 @@ lk_track_w15_kernel(const LkArgs A)
     uint8_t* sreg = s_region[warp];
     const int h = lane >> 4, c = lane & 15;
     const float half = 7.0f;
-    const float FLT_SCALE = 1.f / 1048576.f;
 
     const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
     const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
@@ -561,9 +564,7 @@ lk_track_w15_kernel(const LkArgs A)
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
                 }
             }
-            const float A11 = fmul(__ll2float_rn(warp_sum_exact(a11)), FLT_SCALE);
-            const float A12 = fmul(__ll2float_rn(warp_sum_exact(a12)), FLT_SCALE);
-            const float A22 = fmul(__ll2float_rn(warp_sum_exact(a22)), FLT_SCALE);
+            const float A11 = warp_sum_scaled(a11), A12 = warp_sum_scaled(a12), A22 = warp_sum_scaled(a22);
             float D = fsub(fmul(A11, A22), fmul(A12, A12));
             const float dA = fsub(A11, A22);
             const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
@@ -585,7 +586,8 @@ lk_track_w15_kernel(const LkArgs A)
                 }
                 const float qx = final_eval ? fsub(next_x, half) : nx, qy = final_eval ? fsub(next_y, half) : ny;
                 const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
-                if (inx < -W15 || inx >= J.w || iny < -W15 || iny >= J.h) {
+                // -15 <= inx < w  <=>  (unsigned)(inx + 15) < (unsigned)(w + 15)
+                if ((unsigned)(inx + W15) >= (unsigned)(J.w + W15) || (unsigned)(iny + W15) >= (unsigned)(J.h + W15)) {
                     if (level == 0) status = 0;
                     break;
                 }
@@ -607,8 +609,7 @@ lk_track_w15_kernel(const LkArgs A)
                 int sb1 = 0, sb2 = 0;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) { sb1 += diff[i] * P.gx[i]; sb2 += diff[i] * P.gy[i]; }
-                const float b1 = fmul(__ll2float_rn(warp_sum_exact(sb1)), FLT_SCALE);
-                const float b2 = fmul(__ll2float_rn(warp_sum_exact(sb2)), FLT_SCALE);
+                const float b1 = warp_sum_scaled(sb1), b2 = warp_sum_scaled(sb2);
                 const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
                 const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
                 nx = fadd(nx, dx); ny = fadd(ny, dy);

@@ -77,6 +77,12 @@ int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t pitch, i
 int vel_decimate4_u8(const uint8_t* src, int32_t width, int32_t height, int32_t pitch, uint8_t* dst, int32_t dst_width,
                      int32_t dst_height, int32_t dst_pitch, vel_stream_t stream);
 
+/* Frame ingest: cv2.cvtColor(imbgr, cv2.COLOR_BGR2GRAY) of vidExample.py:91 for a batch of
+ * interleaved 8-bit BGR frames, in OpenCV's 15-bit fixed point:
+ * gray = (3735*B + 19235*G + 9798*R + 16384) >> 15 (bit-exact against cv2 4.13). */
+int vel_bgr2gray_u8(const uint8_t* bgr, int64_t bgr_stride, int32_t bgr_pitch, int32_t nframes, int32_t width, int32_t height,
+                    uint8_t* gray, int64_t gray_stride, int32_t gray_pitch, vel_stream_t stream);
+
 /* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
  * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
  * forward result fused in the same kernel with

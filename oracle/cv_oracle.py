@@ -38,6 +38,8 @@ def lib():
         L.orc_remap_affine_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, C.c_int, u8p,
                                           C.c_int]
         L.orc_remap_affine_u8.restype = None
+        L.orc_bgr2gray_u8.argtypes = [u8p, C.c_int, C.c_int, C.c_int, u8p, C.c_int]
+        L.orc_bgr2gray_u8.restype = None
         L.orc_knn2_hamming.argtypes = [u8p, C.c_int, u8p, C.c_int, C.c_int, i32p, i32p]
         L.orc_knn2_hamming.restype = None
         L.orc_knn2_l2.argtypes = [f32p, C.c_int, f32p, C.c_int, C.c_int, i32p, f32p]
@@ -142,3 +144,11 @@ def knn2_l2(q, t):
     dist = np.empty((q.shape[0], 2), np.float32)
     lib().orc_knn2_l2(_f32(q), q.shape[0], _f32(t), t.shape[0], q.shape[1], _i32(idx), _f32(dist))
     return idx, dist
+
+
+def bgr2gray(bgr):
+    bgr = np.ascontiguousarray(bgr, np.uint8)
+    h, w, _ = bgr.shape
+    out = np.empty((h, w), np.uint8)
+    lib().orc_bgr2gray_u8(_u8(bgr), w, h, 3 * w, _u8(out), w)
+    return out

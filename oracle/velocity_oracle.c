@@ -12,6 +12,7 @@
  *                                                          meshgrid arithmetic of utils/KLT.py:70-72)
  *     cv2.resize(.., 1/4, NEAREST) utils/KLT.py:111,113 -> orc_decimate4_u8
  *     cv2.BFMatcher().knnMatch(k=2) utils/KLT.py:16,25  -> orc_knn2_hamming / orc_knn2_l2
+ *     cv2.cvtColor(BGR2GRAY)     vidExample.py:91       -> orc_bgr2gray_u8
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
  * load this library.  The product (velocity_b200/) never does.
@@ -393,6 +394,16 @@ ORC_API void orc_knn2_l2(const float* q, int nq, const float* t, int nt, int dim
         idx[2 * i] = b0; idx[2 * i + 1] = b1;
         dist[2 * i] = b0 < 0 ? -1.f : sqrtf(d0); dist[2 * i + 1] = b1 < 0 ? -1.f : sqrtf(d1);
     }
+}
+
+/* cv2.cvtColor(BGR2GRAY) for CV_8UC3 (vidExample.py:91): OpenCV 4.13 uses 15-bit fixed point. */
+ORC_API void orc_bgr2gray_u8(const uint8_t* bgr, int w, int h, int bpitch, uint8_t* gray, int gpitch)
+{
+    for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+            const uint8_t* p = bgr + (size_t)y * bpitch + 3 * x;
+            gray[(size_t)y * gpitch + x] = (uint8_t)((3735 * p[0] + 19235 * p[1] + 9798 * p[2] + 16384) >> 15);
+        }
 }
 
 ORC_API int orc_version(void) { return 1; }

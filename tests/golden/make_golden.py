@@ -250,6 +250,14 @@ def gen_match():
     save("match_knn2", q=q, t=t, idx=idx, dist=dist, qf=qf, tf=tf, idxf=idxf, distf=distf)
 
 
+def gen_ingest():
+    """cv2.cvtColor(BGR2GRAY) (vidExample.py:91) on random colours plus the extreme / rounding-edge triples."""
+    rng = np.random.default_rng(91)
+    bgr = rng.integers(0, 256, (61, 83, 3), dtype=np.uint8)
+    bgr[0, :8] = [[0, 0, 0], [255, 255, 255], [255, 0, 0], [0, 255, 0], [0, 0, 255], [1, 1, 1], [254, 255, 254], [128, 127, 129]]
+    save("ingest_bgr", bgr=bgr, gray=cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
+
+
 def gen_e2e():
     """vidExample.py end to end on the two clips that have plate fixtures."""
     mod, ns = ref_shim.load_vid_example()
@@ -295,6 +303,7 @@ def main():
     gen_msv(ref)
     gen_ba(ref)
     gen_match()
+    gen_ingest()
     gen_e2e()
 
 

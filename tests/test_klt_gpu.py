@@ -176,3 +176,16 @@ def test_sequence_tracker_host_api_matches_per_pair_calls(cuda):
     for k in range(6):
         q2, qv, qerr = KLT.cv2calcOpticalFlowPyrLK(frames[k], frames[k + 1], pts, None, fbt=1.0, **lk)
         assert np.array_equal(p2[k], q2) and np.array_equal(v[k], qv) and np.array_equal(err[k], qerr.ravel())
+
+
+def test_bgr2gray_bit_exact(cuda):
+    from oracle import cv_oracle as O
+    from velocity_b200 import ingest
+
+    g = golden("ingest_bgr")
+    assert np.array_equal(ingest.bgr2gray(g["bgr"]), g["gray"])
+    rng = np.random.default_rng(2)
+    batch = rng.integers(0, 256, (3, 270, 480, 3), dtype=np.uint8)
+    out = ingest.bgr2gray(cuda.from_numpy(batch).cuda()).cpu().numpy()
+    for k in range(3):
+        assert np.array_equal(out[k], O.bgr2gray(batch[k]))

@@ -67,3 +67,8 @@ def test_empty_and_single_point():
     assert p2.shape == (0, 2) and st.shape == (0, 1)
     p2, st, err = O.calcOpticalFlowPyrLK(im, im, np.float32([[64.25, 40.75]]), (15, 15), 2, (3, 10, 0.1))
     assert st[0, 0] == 1 and np.abs(p2 - [[64.25, 40.75]]).max() < 1e-3 and err[0, 0] == 0
+
+
+def test_bgr2gray_against_reference():
+    g = golden("ingest_bgr")
+    assert np.array_equal(O.bgr2gray(g["bgr"]), g["gray"])

@@ -44,6 +44,7 @@ SIGNATURES = {
     "vel_pyr_layout_make": (C.c_int, [_I32, _I32, _I32, _I32, _I32, C.POINTER(PyrLayout)]),
     "vel_pyramid_u8": (C.c_int, [_P, _I64, _I32, _I32, C.POINTER(PyrLayout), _P, _I64, _P]),
     "vel_decimate4_u8": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _I32, _P]),
+    "vel_bgr2gray_u8": (C.c_int, [_P, _I64, _I32, _I32, _I32, _I32, _P, _I64, _I32, _P]),
     "vel_lk_track": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _P, _I64, C.POINTER(PyrLayout), _I32, _P, _I64, _I32,
                                C.POINTER(LkParams), _P, _P, _P, _P, _P]),
     "vel_remap_affine_u8": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(C.c_float), _I32, _I32, _I32, _I32, _P, _I32, _P]),

@@ -124,6 +124,58 @@ def test_lk_full_size_properties(cuda):
     assert np.array_equal(v[sel], ov) and np.array_equal(p2[sel], o2)
 
 
+def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
+    """The default 15x15 kernel gathers aligned words and re-aligns them per lane; the byte-gather
+    kernel (VEL_LK_W15=bytes) is the independent implementation.  Both must equal the oracle bit for
+    bit on ROI views with every base misalignment, on points hugging / leaving the frame border,
+    on a frame whose width is not a multiple of 4, and on the minimum 16-px-wide top level."""
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT, synth
+
+    rng = np.random.default_rng(7)
+    big0 = synth.texture(300, 420, 11)
+    big1 = np.roll(big0, (2, -3), (0, 1))
+    d0, d1 = cuda.from_numpy(big0).cuda(), cuda.from_numpy(big1).cuda()
+    lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 10, 0.03))
+    cases = []
+    for x0 in (0, 1, 2, 3, 5):           # base pointer misalignment 0..3 (pitch stays 420)
+        y0, hh, ww = 3 + x0, 240, 333 + x0
+        cases.append((d0[y0:y0 + hh, x0:x0 + ww], d1[y0:y0 + hh, x0:x0 + ww], big0[y0:y0 + hh, x0:x0 + ww], big1[y0:y0 + hh, x0:x0 + ww]))
+    odd0, odd1 = np.ascontiguousarray(big0[:131, :203]), np.ascontiguousarray(big1[:131, :203])   # host upload, width % 4 != 0
+    cases.append((odd0, odd1, odd0, odd1))
+    for a, b, ha, hb in cases:
+        h, w = ha.shape
+        inner = synth.harris_tracks(np.ascontiguousarray(ha), 150, border=2)
+        edge = np.stack([rng.uniform(-12, w + 12, 120), rng.uniform(-12, h + 12, 120)], 1).astype(np.float32)
+        rim = np.float32([[0, 0], [w - 1, h - 1], [7.5, 7.5], [w - 8.5, h - 8.5], [8, h / 2], [w - 9, h / 2], [w / 2, 8.01], [w / 2, h - 9.2],
+                          [-14.99, 30], [w - 0.01, 40], [50, -14.9], [60, h - 0.5]])
+        pts = np.concatenate([inner, edge, rim]).astype(np.float32)
+        for fbt in (None, 1.0):
+            o2, ov, oerr = KO.lk_forward_backward(np.ascontiguousarray(ha), np.ascontiguousarray(hb), pts, fbt=fbt, **lk)
+            res = {}
+            for impl in ("words", "bytes"):
+                if impl == "bytes":
+                    monkeypatch.setenv("VEL_LK_W15", "bytes")
+                else:
+                    monkeypatch.delenv("VEL_LK_W15", raising=False)
+                res[impl] = KLT.cv2calcOpticalFlowPyrLK(a, b, pts, None, fbt=fbt, **lk)
+            monkeypatch.delenv("VEL_LK_W15", raising=False)
+            for impl, (p2, v, err) in res.items():
+                assert np.array_equal(v, ov), (impl, ha.shape, fbt)
+                assert np.array_equal(p2, o2), (impl, ha.shape, fbt)
+                ok = oerr.ravel() != 0
+                assert np.array_equal(err[ok], oerr[ok]), (impl, ha.shape, fbt)
+            assert ov.any() and not ov.all()     # the case mixes tracked, lost and never-inside points
+    # smallest legal top level: 16 px wide / high
+    tiny0 = synth.texture(64, 64, 3)
+    tiny1 = np.roll(tiny0, (1, 1), (0, 1))
+    pts = rng.uniform(0, 63, (64, 2)).astype(np.float32)
+    lk2 = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.03))
+    o2, ov, _ = KO.lk_forward_backward(tiny0, tiny1, pts, fbt=1.0, **lk2)
+    p2, v, _ = KLT.cv2calcOpticalFlowPyrLK(tiny0, tiny1, pts, None, fbt=1.0, **lk2)
+    assert np.array_equal(v, ov) and np.array_equal(p2, o2)
+
+
 def test_edge_cases_empty_single_and_errors(cuda):
     """Empty and single-point inputs, points far outside the frame (status 0, no crash), argument
     errors surfaced as RuntimeError with the C ABI's message; a point set on a pure-constant image

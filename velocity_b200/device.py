@@ -53,5 +53,12 @@ def image_view(im):
     a = np.asarray(im) if not isinstance(im, torch.Tensor) else im.numpy()
     if a.dtype != np.uint8 or a.ndim != 2:
         raise ValueError("expected a 2-D uint8 image, got %s %s" % (a.dtype, a.shape))
-    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    h, w = a.shape
+    if w % 4 == 0:
+        t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    else:
+        # rows padded to a multiple of 16 bytes: the word-gathering 15x15 LK kernel needs pitch % 4 == 0
+        buf = torch.empty((h, (w + 15) // 16 * 16), dtype=torch.uint8, device="cuda")
+        t = buf[:, :w]
+        t.copy_(torch.from_numpy(np.ascontiguousarray(a)))
     return t, t.data_ptr(), t.shape[1], t.shape[0], t.stride(0)

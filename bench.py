@@ -323,7 +323,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=16, help="frames per H2D/compute pipeline chunk of the e2e path")
+    ap.add_argument("--chunk", type=int, default=8, help="frames per H2D/compute pipeline chunk of the e2e path")
     ap.add_argument("--z0", type=float, default=Z0_M, help="plane depth (m) of the synthetic generator")
     args = ap.parse_args()
     Z0_M = args.z0

@@ -125,9 +125,9 @@ def test_lk_full_size_properties(cuda):
 
 
 def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
-    """The default 15x15 kernel gathers aligned words and re-aligns them per lane; the byte-gather
-    kernel (VEL_LK_W15=bytes) is the independent implementation.  Both must equal the oracle bit for
-    bit on ROI views with every base misalignment, on points hugging / leaving the frame border,
+    """The default 15x15 kernel (two points per warp) gathers aligned words and re-aligns them per
+    lane; the byte-gather kernel (VEL_LK_W15=bytes) is the independent implementation.  Both must
+    equal the oracle bit for bit on ROI views with every base misalignment, on points hugging / leaving the frame border,
     on a frame whose width is not a multiple of 4, and on the minimum 16-px-wide top level."""
     from oracle import klt_oracle as KO
     from velocity_b200 import KLT, synth
@@ -153,11 +153,11 @@ def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
         for fbt in (None, 1.0):
             o2, ov, oerr = KO.lk_forward_backward(np.ascontiguousarray(ha), np.ascontiguousarray(hb), pts, fbt=fbt, **lk)
             res = {}
-            for impl in ("words", "bytes"):
-                if impl == "bytes":
-                    monkeypatch.setenv("VEL_LK_W15", "bytes")
-                else:
+            for impl in ("default", "bytes"):     # default = word-gathering kernel, two points per warp
+                if impl == "default":
                     monkeypatch.delenv("VEL_LK_W15", raising=False)
+                else:
+                    monkeypatch.setenv("VEL_LK_W15", impl)
                 res[impl] = KLT.cv2calcOpticalFlowPyrLK(a, b, pts, None, fbt=fbt, **lk)
             monkeypatch.delenv("VEL_LK_W15", raising=False)
             for impl, (p2, v, err) in res.items():

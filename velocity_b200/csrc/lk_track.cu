@@ -650,25 +650,7 @@ lk_track_w15_kernel(const LkArgs A)
     }
 }
 
-// =====================================================================================================
-// 15x15 "quad" kernel: the default path for the reference's lk_coarse window (utils/KLT.py:106) whenever
-// every row pitch is a multiple of 4 bytes (always true for the pyramid levels; true for level 0 of
-// ordinary frames and of ROI views cut from them).
-//
-// One warp per point as in the kernel above, but lane = (rp, cg) owns the 2x4 PIXEL QUAD rows
-// 2rp..2rp+1, columns 4cg..4cg+3 of the 16x16 footprint.  Consequences:
-//   * pixels are fetched as aligned 32-bit words (2 per row instead of 1 byte per pixel); the lane
-//     re-aligns them with one funnel shift per window, so a search iteration costs 6 word loads;
-//   * a bilinear sample is two DP2A instructions: the packed 16-bit weight pairs (w00,w01) / (w10,w11)
-//     against two adjacent pixel bytes, with 256 - (I << 9) as the accumulator input, so
-//     diff = dp2a(dp2a(I', top, W0), bottom, W1) >> 9 -- no cross-lane traffic at all;
-//   * no shared memory and no warp barriers: the template's Scharr tile comes from the lane's own
-//     5 x 7 byte neighbourhood (DP4A horizontal taps, vertical taps in registers); the only
-//     collectives are the REDUX sums of the 2x2 system.
-// Arithmetic and float32 operation order are those of the oracle: results are bit-identical to the
-// kernel above (tests/test_klt_gpu.py runs both).
-constexpr int WQ_WARPS = 8;
-
+// ---- helpers of the word-gathering 15x15 kernel (lk_w15h.cuh) --------------------------------------------------------
 __device__ __forceinline__ int dp2a_lo(int w, unsigned px, int acc)
 {
     int d;
@@ -683,288 +665,7 @@ __device__ __forceinline__ int dp2a_hi(int w, unsigned px, int acc)
 }
 __device__ __forceinline__ unsigned ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
 
-struct QPatch {
-    int I[8], gx[8], gy[8];   // pixel i = 4 * rr + j  <->  tile row 2rp + rr, tile column 4cg + j; I holds 256 - (I << 9)
-};
-
-// the lane's three J rows (tile rows 2rp .. 2rp+2) as byte windows: w0 = tile columns 4cg..4cg+3,
-// w1 = 4cg+1..4cg+4.  Tile row 16 / column 16 only feed the inactive row/column 15 of the footprint.
-__device__ __forceinline__ void wq_gather(const Img& J, int inx, int iny, int rp, int cg, unsigned (&w0)[3], unsigned (&w1)[3])
-{
-    const bool inside = (unsigned)inx <= (unsigned)(J.w - 16) && (unsigned)iny <= (unsigned)(J.h - 16);
-    const unsigned pitch = (unsigned)J.pitch;
-    if (inside) {
-        const uint8_t* a = J.p + ((unsigned)(iny + 2 * rp) * pitch + (unsigned)(inx + 4 * cg));
-        const unsigned mis = (unsigned)(size_t)a & 3u, sh = mis * 8u;
-        const uint8_t* r0 = a - mis;
-        const uint8_t* r1 = r0 + pitch;
-        const uint8_t* r2 = r1 + (rp == 7 ? 0u : pitch);            // tile row 16 does not exist: re-read row 15
-        // the second word of the last column group may lie wholly beyond column 15: do not touch it
-        const bool skip_hi = (cg == 3) && (mis == 0);
-        const unsigned l0 = ldg_u32(r0), l1 = ldg_u32(r1), l2 = ldg_u32(r2);
-        unsigned h0 = l0, h1 = l1, h2 = l2;
-        if (!skip_hi) { h0 = ldg_u32(r0 + 4); h1 = ldg_u32(r1 + 4); h2 = ldg_u32(r2 + 4); }
-        w0[0] = __funnelshift_r(l0, h0, sh); w1[0] = __funnelshift_rc(l0, h0, sh + 8u);
-        w0[1] = __funnelshift_r(l1, h1, sh); w1[1] = __funnelshift_rc(l1, h1, sh + 8u);
-        w0[2] = __funnelshift_r(l2, h2, sh); w1[2] = __funnelshift_rc(l2, h2, sh + 8u);
-    } else {
-        unsigned xo[5];
-#pragma unroll
-        for (int b = 0; b < 5; ++b) xo[b] = reflect_safe(inx + 4 * cg + b, J.w);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            const unsigned yo = reflect_safe(iny + min(2 * rp + k, 15), J.h) * pitch;
-            const unsigned v0 = ldg_u8(J.p + (yo + xo[0])), v1 = ldg_u8(J.p + (yo + xo[1])), v2 = ldg_u8(J.p + (yo + xo[2])),
-                           v3 = ldg_u8(J.p + (yo + xo[3])), v4 = ldg_u8(J.p + (yo + xo[4]));
-            const unsigned mid = v1 | (v2 << 8) | (v3 << 16);
-            w0[k] = v0 | (mid << 8);
-            w1[k] = mid | (v4 << 24);
-        }
-    }
-}
-
-// bilinear sample of the lane's 8 pixels minus the template: diff = (sum + 256 - (I << 9)) >> 9
-__device__ __forceinline__ void wq_diff(const unsigned (&w0)[3], const unsigned (&w1)[3], int W0, int W1, const QPatch& P, int (&diff)[8])
-{
-#pragma unroll
-    for (int rr = 0; rr < 2; ++rr) {
-        const unsigned t0 = w0[rr], t1 = w1[rr], b0 = w0[rr + 1], b1 = w1[rr + 1];
-        diff[4 * rr + 0] = dp2a_lo(W1, b0, dp2a_lo(W0, t0, P.I[4 * rr + 0])) >> 9;
-        diff[4 * rr + 1] = dp2a_lo(W1, b1, dp2a_lo(W0, t1, P.I[4 * rr + 1])) >> 9;
-        diff[4 * rr + 2] = dp2a_hi(W1, b0, dp2a_hi(W0, t0, P.I[4 * rr + 2])) >> 9;
-        diff[4 * rr + 3] = dp2a_hi(W1, b1, dp2a_hi(W0, t1, P.I[4 * rr + 3])) >> 9;
-    }
-}
-
-__global__ void __launch_bounds__(32 * WQ_WARPS, 3)
-lk_track_w15q_kernel(const LkArgs A)
-{
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.y;
-    const int pt = blockIdx.x * WQ_WARPS + warp;
-    if (pt >= A.npts) return;
-    const int cg = lane & 3, rp = lane >> 2;
-    const float half = 7.0f;
-
-    const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
-    const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
-    const uint8_t* N0 = A.next0 + (long long)pair * A.next_stride;
-    const uint8_t* Np = A.next_pyr ? A.next_pyr + (long long)pair * A.next_pyr_stride : nullptr;
-    const float* pin = A.pts + (long long)pair * A.pts_stride + 2ll * pt;
-    const float px0 = __ldg(pin), py0 = __ldg(pin + 1);
-
-    float fx = 0.f, fy = 0.f, ferr = 0.f, bx = 0.f, by = 0.f;
-    int fst = 0, st = 0;
-    const int npass = A.fbt >= 0.f ? 2 : 1;
-
-    for (int pass = 0; pass < npass; ++pass) {
-        const uint8_t* I0 = pass ? N0 : P0;
-        const uint8_t* Ipyr = pass ? Np : Pp;
-        const uint8_t* J0 = pass ? P0 : N0;
-        const uint8_t* Jpyr = pass ? Pp : Np;
-        const int I0_pitch = pass ? A.next_pitch : A.prev_pitch, J0_pitch = pass ? A.prev_pitch : A.next_pitch;
-        const float px = pass ? fx : px0, py = pass ? fy : py0;
-
-        int status = 1;
-        float err = 0.f;
-        float next_x = 0.f, next_y = 0.f;
-
-        for (int level = A.lv.max_level; level >= 0; --level) {
-            Img I, J;
-            I.w = J.w = A.lv.w[level];
-            I.h = J.h = A.lv.h[level];
-            if (level == 0) { I.p = I0; I.pitch = I0_pitch; J.p = J0; J.pitch = J0_pitch; }
-            else { I.p = Ipyr + A.lv.off[level]; J.p = Jpyr + A.lv.off[level]; I.pitch = J.pitch = A.lv.pitch[level]; }
-
-            const float scale = 1.f / (float)(1 << level);
-            float prev_x = fmul(px, scale), prev_y = fmul(py, scale);
-            float nx, ny;
-            if (level == A.lv.max_level) { nx = prev_x; ny = prev_y; }
-            else { nx = fmul(next_x, 2.f); ny = fmul(next_y, 2.f); }
-            next_x = nx; next_y = ny;
-
-            prev_x = fsub(prev_x, half); prev_y = fsub(prev_y, half);
-            const int ipx = __float2int_rd(prev_x), ipy = __float2int_rd(prev_y);
-            if (ipx < -W15 || ipx >= I.w || ipy < -W15 || ipy >= I.h) {
-                if (level == 0) { status = 0; err = 0.f; }
-                continue;
-            }
-            Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
-            int W0 = (int)__byte_perm((unsigned)w.w00, (unsigned)w.w01, 0x5410);
-            int W1 = (int)__byte_perm((unsigned)w.w10, (unsigned)w.w11, 0x5410);
-
-            // ---- template: the lane's 5 image rows (tile rows 2rp-1 .. 2rp+3) x 7 bytes (tile columns 4cg-1 .. 4cg+5) ----
-            QPatch P;
-            int a11 = 0, a12 = 0, a22 = 0;
-            {
-                const bool interior = ipx >= 1 && ipy >= 1 && ipx + 16 < I.w && ipy + 16 < I.h;
-                const unsigned pitch = (unsigned)I.pitch;
-                unsigned lo[5], hi[5];   // bytes 0..3 and 4..7 of each row
-                if (interior) {
-                    const uint8_t* a = I.p + ((unsigned)(ipy + 2 * rp - 1) * pitch + (unsigned)(ipx + 4 * cg - 1));
-                    const unsigned mis = (unsigned)(size_t)a & 3u, sh = mis * 8u;
-                    const uint8_t* r = a - mis;
-                    // never touch a word that lies wholly beyond tile column 16 / tile row 16
-                    const bool skip_w2 = (cg == 3) && (mis < 3);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const unsigned L0 = ldg_u32(r), L1 = ldg_u32(r + 4);
-                        unsigned L2 = L1;
-                        if (!skip_w2) L2 = ldg_u32(r + 8);
-                        lo[q] = __funnelshift_r(L0, L1, sh);
-                        hi[q] = __funnelshift_r(L1, L2, sh);
-                        if (q < 3 || (q == 3 && rp != 7)) r += pitch;
-                    }
-                } else {
-                    unsigned xo[7];
-#pragma unroll
-                    for (int b = 0; b < 7; ++b) xo[b] = reflect_safe(ipx + 4 * cg - 1 + b, I.w);
-#pragma unroll
-                    for (int q = 0; q < 5; ++q) {
-                        const unsigned yo = reflect_safe(ipy + 2 * rp - 1 + q, I.h) * pitch;
-                        lo[q] = ldg_u8(I.p + (yo + xo[0])) | (ldg_u8(I.p + (yo + xo[1])) << 8) | (ldg_u8(I.p + (yo + xo[2])) << 16) |
-                                (ldg_u8(I.p + (yo + xo[3])) << 24);
-                        hi[q] = ldg_u8(I.p + (yo + xo[4])) | (ldg_u8(I.p + (yo + xo[5])) << 8) | (ldg_u8(I.p + (yo + xo[6])) << 16);
-                    }
-                }
-                // horizontal taps of the Scharr pair at tile columns 4cg + t, t = 0..4, on all 5 rows
-                int hd[5][5], hs[5][5];
-                unsigned win1[5], win2[5];
-#pragma unroll
-                for (int q = 0; q < 5; ++q) {
-                    win1[q] = __funnelshift_r(lo[q], hi[q], 8);
-                    win2[q] = __funnelshift_r(lo[q], hi[q], 16);
-                    const unsigned win3 = __funnelshift_r(lo[q], hi[q], 24);
-                    const unsigned wins[5] = {lo[q], win1[q], win2[q], win3, hi[q]};
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) {
-                        hd[q][t] = dp4a_us(wins[t], 0x000100FF, 0);   // (-1, 0, +1, 0)
-                        hs[q][t] = dp4a_us(wins[t], 0x00030A03, 0);   // ( 3,10,  3, 0)
-                    }
-                }
-                // Scharr pair at the lane's 3 x 5 tile positions (constant 0 outside the image)
-                int gx[3][5], gy[3][5];
-#pragma unroll
-                for (int y = 0; y < 3; ++y) {
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) {
-                        gx[y][t] = 3 * (hd[y][t] + hd[y + 2][t]) + 10 * hd[y + 1][t];
-                        gy[y][t] = hs[y + 2][t] - hs[y][t];
-                    }
-                }
-                if (!interior) {   // the derivative image is padded with constant 0 outside the frame
-#pragma unroll
-                    for (int y = 0; y < 3; ++y) {
-                        const bool in_y = (unsigned)(ipy + 2 * rp + y) < (unsigned)I.h;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) {
-                            if (!(in_y && (unsigned)(ipx + 4 * cg + t) < (unsigned)I.w)) { gx[y][t] = 0; gy[y][t] = 0; }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int rr = 0; rr < 2; ++rr) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int i = 4 * rr + j;
-                        const bool active = (cg < 3 || j < 3) && (rp < 7 || rr == 0);
-                        // template pixel: tile column 4cg + j is byte j + 1 of the row
-                        const unsigned top = (j & 1) ? win2[rr + 1] : win1[rr + 1], bot = (j & 1) ? win2[rr + 2] : win1[rr + 2];
-                        const int s = (j & 2) ? dp2a_hi(W1, bot, dp2a_hi(W0, top, 1 << 8)) : dp2a_lo(W1, bot, dp2a_lo(W0, top, 1 << 8));
-                        const int ival = s >> 9;
-                        int ix = (gx[rr][j] * w.w00 + gx[rr][j + 1] * w.w01 + gx[rr + 1][j] * w.w10 + gx[rr + 1][j + 1] * w.w11 + (1 << 13)) >> 14;
-                        int iy = (gy[rr][j] * w.w00 + gy[rr][j + 1] * w.w01 + gy[rr + 1][j] * w.w10 + gy[rr + 1][j + 1] * w.w11 + (1 << 13)) >> 14;
-                        if (!active) { ix = 0; iy = 0; }
-                        P.I[i] = (1 << 8) - (ival << 9); P.gx[i] = ix; P.gy[i] = iy;
-                        a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
-                    }
-                }
-            }
-            const float A11 = warp_sum_scaled(a11), A12 = warp_sum_scaled(a12), A22 = warp_sum_scaled(a22);
-            float D = fsub(fmul(A11, A22), fmul(A12, A12));
-            const float dA = fsub(A11, A22);
-            const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
-            const float min_eig = __fdiv_rn(fsub(fadd(A22, A11), __fsqrt_rn(disc)), (float)(2 * W15 * W15));
-            if (min_eig < A.min_eig || D < 1.1920928955078125e-07f) {
-                if (level == 0) status = 0;
-                continue;
-            }
-            D = __fdiv_rn(1.f, D);
-
-            // ---- Newton iterations; at level 0 one extra trip through the same code evaluates err -----
-            nx = fsub(nx, half); ny = fsub(ny, half);
-            float pdx = 0.f, pdy = 0.f;
-            bool final_eval = false;
-            for (int j = 0;; ++j) {
-                if (!final_eval && j >= A.max_count) {
-                    if (level == 0 && status) final_eval = true;
-                    else break;
-                }
-                const float qx = final_eval ? fsub(next_x, half) : nx, qy = final_eval ? fsub(next_y, half) : ny;
-                const int inx = __float2int_rd(qx), iny = __float2int_rd(qy);
-                if ((unsigned)(inx + W15) >= (unsigned)(J.w + W15) || (unsigned)(iny + W15) >= (unsigned)(J.h + W15)) {
-                    if (level == 0) status = 0;
-                    break;
-                }
-                w = bilin_weights(fsub(qx, (float)inx), fsub(qy, (float)iny));
-                W0 = (int)__byte_perm((unsigned)w.w00, (unsigned)w.w01, 0x5410);
-                W1 = (int)__byte_perm((unsigned)w.w10, (unsigned)w.w11, 0x5410);
-                unsigned w0[3], w1[3];
-                int diff[8];
-                wq_gather(J, inx, iny, rp, cg, w0, w1);
-                wq_diff(w0, w1, W0, W1, P, diff);
-                if (final_eval) {
-                    int e = 0;
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const bool active = (cg < 3 || (i & 3) < 3) && (rp < 7 || i < 4);
-                        e += active ? abs(diff[i]) : 0;
-                    }
-                    e = __reduce_add_sync(0xffffffffu, e);
-                    err = __fdiv_rn((float)e, (float)(32 * W15 * W15));
-                    break;
-                }
-                int sb1 = 0, sb2 = 0;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) { sb1 += diff[i] * P.gx[i]; sb2 += diff[i] * P.gy[i]; }
-                const float b1 = warp_sum_scaled(sb1), b2 = warp_sum_scaled(sb2);
-                const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
-                const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
-                nx = fadd(nx, dx); ny = fadd(ny, dy);
-                next_x = fadd(nx, half); next_y = fadd(ny, half);
-                bool stop = fadd(fmul(dx, dx), fmul(dy, dy)) <= A.eps2;
-                if (!stop && j > 0 && fabsf(fadd(dx, pdx)) < 0.01f && fabsf(fadd(dy, pdy)) < 0.01f) {
-                    next_x = fsub(next_x, fmul(dx, 0.5f));
-                    next_y = fsub(next_y, fmul(dy, 0.5f));
-                    stop = true;
-                }
-                pdx = dx; pdy = dy;
-                if (stop) {
-                    if (level == 0 && status) final_eval = true;
-                    else break;
-                }
-            }
-        }
-
-        if (pass == 0) {
-            fx = next_x; fy = next_y; fst = status; ferr = err; st = status;
-            if (!fst) break;   // the backward pass cannot change a failed track
-        } else {
-            bx = next_x; by = next_y;
-            const float ddx = fsub(px0, bx), ddy = fsub(py0, by);
-            const float fbe = __fsqrt_rn(fadd(fmul(ddx, ddx), fmul(ddy, ddy)));
-            st = status && (fbe < A.fbt);
-        }
-    }
-    if (lane == 0) {
-        const long long o = (long long)pair * A.npts + pt;
-        A.out[2 * o] = fx;
-        A.out[2 * o + 1] = fy;
-        A.status[o] = (uint8_t)st;
-        A.err[o] = fst ? ferr : 0.f;
-        if (A.back) { A.back[2 * o] = bx; A.back[2 * o + 1] = by; }
-    }
-}
+#include "lk_w15h.cuh"
 
 // =====================================================================================================
 // Column-streaming path for mid-size windows (16 <= win_w <= COLS-1, win_h <= 63; the reference's
@@ -1251,15 +952,15 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
 
     cudaStream_t st = (cudaStream_t)stream;
     if (ww == W15 && wh == W15) {
-        // quad kernel: needs every row pitch to be a multiple of 4 bytes (word loads re-aligned per lane);
-        // VEL_LK_W15=bytes forces the byte-gather kernel (kept for odd pitches and as a cross-check)
-        bool quad = (prev_pitch % 4 == 0) && (next_pitch % 4 == 0);
-        for (int l = 1; l <= layout->max_level; ++l) quad = quad && (layout->pitch[l] % 4 == 0);
+        // word-gathering kernel (two points per warp): needs every row pitch to be a multiple of 4 bytes;
+        // VEL_LK_W15=bytes forces the byte-gather kernel (kept for odd pitches and as an independent cross-check)
+        bool words = (prev_pitch % 4 == 0) && (next_pitch % 4 == 0);
+        for (int l = 1; l <= layout->max_level; ++l) words = words && (layout->pitch[l] % 4 == 0);
         const char* force = getenv("VEL_LK_W15");
-        if (force && strcmp(force, "bytes") == 0) quad = false;
-        if (quad) {
-            dim3 grid((npts + WQ_WARPS - 1) / WQ_WARPS, npairs);
-            lk_track_w15q_kernel<<<grid, 32 * WQ_WARPS, 0, st>>>(A);
+        if (force && strcmp(force, "bytes") == 0) words = false;
+        if (words) {
+            dim3 grid((npts + 2 * WH_WARPS - 1) / (2 * WH_WARPS), npairs);
+            lk_track_w15h_kernel<<<grid, 32 * WH_WARPS, 0, st>>>(A);
         } else {
             dim3 grid((npts + W15_WARPS - 1) / W15_WARPS, npairs);
             lk_track_w15_kernel<<<grid, 32 * W15_WARPS, 0, st>>>(A);

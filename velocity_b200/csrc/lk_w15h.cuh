@@ -28,13 +28,34 @@ __device__ __forceinline__ int half_sum(int v, unsigned hmask)
     return v;
 }
 
-// float(sum over the half) * 2^-20 with a single rounding, exact for |lane value| < 2^31
-// (same two-limb argument as warp_sum_scaled)
-__device__ __forceinline__ float half_sum_scaled(int v, unsigned hmask)
+// Four exact 16-lane sums for the price of nine shuffles (instead of sixteen): the first two butterfly steps also
+// TRANSPOSE -- after xor 8 a lane carries only two of the four quantities, after xor 4 only one -- so steps xor 2 and
+// xor 1 reduce a single register; lane (b3, b2) of the half then owns the total of q[2*b3 + b2] and four indexed
+// shuffles hand every total to every lane.  Wrap-around uint32 arithmetic: exact whenever each total fits 32 bits.
+__device__ __forceinline__ void half_sum4(unsigned (&q)[4], unsigned hmask, int lane)
 {
-    const int slo = half_sum((int)((unsigned)v & 0xffffu), hmask);   // < 2^20
-    const int shi = half_sum(v >> 16, hmask);                          // |.| < 2^19
-    return __fmaf_rn((float)shi, 0.0625f, __fmul_rn((float)slo, 1.f / 1048576.f));
+    const bool b3 = lane & 8, b2 = lane & 4;
+    unsigned k0 = b3 ? q[2] : q[0], k1 = b3 ? q[3] : q[1];
+    const unsigned s0 = b3 ? q[0] : q[2], s1 = b3 ? q[1] : q[3];
+    k0 += __shfl_xor_sync(hmask, s0, 8);
+    k1 += __shfl_xor_sync(hmask, s1, 8);
+    unsigned k = b2 ? k1 : k0;
+    const unsigned s = b2 ? k0 : k1;
+    k += __shfl_xor_sync(hmask, s, 4);
+    k += __shfl_xor_sync(hmask, k, 2);
+    k += __shfl_xor_sync(hmask, k, 1);
+    const int base = lane & 16;
+    q[0] = __shfl_sync(hmask, k, base);
+    q[1] = __shfl_sync(hmask, k, base + 4);
+    q[2] = __shfl_sync(hmask, k, base + 8);
+    q[3] = __shfl_sync(hmask, k, base + 12);
+}
+
+// float(hi * 65536 + lo) * 2^-20 with a single rounding: both limbs are exact in float32 (|hi| < 2^19, lo < 2^20) and
+// one FMA rounds their exact sum once (same argument as warp_sum_scaled)
+__device__ __forceinline__ float limbs_scaled(unsigned lo, unsigned hi)
+{
+    return __fmaf_rn((float)(int)hi, 0.0625f, __fmul_rn((float)lo, 1.f / 1048576.f));
 }
 
 // the lane's five J rows (tile rows 4rq .. 4rq+4) as byte windows: w0 = tile columns 4cg..4cg+3, w1 = 4cg+1..4cg+4
@@ -232,7 +253,11 @@ lk_track_w15h_kernel(const LkArgs A)
                     }
                 }
             }
-            const float A11 = half_sum_scaled(a11, hmask), A12 = half_sum_scaled(a12, hmask), A22 = half_sum_scaled(a22, hmask);
+            // a11, a22 >= 0 and their totals stay below 2^32 (225 px x 4080^2): one unsigned word each; a12 needs two limbs
+            unsigned qa[4] = {(unsigned)a11, (unsigned)a22, (unsigned)a12 & 0xffffu, (unsigned)(a12 >> 16)};
+            half_sum4(qa, hmask, lane);
+            const float A11 = fmul(__uint2float_rn(qa[0]), 1.f / 1048576.f), A22 = fmul(__uint2float_rn(qa[1]), 1.f / 1048576.f);
+            const float A12 = limbs_scaled(qa[2], qa[3]);
             float D = fsub(fmul(A11, A22), fmul(A12, A12));
             const float dA = fsub(A11, A22);
             const float disc = fadd(fmul(dA, dA), fmul(fmul(4.f, A12), A12));
@@ -291,7 +316,9 @@ lk_track_w15h_kernel(const LkArgs A)
                     sb1 += df[4 * rr + 0] * g1.x + df[4 * rr + 1] * g1.y + df[4 * rr + 2] * g1.z + df[4 * rr + 3] * g1.w;
                     sb2 += df[4 * rr + 0] * g2.x + df[4 * rr + 1] * g2.y + df[4 * rr + 2] * g2.z + df[4 * rr + 3] * g2.w;
                 }
-                const float b1 = half_sum_scaled(sb1, hmask), b2 = half_sum_scaled(sb2, hmask);
+                unsigned qb[4] = {(unsigned)sb1 & 0xffffu, (unsigned)(sb1 >> 16), (unsigned)sb2 & 0xffffu, (unsigned)(sb2 >> 16)};
+                half_sum4(qb, hmask, lane);
+                const float b1 = limbs_scaled(qb[0], qb[1]), b2 = limbs_scaled(qb[2], qb[3]);
                 const float dx = fmul(fsub(fmul(A12, b2), fmul(A22, b1)), D);
                 const float dy = fmul(fsub(fmul(A12, b1), fmul(A11, b2)), D);
                 nx = fadd(nx, dx); ny = fadd(ny, dy);

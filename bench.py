@@ -295,11 +295,11 @@ def run_ours(args):
                        "pairs_per_step_per_gpu": PAIRS, "tracks": NPTS, "plane_depth_m": Z0_M, "frames_resident_mb": (PAIRS + 1) * HW_B / 1e6,
                        "l2_policy": "inputs (%d MB of frames per step) larger than L2; e2e additionally flushes L2" % ((PAIRS + 1) * HW_B // 1000000),
                        "valid_fraction": valid_frac, "sharding": "frames, no collective"},
-            "roofline": {"bound": "hbm", "kernel": "lk_track_kernel (K2)", "achieved": k2_gbs, "peak": peaks["hbm_gbs"],
+            "roofline": {"bound": "hbm", "kernel": "lk_track_w15h_kernel (K2)", "achieved": k2_gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                          "bytes_per_launch": PAIRS * K2_BYTES_PER_PAIR_FB, "ms_per_launch": k2_ms,
-                         "note": "K2 is instruction-issue-bound (ncu: >80% issue slots busy, DRAM traffic ~2.7 MB/pair because "
-                                 "each pyramid is read from HBM once and served from L2 for its other roles); the HBM-bound "
+                         "note": "K2 is instruction-issue/latency-bound (ncu: 72% issue slots busy, DRAM traffic ~2.7 MB/pair because "
+                                 "each pyramid is read from HBM once and served from L2/L1 for its other roles); the HBM-bound "
                                  "stage of KLT is K1, reported in k1_pyramid",
                          "k1_pyramid": {"achieved": k1_gbs, "frac": k1_gbs / peaks["hbm_gbs"], "ms_per_step": k1_ms,
                                         "bytes_per_step": (PAIRS + 1) * K1_BYTES_PER_FRAME},

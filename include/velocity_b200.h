@@ -83,6 +83,18 @@ int vel_decimate4_u8(const uint8_t* src, int32_t width, int32_t height, int32_t 
 int vel_bgr2gray_u8(const uint8_t* bgr, int64_t bgr_stride, int32_t bgr_pitch, int32_t nframes, int32_t width, int32_t height,
                     uint8_t* gray, int64_t gray_stride, int32_t gray_pitch, vel_stream_t stream);
 
+/* K9.  Feature initialisation: cv2.goodFeaturesToTrack(roi, maxCorners, quality, 0,
+ * blockSize=5, useHarrisDetector=True) of vidExample.py:110 (Harris k = 0.04 there), in OpenCV 4.13's arithmetic
+ * (fused Sobel taps, float64 running box sums, unfused response; restated in oracle/gftt_oracle.py): the same
+ * corners in the same order as cv2.  img is one uint8 image; out_xy receives up to max_corners (x, y) float32
+ * pairs, out_count[1] their number (both DEVICE); response, if not NULL, receives the float32 [height][width]
+ * Harris response.  work must hold vel_good_features_workspace() bytes.  Only block_size 5 and minDistance 0
+ * (what the reference passes) are implemented. */
+size_t vel_good_features_workspace(int32_t width, int32_t height, int32_t max_corners);
+int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32_t height, int32_t pitch, int32_t max_corners,
+                                double quality, int32_t block_size, double k, void* work, size_t work_bytes, float* response,
+                                float* out_xy, int32_t* out_count, vel_stream_t stream);
+
 /* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
  * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
  * forward result fused in the same kernel with

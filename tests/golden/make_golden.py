@@ -258,6 +258,20 @@ def gen_ingest():
     save("ingest_bgr", bgr=bgr, gray=cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY))
 
 
+def gen_gftt():
+    """cv2.goodFeaturesToTrack(roi, n, q, 0, blockSize=5, useHarrisDetector=True) (vidExample.py:110) and the Harris
+    response behind it, on widths that are / are not multiples of 32 and 16 (cv2's SIMD tails)."""
+    out = {}
+    for tag, (h, w, seed) in {"a": (120, 160, 21), "b": (97, 203, 22), "c": (150, 77, 23)}.items():
+        im = synth.texture(h, w, seed)
+        out["im_" + tag] = im
+        out["resp_" + tag] = cv2.cornerHarris(im, 5, 3, 0.04)
+        for n, q in ((1000, 0.01), (64, 0.05), (4096, 0.001)):
+            c = cv2.goodFeaturesToTrack(im, n, q, 0, blockSize=5, useHarrisDetector=True)
+            out["xy_%s_%d" % (tag, n)] = np.zeros((0, 1, 2), np.float32) if c is None else c
+    save("gftt", **out)
+
+
 def gen_e2e():
     """vidExample.py end to end on the two clips that have plate fixtures."""
     mod, ns = ref_shim.load_vid_example()
@@ -304,6 +318,7 @@ def main():
     gen_ba(ref)
     gen_match()
     gen_ingest()
+    gen_gftt()
     gen_e2e()
 
 

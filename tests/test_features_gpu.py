@@ -1,0 +1,68 @@
+"""Parity of K9 (Harris response + goodFeaturesToTrack selection, csrc/features.cu) against the CPU oracle and the
+cv2-generated golden vectors: same response bits, same corners, same order."""
+import numpy as np
+import pytest
+
+from util import golden
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from velocity_b200 import _lib
+
+    _lib.lib()
+    return torch
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+def test_harris_response_equals_oracle_bit_for_bit(cuda, tag):
+    from oracle import gftt_oracle as G
+    from velocity_b200 import features
+
+    g = golden("gftt")
+    im = g["im_" + tag]
+    _, _, resp = features.harris_corners_device(im, 100, 0.01, want_response=True)
+    R = resp.cpu().numpy()
+    assert np.array_equal(R, G.harris_response(im))          # CUDA == oracle, every pixel
+    ref, tail = g["resp_" + tag], (im.shape[1] // 16) * 16   # == cv2 except its last-row SIMD tail (oracle header)
+    assert np.array_equal(R[:-1], ref[:-1]) and np.array_equal(R[-1, :tail], ref[-1, :tail])
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("n,q", [(1000, 0.01), (64, 0.05), (4096, 0.001)])
+def test_good_features_equal_cv2_golden(cuda, tag, n, q):
+    from velocity_b200 import features
+
+    g = golden("gftt")
+    ref = g["xy_%s_%d" % (tag, n)]
+    out = features.goodFeaturesToTrack(g["im_" + tag], n, q, 0, blockSize=5, useHarrisDetector=True)
+    assert out.dtype == np.float32 and out.shape == ref.shape
+    assert np.array_equal(out, ref)
+
+
+def test_good_features_full_frame_and_views(cuda):
+    """1080p frame (BASELINE size): equal to the oracle; a CUDA ROI view (pitch != width, as vidExample.py:109 cuts it)
+    gives the same corners as the contiguous copy; unsupported configurations are refused, not approximated."""
+    from oracle import gftt_oracle as G
+    from velocity_b200 import features, synth
+
+    im = synth.texture(1080, 1920, 77)
+    out = features.goodFeaturesToTrack(im, 4096, 0.001, 0, blockSize=5, useHarrisDetector=True)
+    assert np.array_equal(out.reshape(-1, 2), G.good_features_to_track(im, 4096, 0.001))
+    d = cuda.from_numpy(im).cuda()
+    roi = d[101:901, 333:1500]
+    a = features.goodFeaturesToTrack(roi, 1000, 0.01, 0, blockSize=5, useHarrisDetector=True)
+    b = features.goodFeaturesToTrack(np.ascontiguousarray(im[101:901, 333:1500]), 1000, 0.01, 0, blockSize=5, useHarrisDetector=True)
+    assert np.array_equal(a, b) and len(a) == 1000
+    assert np.array_equal(a.reshape(-1, 2), G.good_features_to_track(im[101:901, 333:1500], 1000, 0.01))
+    flat = np.full((64, 64), 9, np.uint8)
+    assert features.goodFeaturesToTrack(flat, 10, 0.01, 0, blockSize=5, useHarrisDetector=True) is None
+    with pytest.raises(NotImplementedError):
+        features.goodFeaturesToTrack(im, 10, 0.01, 5, blockSize=5, useHarrisDetector=True)
+    with pytest.raises(NotImplementedError):
+        features.goodFeaturesToTrack(im, 10, 0.01, 0, blockSize=3, useHarrisDetector=True)

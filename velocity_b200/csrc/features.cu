@@ -1,0 +1,283 @@
+// K9: feature initialisation -- cv2.goodFeaturesToTrack(roi, maxCorners, quality, 0, blockSize=5,
+// useHarrisDetector=True) as the reference calls it at vidExample.py:110.
+//
+// The arithmetic is OpenCV's (un-vendored, unpinned: requirements.txt:5; pinned here by black-box comparison
+// against opencv-python 4.13.0 and restated on the CPU in oracle/gftt_oracle.py):
+//   1. Sobel pair, CV_32F, scale s = 1/(4*blockSize*255), REFLECT_101, float32 kernel (k1, k0, k1) = (1,2,1)*s:
+//        Dx = fma(r(y-1) + r(y+1), k1, r(y)*k0),  r = p(x+1) - p(x-1)
+//        Dy = t(y+1) - t(y-1),  t = fma(p(x+1), k1, fma(p(x), k0, p(x-1)*k1)) for columns < 32*(w/32),
+//             ((p(x-1)*k1 + p(x)*k0) + p(x+1)*k1) in the remaining columns (cv2's scalar row-filter tail)
+//   2. cov = (Dx*Dx, Dx*Dy, Dy*Dy), float32
+//   3. 5x5 box sums (REFLECT_101) in float64: row sums left to right, then cv2's RUNNING column sum from the top of
+//      the image (SUM += entering row; out = float(SUM); SUM -= leaving row).  Double sums are exact -- hence
+//      order-free -- except where a cancellation residue of the fused Sobel makes a gradient ~1e-11; replicating
+//      the running order keeps even those pixels bit-identical, at the price of a sequential walk down each column.
+//   4. R = (a*c - b*b) - k*((a+c)*(a+c)), float32, unfused
+//   5. keep R > float(max(R)*quality); 3x3 local maxima inside the 1-px frame; order by value descending, ties by
+//      higher raster address; first maxCorners.  (minDistance = 0 as in the reference: no spacing filter.)
+//
+// HBM streaming: the frame is read once (cov kernel), cov/R planes are written and read once.  Every float step uses
+// explicit round-to-nearest intrinsics so nothing is contracted differently from the oracle.  Selection is
+// deterministic: candidates are appended with an atomic counter (arbitrary order), then the K-th largest 64-bit key
+// (value bits << 32 | address, all distinct) is found by an 8-pass radix select and the survivors are ranked by
+// counting -- no host round trip, no library sort.
+#include "common.cuh"
+
+namespace {
+
+struct GfttState {           // device-resident control block at the start of the workspace
+    unsigned max_bits;       // orderable bits of max(R)
+    unsigned n_cand;         // candidates appended
+    unsigned n_sel;          // survivors appended
+    unsigned n_out;          // min(n_cand, max_corners)
+    unsigned long long prefix;   // radix-select prefix; after 8 passes the K-th largest key
+    unsigned remaining;      // rank still to descend inside the current prefix
+    unsigned hist[256];
+};
+
+__device__ __forceinline__ unsigned orderable(float v)
+{
+    const unsigned u = __float_as_uint(v);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable(unsigned u)
+{
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
+__global__ void gftt_reset_kernel(GfttState* S)
+{
+    if (threadIdx.x == 0) { S->max_bits = 0u; S->n_cand = 0u; S->n_sel = 0u; S->n_out = 0u; S->prefix = 0ull; S->remaining = 0u; }
+    S->hist[threadIdx.x] = 0u;
+}
+
+// steps 1-2: one thread per pixel
+__global__ void __launch_bounds__(256)
+harris_cov_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, float k1, float k0, int fused_cols,
+                  float* __restrict__ cxx, float* __restrict__ cxy, float* __restrict__ cyy)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const int xm = reflect101(x - 1, w), xp = reflect101(x + 1, w);
+    const uint8_t* r0 = img + (size_t)reflect101(y - 1, h) * pitch;
+    const uint8_t* r1 = img + (size_t)y * pitch;
+    const uint8_t* r2 = img + (size_t)reflect101(y + 1, h) * pitch;
+    const float a0 = (float)__ldg(r0 + xm), a1 = (float)__ldg(r0 + x), a2 = (float)__ldg(r0 + xp);
+    const float b0 = (float)__ldg(r1 + xm), b2 = (float)__ldg(r1 + xp);
+    const float c0 = (float)__ldg(r2 + xm), c1 = (float)__ldg(r2 + x), c2 = (float)__ldg(r2 + xp);
+    const float ra = __fsub_rn(a2, a0), rb = __fsub_rn(b2, b0), rc = __fsub_rn(c2, c0);
+    const float dx = __fmaf_rn(__fadd_rn(ra, rc), k1, __fmul_rn(rb, k0));
+    float ta, tc;
+    if (x < fused_cols) {
+        ta = __fmaf_rn(a2, k1, __fmaf_rn(a1, k0, __fmul_rn(a0, k1)));
+        tc = __fmaf_rn(c2, k1, __fmaf_rn(c1, k0, __fmul_rn(c0, k1)));
+    } else {
+        ta = __fadd_rn(__fadd_rn(__fmul_rn(a0, k1), __fmul_rn(a1, k0)), __fmul_rn(a2, k1));
+        tc = __fadd_rn(__fadd_rn(__fmul_rn(c0, k1), __fmul_rn(c1, k0)), __fmul_rn(c2, k1));
+    }
+    const float dy = __fsub_rn(tc, ta);
+    const size_t o = (size_t)y * w + x;
+    cxx[o] = __fmul_rn(dx, dx);
+    cxy[o] = __fmul_rn(dx, dy);
+    cyy[o] = __fmul_rn(dy, dy);
+}
+
+// steps 3-4: one thread per column, walking down the rows with cv2's running float64 column sums
+constexpr int BOX_THREADS = 64;
+
+__device__ __forceinline__ double row5(const float* __restrict__ plane, size_t row_off, const int (&xs)[5])
+{
+    const float* r = plane + row_off;
+    double s = __dadd_rn((double)__ldg(r + xs[0]), (double)__ldg(r + xs[1]));
+    s = __dadd_rn(s, (double)__ldg(r + xs[2]));
+    s = __dadd_rn(s, (double)__ldg(r + xs[3]));
+    return __dadd_rn(s, (double)__ldg(r + xs[4]));
+}
+
+__global__ void __launch_bounds__(BOX_THREADS)
+harris_box_response_kernel(const float* __restrict__ cxx, const float* __restrict__ cxy, const float* __restrict__ cyy,
+                           int w, int h, float kf, float* __restrict__ R, GfttState* S)
+{
+    const int x = blockIdx.x * BOX_THREADS + threadIdx.x;
+    float vmax = -INFINITY;
+    if (x < w) {
+        int xs[5];
+#pragma unroll
+        for (int d = 0; d < 5; ++d) xs[d] = reflect101(x + d - 2, w);
+        double ring[3][5];        // row sums of the five rows inside the window; slot = (row + 2) % 5
+        double sum[3] = {0., 0., 0.};
+#pragma unroll
+        for (int i = -2; i <= 1; ++i) {
+            const size_t ro = (size_t)reflect101(i, h) * w;
+            ring[0][i + 2] = row5(cxx, ro, xs); ring[1][i + 2] = row5(cxy, ro, xs); ring[2][i + 2] = row5(cyy, ro, xs);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) sum[c] = __dadd_rn(sum[c], ring[c][i + 2]);
+        }
+        for (int y0 = 0; y0 < h; y0 += 5) {
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {
+                const int y = y0 + j;
+                if (y < h) {
+                    const int enter = (j + 4) % 5, leave = j;       // slots of rows y+2 and y-2 (y0 is a multiple of 5)
+                    const size_t ro = (size_t)reflect101(y + 2, h) * w;
+                    const double e0 = row5(cxx, ro, xs), e1 = row5(cxy, ro, xs), e2 = row5(cyy, ro, xs);
+                    const double s0 = __dadd_rn(sum[0], e0), s1 = __dadd_rn(sum[1], e1), s2 = __dadd_rn(sum[2], e2);
+                    sum[0] = __dsub_rn(s0, ring[0][leave]); sum[1] = __dsub_rn(s1, ring[1][leave]); sum[2] = __dsub_rn(s2, ring[2][leave]);
+                    ring[0][enter] = e0; ring[1][enter] = e1; ring[2][enter] = e2;
+                    const float a = __double2float_rn(s0), b = __double2float_rn(s1), c = __double2float_rn(s2);
+                    const float ac = __fadd_rn(a, c);
+                    const float r = __fsub_rn(__fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), __fmul_rn(kf, __fmul_rn(ac, ac)));
+                    R[(size_t)y * w + x] = r;
+                    vmax = fmaxf(vmax, r);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+    if ((threadIdx.x & 31) == 0 && vmax > -INFINITY) atomicMax(&S->max_bits, orderable(vmax));
+}
+
+// step 5a: threshold + 3x3 non-maximum suppression, candidates appended as 64-bit keys
+__global__ void __launch_bounds__(256)
+gftt_candidates_kernel(const float* __restrict__ R, int w, int h, double quality, GfttState* S,
+                       unsigned long long* __restrict__ keys, unsigned capacity)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x + 1, y = blockIdx.y + 1;
+    if (x >= w - 1 || y >= h - 1) return;
+    const float thr = (float)((double)from_orderable(S->max_bits) * quality);
+    const float* c = R + (size_t)y * w + x;
+    const float v = __ldg(c);
+    if (!(v > thr) || v == 0.f) return;
+#pragma unroll
+    for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+            if (dx == 0 && dy == 0) continue;
+            const float n = __ldg(c + dy * w + dx);
+            if ((n > thr ? n : 0.f) > v) return;     // a thresholded neighbour is larger: not a local maximum
+        }
+    const unsigned slot = atomicAdd(&S->n_cand, 1u);
+    if (slot < capacity) keys[slot] = ((unsigned long long)orderable(v) << 32) | (unsigned)(y * w + x);
+}
+
+// step 5b: radix select of the K-th largest key, 8 bits per pass from the top
+__global__ void gftt_hist_kernel(const unsigned long long* __restrict__ keys, GfttState* S, int shift, unsigned capacity)
+{
+    __shared__ unsigned sh[256];
+    sh[threadIdx.x] = 0u;
+    __syncthreads();
+    const unsigned n = min(S->n_cand, capacity);
+    const unsigned long long prefix = S->prefix;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (shift == 56 || (k >> (shift + 8)) == (prefix >> (shift + 8))) atomicAdd(&sh[(unsigned)(k >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (sh[threadIdx.x]) atomicAdd(&S->hist[threadIdx.x], sh[threadIdx.x]);
+}
+
+__global__ void gftt_pick_kernel(GfttState* S, int shift, unsigned max_corners, unsigned capacity)
+{
+    if (threadIdx.x == 0) {
+        const unsigned n = min(S->n_cand, capacity);
+        if (shift == 56) { S->n_out = min(n, max_corners); S->remaining = S->n_out; S->prefix = 0ull; }
+        if (n > max_corners) {
+            unsigned rem = S->remaining, cum = 0u;
+            for (int b = 255; b >= 0; --b) {
+                const unsigned c = S->hist[b];
+                if (cum + c >= rem) { S->prefix |= (unsigned long long)b << shift; S->remaining = rem - cum; break; }
+                cum += c;
+            }
+        }
+    }
+    __syncthreads();
+    S->hist[threadIdx.x] = 0u;
+}
+
+__global__ void gftt_compact_kernel(const unsigned long long* __restrict__ keys, GfttState* S, unsigned long long* __restrict__ sel,
+                                    unsigned max_corners, unsigned capacity)
+{
+    const unsigned n = min(S->n_cand, capacity);
+    const unsigned long long kth = n > max_corners ? S->prefix : 0ull;     // keys are distinct: exactly n_out keys are >= kth
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = keys[i];
+        if (k >= kth) {
+            const unsigned slot = atomicAdd(&S->n_sel, 1u);
+            if (slot < max_corners) sel[slot] = k;
+        }
+    }
+}
+
+// step 5c: rank the survivors by counting (keys are distinct), write (x, y) in cv2's order
+__global__ void gftt_rank_kernel(const unsigned long long* __restrict__ sel, const GfttState* S, int w, float* __restrict__ out_xy,
+                                 int* __restrict__ out_count)
+{
+    const unsigned n = S->n_out;
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = (int)n;
+    for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long k = sel[i];
+        unsigned rank = 0;
+        for (unsigned j = 0; j < n; ++j) rank += sel[j] > k;
+        const unsigned addr = (unsigned)k;
+        out_xy[2 * rank] = (float)(addr % (unsigned)w);
+        out_xy[2 * rank + 1] = (float)(addr / (unsigned)w);
+    }
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+VEL_API size_t vel_good_features_workspace(int32_t width, int32_t height, int32_t max_corners)
+{
+    if (width <= 0 || height <= 0 || max_corners <= 0) return 0;
+    const size_t px = (size_t)width * height;
+    return align256(sizeof(GfttState)) + 4 * align256(px * sizeof(float)) + align256(px * sizeof(unsigned long long)) +
+           align256((size_t)max_corners * sizeof(unsigned long long));
+}
+
+VEL_API int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32_t height, int32_t pitch, int32_t max_corners,
+                                        double quality, int32_t block_size, double k, void* work, size_t work_bytes,
+                                        float* response, float* out_xy, int32_t* out_count, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(img && work && out_xy && out_count, "vel_good_features_harris_u8: NULL argument");
+    VEL_CHECK_ARG(width >= 8 && height >= 8 && pitch >= width, "vel_good_features_harris_u8: image %dx%d (pitch %d) too small", width,
+                  height, pitch);
+    VEL_CHECK_ARG((long long)width * height < (1ll << 31), "vel_good_features_harris_u8: image too large");
+    VEL_CHECK_ARG(max_corners > 0 && max_corners <= 65536, "vel_good_features_harris_u8: max_corners %d outside [1,65536]", max_corners);
+    VEL_CHECK_ARG(quality > 0. && quality < 1., "vel_good_features_harris_u8: quality must be in (0,1)");
+    if (block_size != 5) {
+        vel_set_error("vel_good_features_harris_u8: only blockSize 5 (the reference's value, vidExample.py:110) is implemented");
+        return VEL_ERR_UNSUPPORTED;
+    }
+    VEL_CHECK_ARG(work_bytes >= vel_good_features_workspace(width, height, max_corners), "vel_good_features_harris_u8: workspace too small");
+
+    const size_t px = (size_t)width * height;
+    char* base = static_cast<char*>(work);
+    GfttState* S = reinterpret_cast<GfttState*>(base); base += align256(sizeof(GfttState));
+    float* cxx = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
+    float* cxy = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
+    float* cyy = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
+    float* R = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base); base += align256(px * sizeof(unsigned long long));
+    unsigned long long* sel = reinterpret_cast<unsigned long long*>(base);
+    if (response) R = response;     // caller wants the response plane (float32 [height][width])
+
+    cudaStream_t st = (cudaStream_t)stream;
+    const float k1 = (float)(1.0 / (4.0 * block_size * 255.0)), k0 = 2.f * k1;
+    gftt_reset_kernel<<<1, 256, 0, st>>>(S);
+    harris_cov_kernel<<<dim3((width + 255) / 256, height), 256, 0, st>>>(img, width, height, pitch, k1, k0, (width / 32) * 32, cxx, cxy, cyy);
+    harris_box_response_kernel<<<(width + BOX_THREADS - 1) / BOX_THREADS, BOX_THREADS, 0, st>>>(cxx, cxy, cyy, width, height, (float)k, R, S);
+    const unsigned capacity = (unsigned)px;
+    gftt_candidates_kernel<<<dim3((width - 2 + 255) / 256, height - 2), 256, 0, st>>>(R, width, height, quality, S, keys, capacity);
+    const int sel_grid = 4 * kNumSMs;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        gftt_hist_kernel<<<sel_grid, 256, 0, st>>>(keys, S, shift, capacity);
+        gftt_pick_kernel<<<1, 256, 0, st>>>(S, shift, (unsigned)max_corners, capacity);
+    }
+    gftt_compact_kernel<<<sel_grid, 256, 0, st>>>(keys, S, sel, (unsigned)max_corners, capacity);
+    gftt_rank_kernel<<<(max_corners + 255) / 256, 256, 0, st>>>(sel, S, width, out_xy, out_count);
+    VEL_LAUNCH_CHECK("good-features kernels");
+    return VEL_OK;
+}

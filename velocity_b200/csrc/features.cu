@@ -16,7 +16,7 @@
 //   5. keep R > float(max(R)*quality); 3x3 local maxima inside the 1-px frame; order by value descending, ties by
 //      higher raster address; first maxCorners.  (minDistance = 0 as in the reference: no spacing filter.)
 //
-// HBM streaming: the frame is read once (cov kernel), cov/R planes are written and read once.  Every float step uses
+// HBM streaming: the frame is read once (cov kernel); cov, row-sum and R planes are written and read once.  Every float step uses
 // explicit round-to-nearest intrinsics so nothing is contracted differently from the oracle.  Selection is
 // deterministic: candidates are appended with an atomic counter (arbitrary order), then the K-th largest 64-bit key
 // (value bits << 32 | address, all distinct) is found by an 8-pass radix select and the survivors are ranked by
@@ -82,55 +82,87 @@ harris_cov_kernel(const uint8_t* __restrict__ img, int w, int h, int pitch, floa
     cyy[o] = __fmul_rn(dy, dy);
 }
 
-// steps 3-4: one thread per column, walking down the rows with cv2's running float64 column sums
-constexpr int BOX_THREADS = 64;
-
-__device__ __forceinline__ double row5(const float* __restrict__ plane, size_t row_off, const int (&xs)[5])
+// step 3a: 5-tap row sums in float64, left to right (cv2's RowSum), one thread per pixel
+__global__ void __launch_bounds__(256)
+harris_rowsum_kernel(const float* __restrict__ cxx, const float* __restrict__ cxy, const float* __restrict__ cyy, int w, int h,
+                     double* __restrict__ sxx, double* __restrict__ sxy, double* __restrict__ syy)
 {
-    const float* r = plane + row_off;
-    double s = __dadd_rn((double)__ldg(r + xs[0]), (double)__ldg(r + xs[1]));
-    s = __dadd_rn(s, (double)__ldg(r + xs[2]));
-    s = __dadd_rn(s, (double)__ldg(r + xs[3]));
-    return __dadd_rn(s, (double)__ldg(r + xs[4]));
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    int xs[5];
+#pragma unroll
+    for (int d = 0; d < 5; ++d) xs[d] = reflect101(x + d - 2, w);
+    const size_t ro = (size_t)y * w;
+    const float* planes[3] = {cxx + ro, cxy + ro, cyy + ro};
+    double* outs[3] = {sxx, sxy, syy};
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        double s = __dadd_rn((double)__ldg(planes[c] + xs[0]), (double)__ldg(planes[c] + xs[1]));
+        s = __dadd_rn(s, (double)__ldg(planes[c] + xs[2]));
+        s = __dadd_rn(s, (double)__ldg(planes[c] + xs[3]));
+        outs[c][ro + x] = __dadd_rn(s, (double)__ldg(planes[c] + xs[4]));
+    }
 }
 
-__global__ void __launch_bounds__(BOX_THREADS)
-harris_box_response_kernel(const float* __restrict__ cxx, const float* __restrict__ cxy, const float* __restrict__ cyy,
-                           int w, int h, float kf, float* __restrict__ R, GfttState* S)
+// steps 3b-4: cv2's running float64 column sums.  One thread per column walks down the rows (the recurrence is what
+// makes the result independent of nothing but cv2's own order); the row sums of the NEXT five rows are requested
+// before the current five are consumed, so each batch of five steps exposes one memory latency.
+constexpr int SCAN_THREADS = 32;
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+harris_colscan_response_kernel(const double* __restrict__ sxx, const double* __restrict__ sxy, const double* __restrict__ syy,
+                               int w, int h, float kf, float* __restrict__ R, GfttState* S)
 {
-    const int x = blockIdx.x * BOX_THREADS + threadIdx.x;
+    const int x = blockIdx.x * SCAN_THREADS + threadIdx.x;
     float vmax = -INFINITY;
     if (x < w) {
-        int xs[5];
-#pragma unroll
-        for (int d = 0; d < 5; ++d) xs[d] = reflect101(x + d - 2, w);
+        const double* pl[3] = {sxx + x, sxy + x, syy + x};
         double ring[3][5];        // row sums of the five rows inside the window; slot = (row + 2) % 5
         double sum[3] = {0., 0., 0.};
 #pragma unroll
         for (int i = -2; i <= 1; ++i) {
             const size_t ro = (size_t)reflect101(i, h) * w;
-            ring[0][i + 2] = row5(cxx, ro, xs); ring[1][i + 2] = row5(cxy, ro, xs); ring[2][i + 2] = row5(cyy, ro, xs);
 #pragma unroll
-            for (int c = 0; c < 3; ++c) sum[c] = __dadd_rn(sum[c], ring[c][i + 2]);
+            for (int c = 0; c < 3; ++c) { ring[c][i + 2] = __ldg(pl[c] + ro); sum[c] = __dadd_rn(sum[c], ring[c][i + 2]); }
+        }
+        double nxt[3][5];         // entering rows y0+2 .. y0+6 of the current batch
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            const size_t ro = (size_t)reflect101(min(j + 2, h + 1), h) * w;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) nxt[c][j] = __ldg(pl[c] + ro);
         }
         for (int y0 = 0; y0 < h; y0 += 5) {
+            double nxt2[3][5];
+#pragma unroll
+            for (int j = 0; j < 5; ++j) {      // rows (y0 + 5) + j + 2, clamped into the reflect-padded range (unused beyond it)
+                const size_t ro = (size_t)reflect101(min(y0 + 7 + j, h + 1), h) * w;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nxt2[c][j] = __ldg(pl[c] + ro);
+            }
 #pragma unroll
             for (int j = 0; j < 5; ++j) {
                 const int y = y0 + j;
                 if (y < h) {
                     const int enter = (j + 4) % 5, leave = j;       // slots of rows y+2 and y-2 (y0 is a multiple of 5)
-                    const size_t ro = (size_t)reflect101(y + 2, h) * w;
-                    const double e0 = row5(cxx, ro, xs), e1 = row5(cxy, ro, xs), e2 = row5(cyy, ro, xs);
-                    const double s0 = __dadd_rn(sum[0], e0), s1 = __dadd_rn(sum[1], e1), s2 = __dadd_rn(sum[2], e2);
-                    sum[0] = __dsub_rn(s0, ring[0][leave]); sum[1] = __dsub_rn(s1, ring[1][leave]); sum[2] = __dsub_rn(s2, ring[2][leave]);
-                    ring[0][enter] = e0; ring[1][enter] = e1; ring[2][enter] = e2;
-                    const float a = __double2float_rn(s0), b = __double2float_rn(s1), c = __double2float_rn(s2);
+                    double s[3];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        s[c] = __dadd_rn(sum[c], nxt[c][j]);
+                        sum[c] = __dsub_rn(s[c], ring[c][leave]);
+                        ring[c][enter] = nxt[c][j];
+                    }
+                    const float a = __double2float_rn(s[0]), b = __double2float_rn(s[1]), c = __double2float_rn(s[2]);
                     const float ac = __fadd_rn(a, c);
                     const float r = __fsub_rn(__fsub_rn(__fmul_rn(a, c), __fmul_rn(b, b)), __fmul_rn(kf, __fmul_rn(ac, ac)));
                     R[(size_t)y * w + x] = r;
                     vmax = fmaxf(vmax, r);
                 }
             }
+#pragma unroll
+            for (int j = 0; j < 5; ++j)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) nxt[c][j] = nxt2[c][j];
         }
     }
 #pragma unroll
@@ -233,7 +265,8 @@ VEL_API size_t vel_good_features_workspace(int32_t width, int32_t height, int32_
 {
     if (width <= 0 || height <= 0 || max_corners <= 0) return 0;
     const size_t px = (size_t)width * height;
-    return align256(sizeof(GfttState)) + 4 * align256(px * sizeof(float)) + align256(px * sizeof(unsigned long long)) +
+    // control block | 3 cov planes + R (float) | 3 row-sum planes (double; the candidate keys reuse the first) | survivors
+    return align256(sizeof(GfttState)) + 4 * align256(px * sizeof(float)) + 3 * align256(px * sizeof(double)) +
            align256((size_t)max_corners * sizeof(unsigned long long));
 }
 
@@ -260,7 +293,10 @@ VEL_API int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32
     float* cxy = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
     float* cyy = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
     float* R = reinterpret_cast<float*>(base); base += align256(px * sizeof(float));
-    unsigned long long* keys = reinterpret_cast<unsigned long long*>(base); base += align256(px * sizeof(unsigned long long));
+    double* sxx = reinterpret_cast<double*>(base); base += align256(px * sizeof(double));
+    double* sxy = reinterpret_cast<double*>(base); base += align256(px * sizeof(double));
+    double* syy = reinterpret_cast<double*>(base); base += align256(px * sizeof(double));
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(sxx);     // the row sums are dead once R exists
     unsigned long long* sel = reinterpret_cast<unsigned long long*>(base);
     if (response) R = response;     // caller wants the response plane (float32 [height][width])
 
@@ -268,7 +304,8 @@ VEL_API int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32
     const float k1 = (float)(1.0 / (4.0 * block_size * 255.0)), k0 = 2.f * k1;
     gftt_reset_kernel<<<1, 256, 0, st>>>(S);
     harris_cov_kernel<<<dim3((width + 255) / 256, height), 256, 0, st>>>(img, width, height, pitch, k1, k0, (width / 32) * 32, cxx, cxy, cyy);
-    harris_box_response_kernel<<<(width + BOX_THREADS - 1) / BOX_THREADS, BOX_THREADS, 0, st>>>(cxx, cxy, cyy, width, height, (float)k, R, S);
+    harris_rowsum_kernel<<<dim3((width + 255) / 256, height), 256, 0, st>>>(cxx, cxy, cyy, width, height, sxx, sxy, syy);
+    harris_colscan_response_kernel<<<(width + SCAN_THREADS - 1) / SCAN_THREADS, SCAN_THREADS, 0, st>>>(sxx, sxy, syy, width, height, (float)k, R, S);
     const unsigned capacity = (unsigned)px;
     gftt_candidates_kernel<<<dim3((width - 2 + 255) / 256, height - 2), 256, 0, st>>>(R, width, height, quality, S, keys, capacity);
     const int sel_grid = 4 * kNumSMs;

@@ -64,10 +64,16 @@ def oracle_modules():
         x, b0, _ = sfm_oracle.solve_last_translation(K, P, B, vg, ii)
         return x, b0
 
+    def gftt(roi, n, q, min_distance, blockSize=5, useHarrisDetector=True):
+        from oracle import gftt_oracle
+
+        assert min_distance == 0 and blockSize == 5 and useHarrisDetector
+        return gftt_oracle.good_features_to_track(roi, n, q).reshape(-1, 1, 2)
+
     klt = types.SimpleNamespace(KLTmain=klt_oracle.klt_main)
     nls = types.SimpleNamespace(estimateWorldCameraPose=estimateWorldCameraPose)
     msv = types.SimpleNamespace(fcnMSV1_t=fcnMSV1_t)
-    return klt, nls, msv
+    return klt, nls, msv, gftt
 
 
 @pytest.mark.parametrize("name", CLIPS)

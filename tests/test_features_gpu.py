@@ -66,3 +66,17 @@ def test_good_features_full_frame_and_views(cuda):
         features.goodFeaturesToTrack(im, 10, 0.01, 5, blockSize=5, useHarrisDetector=True)
     with pytest.raises(NotImplementedError):
         features.goodFeaturesToTrack(im, 10, 0.01, 0, blockSize=3, useHarrisDetector=True)
+
+
+def test_good_features_against_cv2_itself(cuda):
+    """The detector against opencv-python run on THIS host (when importable), at the BASELINE frame size and on the
+    plate ROI geometry of vidExample.py:109 (width not a multiple of 16): same corners, same order."""
+    cv2 = pytest.importorskip("cv2")
+    from velocity_b200 import features, synth
+
+    frames, _ = synth.plane_sequence(1, h=1080, w=1920, seed=9, Z0=40.0)
+    for im in (frames[0], np.ascontiguousarray(frames[0][40:1041, 260:1661])):
+        for n, q in ((1000, 0.01), (4096, 0.001)):
+            ref = cv2.goodFeaturesToTrack(im, n, q, 0, blockSize=5, useHarrisDetector=True)
+            out = features.goodFeaturesToTrack(im, n, q, 0, blockSize=5, useHarrisDetector=True)
+            assert out.shape == ref.shape and np.array_equal(out, ref), (im.shape, n, q)

@@ -176,6 +176,29 @@ def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
     assert np.array_equal(v, ov) and np.array_equal(p2, o2)
 
 
+def test_full_size_against_cv2_itself(cuda):
+    """BASELINE config 2 at full size against the reference's own arithmetic provider run on THIS host
+    (opencv-python, when importable): forward-backward masks identical except where cv2's float32-lane
+    accumulation flips a stop criterion (<= 0.7 % of points), points of commonly valid
+    tracks within the stated tolerance, on a rendered consecutive pair of the synthetic sequence."""
+    cv2 = pytest.importorskip("cv2")
+    from velocity_b200 import KLT, synth
+
+    frames, _ = synth.plane_sequence(2, h=1080, w=1920, seed=1234, Z0=40.0)
+    pts = synth.harris_tracks(frames[0], 4096)
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(frames[0], frames[1], pts, None, fbt=1.0, **lk)
+    q2, st, qerr = cv2.calcOpticalFlowPyrLK(frames[0], frames[1], pts, None, **lk)
+    q1, st1, _ = cv2.calcOpticalFlowPyrLK(frames[1], frames[0], q2, None, **lk)
+    d = pts - q1
+    qv = st.ravel().astype(bool) & st1.ravel().astype(bool) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < np.float32(1.0))
+    assert (v != qv).mean() <= 0.007
+    both = v & qv
+    assert both.mean() > 0.98
+    assert np.abs(p2 - q2)[both].max() <= LK_POINT_TOL_PX
+    assert np.abs(err - qerr)[both].max() <= LK_ERR_TOL
+
+
 def test_edge_cases_empty_single_and_errors(cuda):
     """Empty and single-point inputs, points far outside the frame (status 0, no crash), argument
     errors surfaced as RuntimeError with the C ABI's message; a point set on a pure-constant image

@@ -166,6 +166,24 @@ def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
                 ok = oerr.ravel() != 0
                 assert np.array_equal(err[ok], oerr[ok]), (impl, ha.shape, fbt)
             assert ov.any() and not ov.all()     # the case mixes tracked, lost and never-inside points
+    # the mid-size-window kernel (51x51 lk_fine, cv2's default 21x21, a rectangular one): word path vs byte path vs oracle
+    a, b, ha, hb = cases[2]
+    h, w = ha.shape
+    pts = np.concatenate([synth.harris_tracks(np.ascontiguousarray(ha), 60, border=2),
+                          np.stack([rng.uniform(-20, w + 20, 40), rng.uniform(-20, h + 20, 40)], 1)]).astype(np.float32)
+    for win, lvl in (((51, 51), 0), ((21, 21), 2), ((19, 33), 1)):
+        lkw = dict(winSize=win, maxLevel=lvl, criteria=(3, 20, 0.003))
+        o2, ov, oerr = KO.lk_forward_backward(np.ascontiguousarray(ha), np.ascontiguousarray(hb), pts, fbt=0.5, **lkw)
+        for impl in ("default", "bytes"):
+            if impl == "default":
+                monkeypatch.delenv("VEL_LK_W15", raising=False)
+            else:
+                monkeypatch.setenv("VEL_LK_W15", impl)
+            p2, v, err = KLT.cv2calcOpticalFlowPyrLK(a, b, pts, None, fbt=0.5, **lkw)
+            ok = oerr.ravel() != 0
+            assert np.array_equal(v, ov) and np.array_equal(p2, o2) and np.array_equal(err[ok], oerr[ok]), (win, impl)
+        monkeypatch.delenv("VEL_LK_W15", raising=False)
+        assert ov.any() and not ov.all()
     # smallest legal top level: 16 px wide / high
     tiny0 = synth.texture(64, 64, 3)
     tiny1 = np.roll(tiny0, (1, 1), (0, 1))

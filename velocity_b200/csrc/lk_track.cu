@@ -39,6 +39,7 @@ struct LkArgs {
     float* out; uint8_t* status; float* err; float* back;
     int win_w, win_h, max_count;
     float eps2, min_eig, fbt;
+    int force_bytes;   // VEL_LK_W15=bytes: byte-gather paths only (cross-check of the word-gather paths)
 };
 
 struct Img {
@@ -669,12 +670,15 @@ __device__ __forceinline__ unsigned ldg_u32(const uint8_t* p) { return __ldg(rei
 
 // =====================================================================================================
 // Column-streaming path for mid-size windows (16 <= win_w <= COLS-1, win_h <= 63; the reference's
-// 51x51 lk_fine, cv2's default 21x21).  One CTA of 128 threads per point: thread = (column slot c,
-// row group g).  Each thread walks DOWN its column: the two J bytes of the previous row stay in
-// registers, so a pixel costs 2 byte loads + 4 IMAD + shift + 2 IMAD against the template held in
-// shared memory (I stored pre-folded as 256 - (I << 9), Ix/Iy packed as short2).  Per-thread sums
-// fit int32 (<= 32 rows x 2^25), the CTA-wide sums are exact int64.  Same arithmetic as every
-// other path => bit-identical results.
+// 51x51 lk_fine, cv2's default 21x21).  One CTA of 128 threads per point; the template lives in shared
+// memory (I pre-folded as 256 - (I << 9), Ix, Iy as int rows of 4-pixel groups).  The template is built with
+// thread = (column slot c, row group g) walking DOWN its column (two bytes of the previous row stay in
+// registers).  Search iterations use thread = (4-column group, row group): per row two aligned word loads
+// re-aligned by funnel shifts, per pixel two DP2A (bilinear sample minus template) + two IMAD (b sums),
+// template operands by 128-bit shared loads -- ~7 instructions per pixel instead of ~11.5 for the byte
+// walk, which remains for odd pitches and windows hanging over the frame border.  Per-thread sums fit
+// int32 (<= 8 rows x 4 pixels x 2^25), the CTA-wide sums are exact int64.  Same arithmetic as every other
+// path => bit-identical results.
 template <int COLS>
 __global__ void __launch_bounds__(128)
 lk_track_cols_kernel(const LkArgs A)
@@ -685,18 +689,29 @@ lk_track_cols_kernel(const LkArgs A)
     const int pair = blockIdx.y, pt = blockIdx.x;
     const int ww = A.win_w, wh = A.win_h, npx = ww * wh;
     const int tw = ww + 1, th = wh + 1;
+    const int wp = (ww + 3) & ~3;                       // template row pitch: 4-pixel groups are 16-byte aligned
     const size_t bytes_D = ((size_t)tw * th * 4 + 15) & ~(size_t)15;
-    const size_t bytes_G = ((size_t)npx * 4 + 15) & ~(size_t)15;
+    const size_t bytes_T = (size_t)wp * wh * 4;
     short2* sD = reinterpret_cast<short2*>(smem_raw);
-    short2* sG = reinterpret_cast<short2*>(smem_raw + bytes_D);
-    int* sI = reinterpret_cast<int*>(smem_raw + bytes_D + bytes_G);
-    long long* red = reinterpret_cast<long long*>(smem_raw + bytes_D + 2 * bytes_G);
+    int* sI = reinterpret_cast<int*>(smem_raw + bytes_D);                 // 256 - (I << 9)
+    int* sGx = reinterpret_cast<int*>(smem_raw + bytes_D + bytes_T);
+    int* sGy = reinterpret_cast<int*>(smem_raw + bytes_D + 2 * bytes_T);
+    long long* red = reinterpret_cast<long long*>(smem_raw + bytes_D + 3 * bytes_T);
+    for (int i = tid; i < wp * wh; i += NT) { sGx[i] = 0; sGy[i] = 0; sI[i] = 0; }   // padding columns stay zero for good
     int parity = 0;
 
     const int c = tid % COLS, g = tid / COLS;
     const int rows_per = (wh + NG - 1) / NG;
     const int r0 = g * rows_per, r1 = min(wh, r0 + rows_per);
     const bool col_active = c < ww && r0 < r1;
+    // search iterations: thread = (4-column group cgw, row group rgw), aligned word gathers + DP2A (pitch % 4 == 0)
+    const int ncg = wp >> 2, nrg = NT / ncg;
+    const int cgw = tid % ncg, rgw = tid / ncg;
+    const int rows_w = (wh + nrg - 1) / nrg;
+    const int wr0 = rgw * rows_w, wr1 = min(wh, wr0 + rows_w);
+    const bool w_active = rgw < nrg && wr0 < wr1;
+    bool words = !A.force_bytes && (A.prev_pitch % 4 == 0) && (A.next_pitch % 4 == 0);
+    for (int l = 1; l <= A.lv.max_level; ++l) words = words && (A.lv.pitch[l] % 4 == 0);
 
     const float half_x = fmul((float)(ww - 1), 0.5f), half_y = fmul((float)(wh - 1), 0.5f);
     const float FLT_SCALE = 1.f / 1048576.f;
@@ -783,8 +798,9 @@ lk_track_cols_kernel(const LkArgs A)
                     const short2 d00 = sD[y * tw + c], d01 = sD[y * tw + c + 1], d10 = sD[(y + 1) * tw + c], d11 = sD[(y + 1) * tw + c + 1];
                     const int ix = (d00.x * w.w00 + d01.x * w.w01 + d10.x * w.w10 + d11.x * w.w11 + (1 << 13)) >> 14;
                     const int iy = (d00.y * w.w00 + d01.y * w.w01 + d10.y * w.w10 + d11.y * w.w11 + (1 << 13)) >> 14;
-                    sI[y * ww + c] = (1 << 8) - (ival << 9);
-                    sG[y * ww + c] = make_short2((short)ix, (short)iy);
+                    sI[y * wp + c] = (1 << 8) - (ival << 9);
+                    sGx[y * wp + c] = ix;
+                    sGy[y * wp + c] = iy;
                     a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;   // <= 32 rows x 2^24: fits int32
                     i00 = i10; i01 = i11;
                 }
@@ -819,11 +835,60 @@ lk_track_cols_kernel(const LkArgs A)
                 }
                 w = bilin_weights(fsub(qx, (float)inx), fsub(qy, (float)iny));
                 int sb1 = 0, sb2 = 0, se = 0;
-                if (col_active) {
-                    const bool inside = inx >= 0 && iny >= 0 && inx + ww < J.w && iny + wh < J.h;
-                    const unsigned pitch = (unsigned)J.pitch;
-                    const int* pI = sI + r0 * ww + c;
-                    const short2* pG = sG + r0 * ww + c;
+                const bool inside = inx >= 0 && iny >= 0 && inx + ww < J.w && iny + wh < J.h;
+                const unsigned pitch = (unsigned)J.pitch;
+                if (words && inside) {
+                    if (w_active) {
+                        const int W0 = (int)__byte_perm((unsigned)w.w00, (unsigned)w.w01, 0x5410);
+                        const int W1 = (int)__byte_perm((unsigned)w.w10, (unsigned)w.w11, 0x5410);
+                        const unsigned off = (unsigned)(iny + wr0) * pitch + (unsigned)(inx + 4 * cgw);
+                        const unsigned mis = ((unsigned)(size_t)J.p + off) & 3u, sh = mis * 8u;
+                        const uint8_t* r = J.p + (int)(off - mis);
+                        // the second word starts at footprint column 4cgw + 4 - mis: beyond column ww nothing active needs it
+                        const bool skip_hi = 4 * cgw + 4 - (int)mis > ww;
+                        // all rows of the thread are requested before the first is consumed (this kernel's shared-memory
+                        // footprint leaves no L1: every gather is an L2 round trip, exposed once instead of once per row)
+                        constexpr int MAXR = 8;                      // rows_w <= ceil(63 / 8)
+                        unsigned lo[MAXR + 1], hi[MAXR + 1];
+#pragma unroll
+                        for (int q = 0; q <= MAXR; ++q) {
+                            lo[q] = 0; hi[q] = 0;
+                            if (wr0 + q <= wr1) {
+                                lo[q] = ldg_u32(r + q * pitch);
+                                hi[q] = lo[q];
+                                if (!skip_hi) hi[q] = ldg_u32(r + q * pitch + 4);
+                            }
+                        }
+                        const int o0 = wr0 * wp + 4 * cgw;
+                        const int4* pI = reinterpret_cast<const int4*>(sI + o0);
+                        const int4* pX = reinterpret_cast<const int4*>(sGx + o0);
+                        const int4* pY = reinterpret_cast<const int4*>(sGy + o0);
+                        const int nact = min(4, ww - 4 * cgw);      // active pixels of this group (the padding has Ix = Iy = 0)
+                        unsigned t0 = __funnelshift_r(lo[0], hi[0], sh), t1 = __funnelshift_rc(lo[0], hi[0], sh + 8u);
+#pragma unroll
+                        for (int q = 0; q < MAXR; ++q) {
+                            if (wr0 + q < wr1) {
+                                const unsigned b0 = __funnelshift_r(lo[q + 1], hi[q + 1], sh), b1 = __funnelshift_rc(lo[q + 1], hi[q + 1], sh + 8u);
+                                const int4 ti = pI[q * (wp >> 2)];
+                                const int d0 = dp2a_lo(W1, b0, dp2a_lo(W0, t0, ti.x)) >> 9;
+                                const int d1 = dp2a_lo(W1, b1, dp2a_lo(W0, t1, ti.y)) >> 9;
+                                const int d2 = dp2a_hi(W1, b0, dp2a_hi(W0, t0, ti.z)) >> 9;
+                                const int d3 = dp2a_hi(W1, b1, dp2a_hi(W0, t1, ti.w)) >> 9;
+                                if (final_eval) {
+                                    se += abs(d0) + (nact > 1 ? abs(d1) : 0) + (nact > 2 ? abs(d2) : 0) + (nact > 3 ? abs(d3) : 0);
+                                } else {
+                                    const int4 gx = pX[q * (wp >> 2)], gy = pY[q * (wp >> 2)];
+                                    sb1 += d0 * gx.x + d1 * gx.y + d2 * gx.z + d3 * gx.w;
+                                    sb2 += d0 * gy.x + d1 * gy.y + d2 * gy.z + d3 * gy.w;
+                                }
+                                t0 = b0; t1 = b1;
+                            }
+                        }
+                    }
+                } else if (col_active) {
+                    const int* pI = sI + r0 * wp + c;
+                    const int* pX = sGx + r0 * wp + c;
+                    const int* pY = sGy + r0 * wp + c;
                     if (inside) {
                         const uint8_t* p = J.p + ((unsigned)(iny + r0) * pitch + (unsigned)(inx + c));
                         int a = __ldg(p), b = __ldg(p + 1);
@@ -832,9 +897,8 @@ lk_track_cols_kernel(const LkArgs A)
                             p += pitch;
                             const int an = __ldg(p), bn = __ldg(p + 1);
                             const int diff = (a * w.w00 + b * w.w01 + an * w.w10 + bn * w.w11 + *pI) >> 9;
-                            const short2 gg = *pG;
-                            sb1 += diff * (int)gg.x; sb2 += diff * (int)gg.y; se += abs(diff);
-                            a = an; b = bn; pI += ww; pG += ww;
+                            sb1 += diff * *pX; sb2 += diff * *pY; se += abs(diff);
+                            a = an; b = bn; pI += wp; pX += wp; pY += wp;
                         }
                     } else {
                         const unsigned x0 = reflect_safe(inx + c, J.w), x1 = reflect_safe(inx + c + 1, J.w);
@@ -844,9 +908,8 @@ lk_track_cols_kernel(const LkArgs A)
                             ry = reflect_safe(iny + y + 1, J.h) * pitch;
                             const int an = __ldg(J.p + ry + x0), bn = __ldg(J.p + ry + x1);
                             const int diff = (a * w.w00 + b * w.w01 + an * w.w10 + bn * w.w11 + *pI) >> 9;
-                            const short2 gg = *pG;
-                            sb1 += diff * (int)gg.x; sb2 += diff * (int)gg.y; se += abs(diff);
-                            a = an; b = bn; pI += ww; pG += ww;
+                            sb1 += diff * *pX; sb2 += diff * *pY; se += abs(diff);
+                            a = an; b = bn; pI += wp; pX += wp; pY += wp;
                         }
                     }
                 }
@@ -898,8 +961,8 @@ lk_track_cols_kernel(const LkArgs A)
 
 size_t cols_smem_bytes(int win_w, int win_h)
 {
-    const size_t npx = (size_t)win_w * win_h, ntile = (size_t)(win_w + 1) * (win_h + 1);
-    return ((ntile * 4 + 15) & ~(size_t)15) + 2 * ((npx * 4 + 15) & ~(size_t)15) + (size_t)2 * 4 * 3 * sizeof(long long);
+    const size_t ntile = (size_t)(win_w + 1) * (win_h + 1), wp = (size_t)((win_w + 3) & ~3);
+    return ((ntile * 4 + 15) & ~(size_t)15) + 3 * wp * win_h * 4 + (size_t)2 * 4 * 3 * sizeof(long long);
 }
 
 size_t group_smem_bytes(int win_w, int win_h, int nt)
@@ -950,14 +1013,16 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
     A.min_eig = params->min_eig_threshold;
     A.fbt = params->fb_threshold;
 
+    const char* force = getenv("VEL_LK_W15");
+    A.force_bytes = (force && strcmp(force, "bytes") == 0) ? 1 : 0;
+
     cudaStream_t st = (cudaStream_t)stream;
     if (ww == W15 && wh == W15) {
         // word-gathering kernel (two points per warp): needs every row pitch to be a multiple of 4 bytes;
         // VEL_LK_W15=bytes forces the byte-gather kernel (kept for odd pitches and as an independent cross-check)
         bool words = (prev_pitch % 4 == 0) && (next_pitch % 4 == 0);
         for (int l = 1; l <= layout->max_level; ++l) words = words && (layout->pitch[l] % 4 == 0);
-        const char* force = getenv("VEL_LK_W15");
-        if (force && strcmp(force, "bytes") == 0) words = false;
+        if (A.force_bytes) words = false;
         if (words) {
             dim3 grid((npts + 2 * WH_WARPS - 1) / (2 * WH_WARPS), npairs);
             lk_track_w15h_kernel<<<grid, 32 * WH_WARPS, 0, st>>>(A);

@@ -194,6 +194,21 @@ def test_lk_w15_word_kernel_equals_byte_kernel_and_oracle(cuda, monkeypatch):
     assert np.array_equal(v, ov) and np.array_equal(p2, o2)
 
 
+def test_lk_randomized_parameters_match_oracle(cuda):
+    """Seeded sweep over the parameter space of cv2.calcOpticalFlowPyrLK as the wrapper exposes it (util.lk_sweep_cases):
+    status masks, points and errors equal the oracle bit for bit (the oracle itself is checked against cv2 on the same
+    sweep by tests/test_oracle_cv.py)."""
+    from oracle import klt_oracle as KO
+    from util import lk_sweep_cases
+    from velocity_b200 import KLT
+
+    for k, im0, im1, pts, lk, fbt in lk_sweep_cases():
+        p2, v, err = KLT.cv2calcOpticalFlowPyrLK(im0, im1, pts, None, fbt=fbt, **lk)
+        o2, ov, oerr = KO.lk_forward_backward(im0, im1, pts, fbt=fbt, **lk)
+        ok = oerr.ravel() != 0
+        assert np.array_equal(v, ov) and np.array_equal(p2, o2) and np.array_equal(err[ok], oerr[ok]), (k, lk, fbt)
+
+
 def test_full_size_against_cv2_itself(cuda):
     """BASELINE config 2 at full size against the reference's own arithmetic provider run on THIS host
     (opencv-python, when importable): forward-backward masks identical except where cv2's float32-lane

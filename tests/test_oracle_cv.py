@@ -72,3 +72,23 @@ def test_empty_and_single_point():
 def test_bgr2gray_against_reference():
     g = golden("ingest_bgr")
     assert np.array_equal(O.bgr2gray(g["bgr"]), g["gray"])
+
+
+def test_oracle_parameter_sweep_against_cv2_itself():
+    """The oracle against the reference's arithmetic provider run on THIS host (opencv-python, when importable) over a
+    seeded parameter sweep: forward-backward masks identical, points within the stated tolerance."""
+    cv2 = pytest.importorskip("cv2")
+    from util import lk_sweep_cases
+
+    for k, im0, im1, pts, lk, fbt in lk_sweep_cases():
+        o2, ov, _ = KO.lk_forward_backward(im0, im1, pts, fbt=fbt, **lk)
+        q2, st, _ = cv2.calcOpticalFlowPyrLK(im0, im1, pts, None, **lk)
+        qv = st.ravel().astype(bool)
+        if fbt is not None:
+            q1, st1, _ = cv2.calcOpticalFlowPyrLK(im1, im0, q2, None, **lk)
+            d = pts - q1
+            qv = qv & st1.ravel().astype(bool) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < np.float32(fbt))
+        assert np.array_equal(ov, qv), (k, lk, fbt)
+        both = ov & qv
+        if both.any():
+            assert np.abs(o2 - q2)[both].max() <= LK_POINT_TOL_PX, (k, lk, fbt)

@@ -32,3 +32,25 @@ PRIM_CASES = ["prim_even", "prim_odd", "prim_tiny"]
 # Tolerances (SURVEY.md 8(c) "Tolerance policy")
 LK_POINT_TOL_PX = 2e-3   # vs cv2 (golden): cv2 accumulates the 2x2 system in float32 SIMD lanes
 LK_ERR_TOL = 1e-2
+
+
+def lk_sweep_cases():
+    """Seeded sweep over cv2.calcOpticalFlowPyrLK's parameter space (window, levels, iteration cap, eps, minimum
+    eigenvalue threshold, forward-backward threshold) on small-shift / large-shift / unrelated pairs, with points
+    anywhere (also outside the frame).  Shared by the CPU test (oracle vs cv2) and the GPU test (CUDA vs oracle)."""
+    from velocity_b200 import synth
+
+    rng = np.random.default_rng(2024)
+    base = synth.texture(260, 372, 31)
+    pairs = [(base, np.roll(base, (1, -2), (0, 1))), (base, np.roll(base, (-7, 9), (0, 1))), (base, synth.texture(260, 372, 32))]
+    wins = [(15, 15), (15, 15), (15, 15), (21, 21), (9, 13), (33, 17)]
+    for k in range(18):
+        im0, im1 = pairs[k % 3]
+        lk = dict(winSize=wins[k % len(wins)], maxLevel=int(rng.integers(0, 5)),
+                  criteria=(3, int(rng.choice([1, 3, 10, 30])), float(rng.choice([0.5, 0.03, 0.001]))),
+                  minEigThreshold=float(rng.choice([1e-4, 1e-4, 3e-3])))
+        fbt = [None, 0.2, 2.0][int(rng.integers(0, 3))]
+        h, w = im0.shape
+        pts = np.concatenate([synth.harris_tracks(im0, 120, border=3),
+                              np.stack([rng.uniform(-20, w + 20, 60), rng.uniform(-20, h + 20, 60)], 1)]).astype(np.float32)
+        yield k, im0, im1, pts, lk, fbt

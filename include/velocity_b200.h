@@ -95,6 +95,14 @@ int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32_t heigh
                                 double quality, int32_t block_size, double k, void* work, size_t work_bytes, float* response,
                                 float* out_xy, int32_t* out_count, vel_stream_t stream);
 
+/* cv2.cornerSubPix(im, p, (win_w, win_h), (-1,-1), criteria) of vidExample.py:113-115 (CV_8UC1 image): refines npts
+ * (x, y) float32 corners IN PLACE (DEVICE), in OpenCV 4.13's arithmetic (restated in oracle/velocity_oracle.c,
+ * orc_corner_subpix_u8): bit-identical to cv2, including corners whose sampling window hangs over the frame border.
+ * max_iters / eps are the criteria's COUNT / EPS members (clamped like cv2: 1..100, eps >= 0; pass 100 / 0 for an
+ * absent member). */
+int vel_corner_subpix_u8(const uint8_t* img, int32_t width, int32_t height, int32_t pitch, float* pts, int32_t npts, int32_t win_w,
+                         int32_t win_h, int32_t max_iters, double eps, vel_stream_t stream);
+
 /* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
  * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
  * forward result fused in the same kernel with

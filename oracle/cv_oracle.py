@@ -152,3 +152,19 @@ def bgr2gray(bgr):
     out = np.empty((h, w), np.uint8)
     lib().orc_bgr2gray_u8(_u8(bgr), w, h, 3 * w, _u8(out), w)
     return out
+
+
+def cornerSubPix(im, corners, winSize=(5, 5), zeroZone=(-1, -1), criteria=(3, 100, 0.001), nthreads=0):
+    """cv2.cornerSubPix as vidExample.py:113-115 calls it (zeroZone (-1,-1)); returns refined float32 [n, 2]."""
+    assert tuple(zeroZone) == (-1, -1)
+    im, pitch = _rowmajor_u8(im)
+    h, w = im.shape
+    pts = np.ascontiguousarray(np.asarray(corners, np.float32).reshape(-1, 2)).copy()
+    ctype, count, eps = criteria
+    L = lib()
+    L.orc_corner_subpix_u8.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.c_int, C.c_int,
+                                       C.c_int, C.c_int, C.c_double]
+    L.orc_corner_subpix_u8.restype = None
+    L.orc_corner_subpix_u8(_u8(im), w, h, pitch, _f32(pts), pts.shape[0], int(winSize[0]), int(winSize[1]),
+                           int(count) if (ctype & 1) else 100, float(eps) if (ctype & 2) else 0.0)
+    return pts

@@ -406,4 +406,110 @@ ORC_API void orc_bgr2gray_u8(const uint8_t* bgr, int w, int h, int bpitch, uint8
         }
 }
 
+/* ---- cv2.cornerSubPix(im, p, (5,5), (-1,-1), criteria) (vidExample.py:113-115), CV_8UC1 input ---------------------------
+ * Arithmetic of OpenCV 4.13 (imgproc cornersubpix.cpp + getRectSubPix 8U->32F), pinned by black-box comparison: 36k
+ * points on six image sizes and three termination criteria reproduce cv2 bit for bit (tests/golden/subpix.npz holds a
+ * committed subset).  Patch elements:
+ *   both rows and both columns inside the frame : (p00*a11 + p01*a12) + (p10*a21 + p11*a22), float32, unfused
+ *   row beyond the frame (replicated), columns inside : fma(p01, a, p00*(1-a))
+ *   column beyond the frame : p0*(1-b) + p1*b with the edge column -- except that rows ABOVE the frame take column
+ *                              w-2 instead of w-1 on the right side (a quirk of cv2 4.13's sampler, reproduced)
+ * then per iteration the 2x2 system of the gradient products, accumulated in float64 in raster order over the
+ * (2*win+1)^2 window with the float32 mask exp(-y^2)*exp(-x^2); an update that leaves the frame is discarded. */
+static void rect_subpix_8u32f(const uint8_t* src, int step, int cols, int rows, float* dst, int dw, int dh, float cx, float cy)
+{
+    const float centx = cx - (dw - 1) * 0.5f, centy = cy - (dh - 1) * 0.5f;
+    const int ipx = (int)floorf(centx), ipy = (int)floorf(centy);
+    const float a = centx - ipx, b = centy - ipy;
+    const float a11 = (1.f - a) * (1.f - b), a12 = a * (1.f - b), a21 = (1.f - a) * b, a22 = a * b, b1 = 1.f - b, b2 = b;
+    if (0 <= ipx && ipx < cols - dw && 0 <= ipy && ipy < rows - dh) {
+        const uint8_t* p = src + (size_t)ipy * step + ipx;
+        for (int i = 0; i < dh; ++i, p += step, dst += dw)
+            for (int j = 0; j < dw; ++j)
+                dst[j] = (p[j] * a11 + p[j + 1] * a12) + (p[j + step] * a21 + p[j + step + 1] * a22);
+        return;
+    }
+    int rx = ipx >= 0 ? 0 : -ipx; if (rx > dw) rx = dw;
+    int rw = ipx < cols - dw ? dw : cols - ipx - 1; if (rw < 0) rw = 0;
+    const int ry = ipy >= 0 ? 0 : -ipy;
+    int rh = ipy < rows - dh ? dh : rows - ipy - 1; if (rh < 0) rh = 0;
+    for (int i = 0; i < dh; ++i, dst += dw) {
+        int y0 = ipy + i; y0 = y0 < 0 ? 0 : (y0 >= rows ? rows - 1 : y0);
+        const int rep = (i < ry || i >= rh);
+        const uint8_t* r0 = src + (size_t)y0 * step;
+        const uint8_t* r1 = rep ? r0 : r0 + step;
+        for (int j = 0; j < dw; ++j) {
+            if (j < rx) dst[j] = r0[0] * b1 + r1[0] * b2;
+            else if (j >= rw) {
+                int xe = ipx + rw - (i < ry ? 1 : 0);
+                xe = xe < 0 ? 0 : (xe >= cols ? cols - 1 : xe);
+                dst[j] = r0[xe] * b1 + r1[xe] * b2;
+            } else {
+                const int x = ipx + j;
+                if (rep) dst[j] = fmaf((float)r0[x + 1], a, r0[x] * (1.f - a));
+                else dst[j] = (r0[x] * a11 + r0[x + 1] * a12) + (r1[x] * a21 + r1[x + 1] * a22);
+            }
+        }
+    }
+}
+
+ORC_API void orc_corner_subpix_u8(const uint8_t* src, int cols, int rows, int step, float* pts, int n, int winw, int winh,
+                                  int max_iters, double eps)
+{
+    const int win_w = winw * 2 + 1, win_h = winh * 2 + 1;
+    float* mask = (float*)malloc(sizeof(float) * win_w * win_h);
+    max_iters = max_iters < 1 ? 1 : (max_iters > 100 ? 100 : max_iters);
+    eps = eps < 0. ? 0. : eps;
+    eps *= eps;
+    for (int i = 0; i < win_h; i++) {
+        const float y = (float)(i - winh) / winh;
+        const float vy = expf(-y * y);
+        for (int j = 0; j < win_w; j++) {
+            const float x = (float)(j - winw) / winw;
+            mask[i * win_w + j] = (float)(vy * expf(-x * x));
+        }
+    }
+#pragma omp parallel
+    {
+        float* buf = (float*)malloc(sizeof(float) * (win_w + 2) * (win_h + 2));
+#pragma omp for schedule(static)
+        for (int k = 0; k < n; ++k) {
+            const float cTx = pts[2 * k], cTy = pts[2 * k + 1];
+            float cIx = cTx, cIy = cTy;
+            int iter = 0;
+            double err = 0;
+            do {
+                rect_subpix_8u32f(src, step, cols, rows, buf, win_w + 2, win_h + 2, cIx, cIy);
+                const float* subpix = buf + (win_w + 2) + 1;
+                double a = 0, b = 0, c = 0, bb1 = 0, bb2 = 0;
+                for (int i = 0, kk = 0; i < win_h; i++, subpix += win_w + 2) {
+                    const double py = i - winh;
+                    for (int j = 0; j < win_w; j++, kk++) {
+                        const double m = mask[kk];
+                        const double tgx = subpix[j + 1] - subpix[j - 1];
+                        const double tgy = subpix[j + win_w + 2] - subpix[j - win_w - 2];
+                        const double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+                        const double px = j - winw;
+                        a += gxx; b += gxy; c += gyy;
+                        bb1 += gxx * px + gxy * py;
+                        bb2 += gxy * px + gyy * py;
+                    }
+                }
+                const double det = a * c - b * b;
+                if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+                const double scale = 1.0 / det;
+                const float nx = (float)(cIx + c * scale * bb1 - b * scale * bb2);
+                const float ny = (float)(cIy - b * scale * bb1 + a * scale * bb2);
+                err = (nx - cIx) * (nx - cIx) + (ny - cIy) * (ny - cIy);
+                if (nx < 0 || nx >= cols || ny < 0 || ny >= rows) break;   /* an update that leaves the frame is discarded */
+                cIx = nx; cIy = ny;
+            } while (++iter < max_iters && err > eps);
+            if (fabsf(cIx - cTx) > winw || fabsf(cIy - cTy) > winh) { cIx = cTx; cIy = cTy; }
+            pts[2 * k] = cIx; pts[2 * k + 1] = cIy;
+        }
+        free(buf);
+    }
+    free(mask);
+}
+
 ORC_API int orc_version(void) { return 1; }

@@ -272,6 +272,25 @@ def gen_gftt():
     save("gftt", **out)
 
 
+def gen_subpix():
+    """cv2.cornerSubPix(im, p, (5,5), (-1,-1), criteria) (vidExample.py:113-115) on detector corners and on random points,
+    many of them within the 7-px rim where the 13x13 sampling window hangs over the frame border."""
+    out = {}
+    crits = {"ref": (EPS | COUNT, 100, 0.001), "loose": (EPS | COUNT, 20, 0.03), "count": (COUNT, 7, 0.0)}
+    for tag, (h, w, seed) in {"a": (120, 160, 41), "b": (97, 203, 42), "c": (31, 40, 43)}.items():
+        im = synth.texture(h, w, seed)
+        rng = np.random.default_rng(seed)
+        p = np.stack([rng.uniform(0, w - 1, 400), rng.uniform(0, h - 1, 400)], 1).astype(np.float32)
+        rim = np.stack([rng.choice([rng.uniform(0, 7), rng.uniform(w - 8, w - 1)], 1) for _ in range(100)] , 0)
+        rim = np.concatenate([rim, rng.uniform(0, h - 1, (100, 1))], 1).astype(np.float32)
+        g = cv2.goodFeaturesToTrack(im, 200, 0.01, 0, blockSize=5, useHarrisDetector=True).reshape(-1, 2)
+        p = np.concatenate([p, rim, g]).astype(np.float32)
+        out["im_" + tag], out["p_" + tag] = im, p
+        for cn, c in crits.items():
+            out["q_%s_%s" % (tag, cn)] = cv2.cornerSubPix(im, p.copy().reshape(-1, 1, 2), (5, 5), (-1, -1), c).reshape(-1, 2)
+    save("subpix", **out)
+
+
 def gen_e2e():
     """vidExample.py end to end on the two clips that have plate fixtures."""
     mod, ns = ref_shim.load_vid_example()
@@ -319,6 +338,7 @@ def main():
     gen_match()
     gen_ingest()
     gen_gftt()
+    gen_subpix()
     gen_e2e()
 
 

@@ -70,10 +70,15 @@ def oracle_modules():
         assert min_distance == 0 and blockSize == 5 and useHarrisDetector
         return gftt_oracle.good_features_to_track(roi, n, q).reshape(-1, 1, 2)
 
+    def subpix(im, p, win, zero_zone, criteria):
+        from oracle import cv_oracle
+
+        return cv_oracle.cornerSubPix(im, p, win, zero_zone, criteria).reshape(np.asarray(p).shape)
+
     klt = types.SimpleNamespace(KLTmain=klt_oracle.klt_main)
     nls = types.SimpleNamespace(estimateWorldCameraPose=estimateWorldCameraPose)
     msv = types.SimpleNamespace(fcnMSV1_t=fcnMSV1_t)
-    return klt, nls, msv, gftt
+    return klt, nls, msv, (gftt, subpix)
 
 
 @pytest.mark.parametrize("name", CLIPS)

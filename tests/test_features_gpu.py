@@ -80,3 +80,29 @@ def test_good_features_against_cv2_itself(cuda):
             ref = cv2.goodFeaturesToTrack(im, n, q, 0, blockSize=5, useHarrisDetector=True)
             out = features.goodFeaturesToTrack(im, n, q, 0, blockSize=5, useHarrisDetector=True)
             assert out.shape == ref.shape and np.array_equal(out, ref), (im.shape, n, q)
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("crit", ["ref", "loose", "count"])
+def test_corner_subpix_equals_cv2_golden(cuda, tag, crit):
+    from velocity_b200 import features
+
+    crits = {"ref": (3, 100, 0.001), "loose": (3, 20, 0.03), "count": (1, 7, 0.0)}
+    g = golden("subpix")
+    p = g["p_" + tag]
+    out = features.cornerSubPix(g["im_" + tag], p.reshape(-1, 1, 2), (5, 5), (-1, -1), crits[crit])
+    assert out.shape == (len(p), 1, 2) and out.dtype == np.float32
+    assert np.array_equal(out.reshape(-1, 2), g["q_%s_%s" % (tag, crit)])
+
+
+def test_corner_subpix_full_frame_against_cv2_itself(cuda):
+    cv2 = pytest.importorskip("cv2")
+    from velocity_b200 import features, synth
+
+    frames, _ = synth.plane_sequence(1, h=1080, w=1920, seed=9, Z0=40.0)
+    im = frames[0]
+    p = cv2.goodFeaturesToTrack(im, 1000, 0.01, 0, blockSize=5, useHarrisDetector=True)
+    ref = cv2.cornerSubPix(im, p.copy(), (5, 5), (-1, -1), (3, 100, 0.001))
+    assert np.array_equal(features.cornerSubPix(im, p, (5, 5), (-1, -1), (3, 100, 0.001)), ref)
+    with pytest.raises(NotImplementedError):
+        features.cornerSubPix(im, p, (5, 5), (2, 2), (3, 100, 0.001))

@@ -31,3 +31,19 @@ def test_good_features_same_corners_same_order(tag, width, n, q):
     mine = G.good_features_to_track(g["im_" + tag], n, q)
     assert mine.dtype == np.float32 and np.array_equal(mine, ref)
     assert len(ref) > 10
+
+
+SUBPIX_CRIT = {"ref": (3, 100, 0.001), "loose": (3, 20, 0.03), "count": (1, 7, 0.0)}
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c"])
+@pytest.mark.parametrize("crit", list(SUBPIX_CRIT))
+def test_corner_subpix_bit_exact(tag, crit):
+    """oracle/velocity_oracle.c::orc_corner_subpix_u8 against cv2.cornerSubPix (golden subpix.npz): every refined corner
+    bit-identical, including those whose 13x13 sampling window hangs over the frame border."""
+    from oracle import cv_oracle as O
+
+    g = golden("subpix")
+    out = O.cornerSubPix(g["im_" + tag], g["p_" + tag], (5, 5), (-1, -1), SUBPIX_CRIT[crit])
+    assert out.dtype == np.float32 and np.array_equal(out, g["q_%s_%s" % (tag, crit)])
+    assert (out != g["p_" + tag]).any(1).mean() > 0.2      # the rest diverged and were reset to the input, as cv2 does

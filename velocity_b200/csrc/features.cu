@@ -22,6 +22,8 @@
 // (value bits << 32 | address, all distinct) is found by an 8-pass radix select and the survivors are ranked by
 // counting -- no host round trip, no library sort.
 #include "common.cuh"
+#include <float.h>
+#include <math.h>
 
 namespace {
 
@@ -257,6 +259,101 @@ __global__ void gftt_rank_kernel(const unsigned long long* __restrict__ sel, con
     }
 }
 
+// ---- cv2.cornerSubPix (vidExample.py:113-115) ------------------------------------------------------------------------
+// One thread per corner: the iteration is a short serial recurrence (float64 sums in raster order are part of the
+// contract) over <= 1000 corners once per clip, so the kernel is about fidelity, not throughput.  The sampler and the
+// update follow oracle/velocity_oracle.c::orc_corner_subpix_u8 operation by operation with explicit rounding
+// intrinsics (nothing may be contracted); the float32 window mask is computed on the HOST with the C library's expf,
+// which is what cv2 itself evaluates.
+constexpr int SUBPIX_MAX_WIN = 7;                                        // half window; the reference uses 5
+struct SubpixMask { float m[(2 * SUBPIX_MAX_WIN + 1) * (2 * SUBPIX_MAX_WIN + 1)]; };
+
+__device__ void rect_subpix_8u32f(const uint8_t* __restrict__ src, int step, int cols, int rows, float* dst, int dw, int dh, float cx,
+                                  float cy)
+{
+    const float centx = __fsub_rn(cx, (dw - 1) * 0.5f), centy = __fsub_rn(cy, (dh - 1) * 0.5f);
+    const int ipx = __float2int_rd(centx), ipy = __float2int_rd(centy);
+    const float a = __fsub_rn(centx, (float)ipx), b = __fsub_rn(centy, (float)ipy);
+    const float b1 = __fsub_rn(1.f, b), b2 = b, a1 = __fsub_rn(1.f, a);
+    const float a11 = __fmul_rn(a1, b1), a12 = __fmul_rn(a, b1), a21 = __fmul_rn(a1, b), a22 = __fmul_rn(a, b);
+    if (0 <= ipx && ipx < cols - dw && 0 <= ipy && ipy < rows - dh) {
+        const uint8_t* p = src + (size_t)ipy * step + ipx;
+        for (int i = 0; i < dh; ++i, p += step, dst += dw)
+            for (int j = 0; j < dw; ++j)
+                dst[j] = __fadd_rn(__fadd_rn(__fmul_rn((float)__ldg(p + j), a11), __fmul_rn((float)__ldg(p + j + 1), a12)),
+                                   __fadd_rn(__fmul_rn((float)__ldg(p + j + step), a21), __fmul_rn((float)__ldg(p + j + step + 1), a22)));
+        return;
+    }
+    int rx = ipx >= 0 ? 0 : -ipx; if (rx > dw) rx = dw;
+    int rw = ipx < cols - dw ? dw : cols - ipx - 1; if (rw < 0) rw = 0;
+    const int ry = ipy >= 0 ? 0 : -ipy;
+    int rh = ipy < rows - dh ? dh : rows - ipy - 1; if (rh < 0) rh = 0;
+    for (int i = 0; i < dh; ++i, dst += dw) {
+        int y0 = ipy + i; y0 = y0 < 0 ? 0 : (y0 >= rows ? rows - 1 : y0);
+        const bool rep = (i < ry || i >= rh);
+        const uint8_t* r0 = src + (size_t)y0 * step;
+        const uint8_t* r1 = rep ? r0 : r0 + step;
+        for (int j = 0; j < dw; ++j) {
+            if (j < rx) dst[j] = __fadd_rn(__fmul_rn((float)__ldg(r0), b1), __fmul_rn((float)__ldg(r1), b2));
+            else if (j >= rw) {
+                int xe = ipx + rw - (i < ry ? 1 : 0);      // cv2 4.13: rows above the frame take column w-2 on the right side
+                xe = xe < 0 ? 0 : (xe >= cols ? cols - 1 : xe);
+                dst[j] = __fadd_rn(__fmul_rn((float)__ldg(r0 + xe), b1), __fmul_rn((float)__ldg(r1 + xe), b2));
+            } else {
+                const int x = ipx + j;
+                if (rep) dst[j] = __fmaf_rn((float)__ldg(r0 + x + 1), a, __fmul_rn((float)__ldg(r0 + x), a1));
+                else dst[j] = __fadd_rn(__fadd_rn(__fmul_rn((float)__ldg(r0 + x), a11), __fmul_rn((float)__ldg(r0 + x + 1), a12)),
+                                        __fadd_rn(__fmul_rn((float)__ldg(r1 + x), a21), __fmul_rn((float)__ldg(r1 + x + 1), a22)));
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(64)
+corner_subpix_kernel(const uint8_t* __restrict__ src, int cols, int rows, int step, float* __restrict__ pts, int n, int winw, int winh,
+                     int max_iters, double eps2, const SubpixMask mask)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const int win_w = 2 * winw + 1, win_h = 2 * winh + 1, bw = win_w + 2;
+    float buf[(2 * SUBPIX_MAX_WIN + 3) * (2 * SUBPIX_MAX_WIN + 3)];
+    const float cTx = pts[2 * k], cTy = pts[2 * k + 1];
+    float cIx = cTx, cIy = cTy;
+    int iter = 0;
+    double err = 0.;
+    do {
+        rect_subpix_8u32f(src, step, cols, rows, buf, bw, win_h + 2, cIx, cIy);
+        double a = 0., b = 0., c = 0., bb1 = 0., bb2 = 0.;
+        for (int i = 0, kk = 0; i < win_h; ++i) {
+            const float* sp = buf + (i + 1) * bw + 1;
+            const double py = (double)(i - winh);
+            for (int j = 0; j < win_w; ++j, ++kk) {
+                const double m = (double)mask.m[kk];
+                const double tgx = (double)__fsub_rn(sp[j + 1], sp[j - 1]);
+                const double tgy = (double)__fsub_rn(sp[j + bw], sp[j - bw]);
+                const double gxx = __dmul_rn(__dmul_rn(tgx, tgx), m), gxy = __dmul_rn(__dmul_rn(tgx, tgy), m),
+                             gyy = __dmul_rn(__dmul_rn(tgy, tgy), m);
+                const double px = (double)(j - winw);
+                a = __dadd_rn(a, gxx); b = __dadd_rn(b, gxy); c = __dadd_rn(c, gyy);
+                bb1 = __dadd_rn(bb1, __dadd_rn(__dmul_rn(gxx, px), __dmul_rn(gxy, py)));
+                bb2 = __dadd_rn(bb2, __dadd_rn(__dmul_rn(gxy, px), __dmul_rn(gyy, py)));
+            }
+        }
+        const double det = __dsub_rn(__dmul_rn(a, c), __dmul_rn(b, b));
+        if (fabs(det) <= DBL_EPSILON * DBL_EPSILON) break;
+        const double scale = __ddiv_rn(1.0, det);
+        const float nx = __double2float_rn(__dsub_rn(__dadd_rn((double)cIx, __dmul_rn(__dmul_rn(c, scale), bb1)), __dmul_rn(__dmul_rn(b, scale), bb2)));
+        const float ny = __double2float_rn(__dadd_rn(__dsub_rn((double)cIy, __dmul_rn(__dmul_rn(b, scale), bb1)), __dmul_rn(__dmul_rn(a, scale), bb2)));
+        const float ex = __fsub_rn(nx, cIx), ey = __fsub_rn(ny, cIy);
+        err = (double)__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+        if (nx < 0.f || nx >= (float)cols || ny < 0.f || ny >= (float)rows) break;     // an update that leaves the frame is discarded
+        cIx = nx; cIy = ny;
+    } while (++iter < max_iters && err > eps2);
+    if (fabsf(__fsub_rn(cIx, cTx)) > (float)winw || fabsf(__fsub_rn(cIy, cTy)) > (float)winh) { cIx = cTx; cIy = cTy; }
+    pts[2 * k] = cIx;
+    pts[2 * k + 1] = cIy;
+}
+
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -316,5 +413,33 @@ VEL_API int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32
     gftt_compact_kernel<<<sel_grid, 256, 0, st>>>(keys, S, sel, (unsigned)max_corners, capacity);
     gftt_rank_kernel<<<(max_corners + 255) / 256, 256, 0, st>>>(sel, S, width, out_xy, out_count);
     VEL_LAUNCH_CHECK("good-features kernels");
+    return VEL_OK;
+}
+
+VEL_API int vel_corner_subpix_u8(const uint8_t* img, int32_t width, int32_t height, int32_t pitch, float* pts, int32_t npts, int32_t win_w,
+                                 int32_t win_h, int32_t max_iters, double eps, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(npts >= 0, "vel_corner_subpix_u8: npts < 0");
+    if (npts == 0) return VEL_OK;
+    VEL_CHECK_ARG(img && pts, "vel_corner_subpix_u8: NULL argument");
+    VEL_CHECK_ARG(width > 0 && height > 0 && pitch >= width, "vel_corner_subpix_u8: bad image %dx%d pitch %d", width, height, pitch);
+    VEL_CHECK_ARG(win_w >= 1 && win_h >= 1 && win_w <= SUBPIX_MAX_WIN && win_h <= SUBPIX_MAX_WIN,
+                  "vel_corner_subpix_u8: half window %dx%d outside [1,%d]", win_w, win_h, SUBPIX_MAX_WIN);
+    VEL_CHECK_ARG(width >= 2 * win_w + 5 && height >= 2 * win_h + 5, "vel_corner_subpix_u8: image smaller than the sampling window");
+    max_iters = max_iters < 1 ? 1 : (max_iters > 100 ? 100 : max_iters);      // cv2: MIN(MAX(maxCount, 1), 100)
+    eps = eps < 0. ? 0. : eps;
+    SubpixMask mask;
+    const int ww = 2 * win_w + 1, wh = 2 * win_h + 1;
+    for (int i = 0; i < wh; ++i) {
+        const float y = (float)(i - win_h) / win_h;
+        const float vy = expf(-y * y);
+        for (int j = 0; j < ww; ++j) {
+            const float x = (float)(j - win_w) / win_w;
+            mask.m[i * ww + j] = (float)(vy * expf(-x * x));
+        }
+    }
+    corner_subpix_kernel<<<(npts + 63) / 64, 64, 0, (cudaStream_t)stream>>>(img, width, height, pitch, pts, npts, win_w, win_h, max_iters,
+                                                                          eps * eps, mask);
+    VEL_LAUNCH_CHECK("corner_subpix_kernel");
     return VEL_OK;
 }

@@ -5,8 +5,8 @@
 with cv2's signature and return layout ([n, 1, 2] float32, strongest first).  The Harris response, the 3x3
 non-maximum suppression and the ordered top-K selection all run in libvelocity_b200.so (K9, csrc/features.cu) and
 return the same corners in the same order as opencv-python 4.13 (tests/test_features_gpu.py).  The sub-pixel
-refinement that follows in the reference (cv2.cornerSubPix, vidExample.py:113) touches <= 1000 points once per
-clip and stays on the host for now.  There is no CPU fallback.
+refinement that follows in the reference (cv2.cornerSubPix, vidExample.py:113-115) is cornerSubPix below: one
+thread per corner, bit-identical to cv2.  There is no CPU fallback.
 """
 import numpy as np
 import torch
@@ -42,3 +42,20 @@ def goodFeaturesToTrack(image, maxCorners, qualityLevel, minDistance, mask=None,
     if n == 0:
         return None
     return np.ascontiguousarray(packed[:2 * n].reshape(n, 1, 2))
+
+
+def cornerSubPix(image, corners, winSize, zeroZone, criteria):
+    """cv2.cornerSubPix for the reference's call (vidExample.py:113-115): uint8 image, zeroZone (-1,-1).  Returns the
+    refined corners as a new float32 array of the input's shape (cv2 also refines its argument in place; numpy inputs
+    are left untouched here)."""
+    require_cuda()
+    if tuple(zeroZone) != (-1, -1):
+        raise NotImplementedError("only zeroZone=(-1,-1) (the reference's value, vidExample.py:114) is implemented")
+    t, p, w, h, pitch = image_view(image)
+    c = np.asarray(corners, np.float32)
+    pts = torch.from_numpy(np.ascontiguousarray(c.reshape(-1, 2))).to(t.device)
+    ctype, count, eps = criteria
+    _lib.check(_lib.lib().vel_corner_subpix_u8(p, w, h, pitch, ptr(pts), pts.shape[0], int(winSize[0]), int(winSize[1]),
+                                               int(count) if (ctype & 1) else 100, float(eps) if (ctype & 2) else 0.0, stream_ptr()),
+               "vel_corner_subpix_u8")
+    return pts.cpu().numpy().reshape(c.shape)

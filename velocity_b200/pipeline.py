@@ -5,9 +5,8 @@ through this package's GPU modules.
     frame i : KLT.KLTmain (3-stage GPU tracker) -> NLS.estimateWorldCameraPose (3-dof, GPU) -> speed
     frame 5 : MSV.fcnMSV1_t re-triangulates every track (GPU) and enables all points
 
-Feature initialisation (vidExample.py:110-115): the Harris detector runs on the GPU (K9, features.py),
-the one-shot sub-pixel refinement of its <= 1000 corners stays in cv2.cornerSubPix; everything inside
-the per-frame loop that the reference delegates to cv2.calcOpticalFlowPyrLK / remap / numpy LM runs
+Feature initialisation (vidExample.py:110-115): the Harris detector and the sub-pixel refinement run on
+the GPU (K9, features.py); everything inside the per-frame loop that the reference delegates to cv2.calcOpticalFlowPyrLK / remap / numpy LM runs
 in libvelocity_b200.so.  The bookkeeping arrays keep the reference's layout (P [5,npts,n],
 B [n,14], S [n,9]) so downstream code (plots) can consume them unchanged.
 """
@@ -23,31 +22,29 @@ HEADER = ("image", "procTime", "pointTracks", "metric", "dt", "time", "dx", "dis
           "#", "(s)", "#", "(pixels)", "(s)", "(s)", "(m)", "(m)", "(km/h)")
 
 
-def detect_plate_features(im, q, max_corners=1000, gftt=None):
-    """vidExample.py:107-116: Harris corners in the plate neighbourhood (GPU, K9), refined to sub-pixel
-    (cv2.cornerSubPix on the host: <= 1000 points, once per clip).  `gftt` replaces the detector (the
-    test-suite passes the CPU oracle's)."""
-    import cv2
-
-    if gftt is None:
+def detect_plate_features(im, q, max_corners=1000, detector=None):
+    """vidExample.py:107-116: Harris corners in the plate neighbourhood, refined to sub-pixel -- both on the GPU (K9).
+    `detector` = (goodFeaturesToTrack, cornerSubPix) replaces them (the test-suite passes the CPU oracle's)."""
+    if detector is None:
         from . import features
 
-        gftt = features.goodFeaturesToTrack
+        detector = (features.goodFeaturesToTrack, features.cornerSubPix)
+    gftt, subpix = detector
     boxa = boundingRect(q, im.shape, border=(0, 0))
     boxb = boundingRect(q, im.shape, border=(700, 500))
     roi = np.ascontiguousarray(im[boxb[2]:boxb[3], boxb[0]:boxb[1]])
     p = gftt(roi, max_corners, 0.01, 0, blockSize=5, useHarrisDetector=True).squeeze()
     p = p + np.float32([boxb[0], boxb[2]])
-    p = cv2.cornerSubPix(im, p, (5, 5), (-1, -1), (cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER, 100, 0.001))
+    p = subpix(im, p, (5, 5), (-1, -1), (2 + 1, 100, 0.001))     # cv2.TERM_CRITERIA_EPS + cv2.TERM_CRITERIA_MAX_ITER
     return np.concatenate((q, p)), boxa, boxb
 
 
 def run_speed_estimation(frames, q, K, frame_times, msv_frame=5, verbose=True, country="Chile", modules=None):
     """frames: sequence of uint8 [H,W] images; q: float32 [4,2] plate corners in frame 0;
     K: 3x3 row-vector intrinsics; frame_times: seconds per frame.  Returns a dict with the
-    reference's S / B / P arrays and the summary statistics it prints.  `modules` = (KLT, NLS, MSV, gftt)
+    reference's S / B / P arrays and the summary statistics it prints.  `modules` = (KLT, NLS, MSV, (gftt, subpix))
     lets the test-suite drive the same loop with the CPU oracle; the default is the GPU path."""
-    klt, nls, msv, gftt = modules if modules is not None else (KLT, NLS, MSV, None)
+    klt, nls, msv, detector = modules if modules is not None else (KLT, NLS, MSV, None)
     n = len(frames)
     q = np.asarray(q, np.float32)
     B = np.zeros([n, 14], dtype=np.float32)
@@ -60,7 +57,7 @@ def run_speed_estimation(frames, q, K, frame_times, msv_frame=5, verbose=True, c
         im = frames[i]
         B[i, 12] = frame_times[i]
         if i == 0:
-            p, boxa, boxb = detect_plate_features(im, q, gftt=gftt)
+            p, boxa, boxb = detect_plate_features(im, q, detector=detector)
             t, R, residuals, _ = nls.estimateWorldCameraPose(K, q, worldPointsLicensePlate(country), findR=True)
             p3 = addcol0(image2world(K, R, t, p).astype(float)) @ R + t
             R = np.eye(3)

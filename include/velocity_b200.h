@@ -103,6 +103,15 @@ int vel_good_features_harris_u8(const uint8_t* img, int32_t width, int32_t heigh
 int vel_corner_subpix_u8(const uint8_t* img, int32_t width, int32_t height, int32_t pitch, float* pts, int32_t npts, int32_t win_w,
                          int32_t win_h, int32_t max_iters, double eps, vel_stream_t stream);
 
+/* K10.  cv2.estimateAffine2D(from, to, method=cv2.RANSAC) (utils/KLT.py:116,127,33) with caller-supplied threshold /
+ * confidence / iteration budget (cv2's defaults: 3.0, 0.99, 2000) on npts (3..8192) float32 correspondences (DEVICE,
+ * interleaved x,y).  OpenCV's RANSAC loop with its fixed-seed RNG (restated in oracle/ransac_oracle.py): the inlier
+ * mask (uint8 [npts], DEVICE) is bit-identical to cv2's; T (double [6] = 2x3 row-major, DEVICE) is the model after
+ * the refinement on the inliers (refine != 0; cv2's 10 LM steps converge to this least-squares fit: agreement
+ * ~1e-12).  info (int32 [3], DEVICE) = {found (0/1), inlier count, RANSAC iterations run}. */
+int vel_estimate_affine2d_ransac(const float* from_xy, const float* to_xy, int32_t npts, double threshold, double confidence,
+                                 int32_t max_iters, int32_t refine, uint8_t* inliers, double* T, int32_t* info, vel_stream_t stream);
+
 /* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
  * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
  * forward result fused in the same kernel with

@@ -8,8 +8,8 @@ restates).  Pinned by tests/golden/lk_*.npz, regional_*.npz, kltmain_pair.npz.
     klt_regional          <- utils/KLT.py:55-95   KLTregional
     klt_main              <- utils/KLT.py:99-134  KLTmain
 
-cv2.estimateAffine2D (RANSAC, utils/KLT.py:116,127) is NOT restated: product and oracle both call
-the host cv2 for it, so it is outside every parity claim.
+cv2.estimateAffine2D (RANSAC, utils/KLT.py:116,127) is restated in oracle/ransac_oracle.py (inlier masks
+bit-exact against cv2, T to ~1e-12) and used by klt_main below.
 """
 import numpy as np
 
@@ -66,7 +66,7 @@ LK_FINE = dict(winSize=(51, 51), maxLevel=0, criteria=(3, 30, 0.001))
 
 
 def klt_main(im, im0, im0_small, p0, nthreads=0):
-    import cv2  # RANSAC only (see module docstring)
+    from .ransac_oracle import estimate_affine_2d
 
     p0 = np.asarray(p0, np.float32)
     s = 1 / 4
@@ -75,13 +75,13 @@ def klt_main(im, im0, im0_small, p0, nthreads=0):
         im0_small = cvo.decimate4(im0)
     p, v, _ = lk_forward_backward(im0_small, im_small, p0 * s, nthreads=nthreads, **LK_COARSE)
     p = p / s
-    T23, inl = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+    T23, inl = estimate_affine_2d(p0[v], p[v])
     v[v] = inl.ravel().astype(bool)
     T = np.eye(3, 2)
     T[2] = (p[v] - p0[v]).mean(0)
     p, v = klt_regional(im0, im, p0, T, LK_COARSE, fbt=1, translate=True, nthreads=nthreads)
     if v.sum() > 10:
-        T23, inl = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+        T23, inl = estimate_affine_2d(p0[v], p[v])
     else:
         raise RuntimeError("KLT coarse-affine failure (descriptor fallback is exercised separately)")
     p, v = klt_regional(im0, im, p0, T23.T, LK_FINE, fbt=0.3, nthreads=nthreads)

@@ -291,6 +291,30 @@ def gen_subpix():
     save("subpix", **out)
 
 
+def gen_ransac():
+    """cv2.estimateAffine2D(from, to, method=cv2.RANSAC) (utils/KLT.py:116,127) on seeded correspondence sets: clean,
+    10-60 % gross outliers, few points, exactly 3 points, all-collinear (no model)."""
+    rng = np.random.default_rng(116)
+    out, k = {}, 0
+    for n, noise, frac in [(600, 0.2, 0.0), (350, 0.5, 0.1), (900, 1.5, 0.3), (120, 0.5, 0.6), (4096, 0.3, 0.25), (12, 0.1, 0.2), (4, 0.0, 0.0),
+                           (3, 0.0, 0.0)]:
+        fr = rng.uniform(0, 1900, (n, 2)).astype(np.float32)
+        A = np.array([[1 + rng.normal() * 0.02, rng.normal() * 0.02], [rng.normal() * 0.02, 1 + rng.normal() * 0.02]])
+        to = (fr @ A.T + rng.normal(size=2) * 20 + rng.normal(size=(n, 2)) * noise).astype(np.float32)
+        nout = int(n * frac)
+        if nout:
+            to[rng.choice(n, nout, replace=False)] += rng.uniform(-80, 80, (nout, 2)).astype(np.float32)
+        T, inl = cv2.estimateAffine2D(fr, to, method=cv2.RANSAC)
+        out["from_%d" % k], out["to_%d" % k], out["T_%d" % k], out["inl_%d" % k] = fr, to, T, inl
+        k += 1
+    line = np.stack([np.arange(9, dtype=np.float32) * 7, np.arange(9, dtype=np.float32) * 3 + 1], 1)
+    T, inl = cv2.estimateAffine2D(line, line + 2, method=cv2.RANSAC)
+    assert T is None
+    out["from_%d" % k], out["to_%d" % k], out["T_%d" % k], out["inl_%d" % k] = line, line + 2, np.zeros((0, 3)), inl
+    out["ncases"] = np.array(k + 1)
+    save("ransac", **out)
+
+
 def gen_e2e():
     """vidExample.py end to end on the two clips that have plate fixtures."""
     mod, ns = ref_shim.load_vid_example()
@@ -339,6 +363,7 @@ def main():
     gen_ingest()
     gen_gftt()
     gen_subpix()
+    gen_ransac()
     gen_e2e()
 
 

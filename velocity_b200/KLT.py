@@ -8,9 +8,9 @@
 All pixel/point arithmetic runs in the sm_100a kernels of libvelocity_b200.so (K1 pyramid, K2
 Lucas-Kanade with fused forward-backward gate, K3 affine remap, K4 descriptor matcher).  Images
 may be numpy arrays (uploaded per call) or CUDA uint8 tensors (used in place, ROI slices are free).
-Outputs are numpy arrays with the reference's shapes and dtypes.  The RANSAC affine fit stays on
-the host in cv2.estimateAffine2D exactly as in the reference (fixed-seed RNG => bit-identical
-inlier masks).  There is no CPU fallback for the kernels.
+Outputs are numpy arrays with the reference's shapes and dtypes.  The RANSAC affine fit
+(cv2.estimateAffine2D, utils/KLT.py:116,127) runs on the GPU too (K10, ransac.py): OpenCV's loop with
+its fixed-seed RNG, bit-identical inlier masks.  There is no CPU fallback for the kernels.
 """
 import ctypes as C
 
@@ -22,6 +22,7 @@ from .common import addcol1
 from .device import image_view, ptr, stream_ptr
 from .images import boundingRect
 from .lk import FrameBatch, lk_params, track_pairs
+from .ransac import estimateAffine2D
 
 TERM_CRITERIA_COUNT, TERM_CRITERIA_EPS = 1, 2
 
@@ -106,8 +107,6 @@ def KLTmain(im, im0, im0_small, p0):
     """Three-stage tracker: quarter-scale LK -> RANSAC -> translated-ROI LK (FB 1.0) -> RANSAC ->
     affine-ROI fine LK (FB 0.3).  Returns (p[v] float32, v bool [N], im_small) like the reference;
     im_small is returned in the form it was produced (CUDA tensor), pass it back as im0_small."""
-    import cv2  # host RANSAC only
-
     p0 = np.asarray(p0)
     d_im, d_im0 = _as_cuda_image(im), _as_cuda_image(im0)
     scale = 1 / 4
@@ -116,7 +115,7 @@ def KLTmain(im, im0, im0_small, p0):
         im0_small = _decimate4_device(d_im0)
     p, v, _ = cv2calcOpticalFlowPyrLK(im0_small, im_small, p0 * scale, None, **LK_COARSE)
     p /= scale
-    T23, inliers = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+    T23, inliers = estimateAffine2D(p0[v], p[v])
     v[v] = inliers.ravel().astype(bool)
 
     translation = p[v] - p0[v]
@@ -125,7 +124,7 @@ def KLTmain(im, im0, im0_small, p0):
     p, v = KLTregional(d_im0, d_im, p0, T, LK_COARSE, fbt=1, translateFlag=True)
 
     if v.sum() > 10:
-        T23, inliers = cv2.estimateAffine2D(p0[v], p[v], method=cv2.RANSAC)
+        T23, inliers = estimateAffine2D(p0[v], p[v])
     else:
         print("KLT coarse-affine failure, running SURF matches full scale.")
         T23, inliers = estimateAffine2D_SURF(d_im0, d_im, p0, scale=1)
@@ -172,4 +171,4 @@ def estimateAffine2D_SURF(im1, im2, p1, scale=1.0):
             raise RuntimeError("estimateAffine2D_SURF: fewer than 10 ratio-test matches on the full frame")
     m1 = np.float32([kp1[q].pt for q, _ in good]) + np.float32([x0, y0])
     m2 = np.float32([kp2[t].pt for _, t in good])
-    return cv2.estimateAffine2D(m1 / scale, m2 / scale, method=cv2.RANSAC)
+    return estimateAffine2D(m1 / scale, m2 / scale)

@@ -119,9 +119,11 @@ pyrdown_tiled_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
 // (lane 0 / 31 fetch them), the horizontal [1 4 6 4 1] pass is 4 dp4a on funnel-shifted words, and the
 // five most recent filtered rows stay in registers as packed 16-bit pairs for the vertical pass.
 // No shared memory, no barriers; 128-byte coalesced stores.
-constexpr int STRIP_H = 16;
 constexpr int STRIP_THREADS = 64;
 
+// STRIP_H output rows per CTA: 16 for the big level-1 grids; 8 for the smaller upper levels, whose grids would
+// otherwise not fill the machine (one partial wave of latency-bound threads)
+template <int STRIP_H>
 __global__ void __launch_bounds__(STRIP_THREADS)
 pyrdown_strip_kernel(const uint8_t* __restrict__ src_base, long long src_stride, int sw, int sh, int spitch,
                      uint8_t* __restrict__ dst_base, long long dst_stride, int dw, int dh, int dpitch)
@@ -237,9 +239,17 @@ VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t 
         const bool strip_ok = (sw % 8 == 0) && sw >= 16 && (spitch % 8 == 0) && ((((uintptr_t)src) | (uintptr_t)sstride) & 7) == 0 &&
                               ((((uintptr_t)(pyr + L->offset[l])) | (uintptr_t)pyr_stride | (uintptr_t)L->pitch[l]) & 3) == 0;
         if (strip_ok) {
-            dim3 grid((sw / 8 + STRIP_THREADS - 1) / STRIP_THREADS, (L->height[l] + STRIP_H - 1) / STRIP_H, nframes);
-            pyrdown_strip_kernel<<<grid, STRIP_THREADS, 0, st>>>(src, sstride, sw, L->height[l - 1], spitch, pyr + L->offset[l],
-                                                                pyr_stride, L->width[l], L->height[l], L->pitch[l]);
+            const int gx = (sw / 8 + STRIP_THREADS - 1) / STRIP_THREADS;
+            const long long ctas16 = (long long)gx * ((L->height[l] + 15) / 16) * nframes;
+            if (ctas16 >= 8ll * 4 * kNumSMs) {      // >= 8 CTAs of 2 warps per scheduler: enough loads in flight
+                dim3 grid(gx, (L->height[l] + 15) / 16, nframes);
+                pyrdown_strip_kernel<16><<<grid, STRIP_THREADS, 0, st>>>(src, sstride, sw, L->height[l - 1], spitch, pyr + L->offset[l],
+                                                                        pyr_stride, L->width[l], L->height[l], L->pitch[l]);
+            } else {
+                dim3 grid(gx, (L->height[l] + 7) / 8, nframes);
+                pyrdown_strip_kernel<8><<<grid, STRIP_THREADS, 0, st>>>(src, sstride, sw, L->height[l - 1], spitch, pyr + L->offset[l],
+                                                                       pyr_stride, L->width[l], L->height[l], L->pitch[l]);
+            }
             VEL_LAUNCH_CHECK("pyrdown_strip_kernel");
         } else {
             dim3 grid((L->width[l] + TILE_W - 1) / TILE_W, (L->height[l] + TILE_H - 1) / TILE_H, nframes);

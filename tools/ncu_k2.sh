@@ -1,5 +1,5 @@
 #!/bin/bash
-# ncu --set full of one K2 launch per kernel variant (args: variants); raw pages land in gpurun_out/
+# ncu --set full of one K2 launch per kernel variant (args: `default` and/or `bytes`); raw pages land in gpurun_out/
 for impl in "$@"; do
   if [ $impl = default ]; then unset VEL_LK_W15; else export VEL_LK_W15=$impl; fi
   python tools/lk_one.py 32 3

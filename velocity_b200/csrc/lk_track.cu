@@ -13,10 +13,12 @@
 // All float32 steps use explicit round-to-nearest intrinsics so no FMA contraction can make the
 // device differ from the oracle: device == oracle bit for bit.
 //
-// Work decomposition: one GROUP of NT threads owns one point for all pyramid levels and both
-// passes.  NT = 32 (a warp, 8 points per CTA) for windows up to 1024 px^2, NT = 128 (a CTA) above.
-// The template (I, Ix, Iy as int16) lives in shared memory; J is gathered from global memory
-// through L1/L2 (the whole pyramid of a 1080p frame is 2.7 MB, i.e. L2 resident).
+// Kernels in this file (all produce identical bits; the dispatcher at the bottom picks by window size and pitch):
+//   lk_track_w15h_kernel   (lk_w15h.cuh) 15x15, pitches % 4 == 0: two points per warp, word gathers + DP2A  -- default
+//   lk_track_w15_kernel    15x15, any pitch: warp per point, byte gathers, REDUX sums (VEL_LK_W15=bytes forces it)
+//   lk_track_cols_kernel   16..63 px wide windows (51x51 lk_fine, cv2's default 21x21): CTA per point, template in smem
+//   lk_track_kernel        every other window up to 127x127: group of 32 / 128 threads per point, int64 sums
+// J is gathered from global memory through L1/L2 (the whole pyramid of a 1080p frame is 2.7 MB, i.e. L2 resident).
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>

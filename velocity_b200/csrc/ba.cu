@@ -181,35 +181,60 @@ ba_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, co
     }
 }
 
-// ---- point kernel: one thread per point, loops over this rank's cameras ---------------------------------
+// ---- point kernel: thread = (point, camera chunk); a second kernel adds the chunks in a fixed order ----------------
+// (one thread per point looping over all cameras is a single 300-trip dependent FP64 chain on 32 CTAs: latency-bound)
+constexpr int PT_MAX_CHUNKS = 32;
+
 __global__ void __launch_bounds__(PT_THREADS)
 ba_point_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z,
-                const double* __restrict__ cams, int nt, int nc, int cam_first, int cam_count, double* __restrict__ V,
-                double* __restrict__ g, double* __restrict__ cost_part)
+                const double* __restrict__ cams, int nt, int nc, int cam_first, int cam_count, int nchunks, double* __restrict__ part)
 {
     __shared__ double sK[9];
-    __shared__ double sred[PT_THREADS / 32];
-    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid;
+    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid, chunk = blockIdx.y;
     if (tid < 9) sK[tid] = Kg[tid];
     __syncthreads();
+    if (i >= nt) return;
+    const int per = (cam_count + nchunks - 1) / nchunks;
+    const int c0 = cam_first + chunk * per, c1 = min(cam_first + cam_count, c0 + per);
+    const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
+    double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0, cost = 0;
+    for (int c = c0; c < c1; ++c) {
+        const double* cm = cams + 12ll * c;
+        double u0, w0, ju[3], jv[3];
+        point_jacobian(sK, cm, cm + 9, c == 0, X, Y, Z, u0, w0, ju, jv);
+        const double ru = z[(long long)c * nt + i] - u0;
+        const double rv = z[(long long)(nc + 1) * nt + (long long)c * nt + i] - w0;
+        v00 += ju[0] * ju[0] + jv[0] * jv[0]; v01 += ju[0] * ju[1] + jv[0] * jv[1]; v02 += ju[0] * ju[2] + jv[0] * jv[2];
+        v11 += ju[1] * ju[1] + jv[1] * jv[1]; v12 += ju[1] * ju[2] + jv[1] * jv[2]; v22 += ju[2] * ju[2] + jv[2] * jv[2];
+        g0 += ju[0] * ru + jv[0] * rv; g1 += ju[1] * ru + jv[1] * rv; g2 += ju[2] * ru + jv[2] * rv;
+        cost += ru * ru + rv * rv;
+    }
+    double* o = part + (long long)chunk * 10 * nt + i;     // [chunk][10][nt]: coalesced across the points of a CTA
+    o[0] = v00; o[(long long)nt] = v01; o[2ll * nt] = v02; o[3ll * nt] = v11; o[4ll * nt] = v12; o[5ll * nt] = v22;
+    o[6ll * nt] = g0; o[7ll * nt] = g1; o[8ll * nt] = g2; o[9ll * nt] = cost;
+}
+
+__global__ void __launch_bounds__(PT_THREADS)
+ba_point_reduce_kernel(const double* __restrict__ part, int nt, int nchunks, double* __restrict__ V, double* __restrict__ g,
+                       double* __restrict__ cost_part)
+{
+    __shared__ double sred[PT_THREADS / 32];
+    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid;
     double cost = 0.0;
     if (i < nt) {
-        const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
-        double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
-        for (int c = cam_first; c < cam_first + cam_count; ++c) {
-            const double* cm = cams + 12ll * c;
-            double u0, w0, ju[3], jv[3];
-            point_jacobian(sK, cm, cm + 9, c == 0, X, Y, Z, u0, w0, ju, jv);
-            const double ru = z[(long long)c * nt + i] - u0;
-            const double rv = z[(long long)(nc + 1) * nt + (long long)c * nt + i] - w0;
-            v00 += ju[0] * ju[0] + jv[0] * jv[0]; v01 += ju[0] * ju[1] + jv[0] * jv[1]; v02 += ju[0] * ju[2] + jv[0] * jv[2];
-            v11 += ju[1] * ju[1] + jv[1] * jv[1]; v12 += ju[1] * ju[2] + jv[1] * jv[2]; v22 += ju[2] * ju[2] + jv[2] * jv[2];
-            g0 += ju[0] * ru + jv[0] * rv; g1 += ju[1] * ru + jv[1] * rv; g2 += ju[2] * ru + jv[2] * rv;
-            cost += ru * ru + rv * rv;
+        double a[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) a[k] = 0.0;
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const double* o = part + (long long)ch * 10 * nt + i;
+#pragma unroll
+            for (int k = 0; k < 10; ++k) a[k] += o[(long long)k * nt];
         }
         double* v = V + 6ll * i;
-        v[0] = v00; v[1] = v01; v[2] = v02; v[3] = v11; v[4] = v12; v[5] = v22;
-        g[3ll * i] = g0; g[3ll * i + 1] = g1; g[3ll * i + 2] = g2;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) v[k] = a[k];
+        g[3ll * i] = a[6]; g[3ll * i + 1] = a[7]; g[3ll * i + 2] = a[8];
+        cost = a[9];
     }
     cost = warp_sum(cost);
     if ((tid & 31) == 0) sred[tid >> 5] = cost;
@@ -402,10 +427,13 @@ VEL_API int vel_ba_accumulate(const double* K, const double* x, const double* z,
                   "vel_ba_accumulate: camera slice [%d,%d) outside [0,%d]", cam_first, cam_first + cam_count, nc);
     cudaStream_t st = (cudaStream_t)stream;
     const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    vel_keep_async_pool_cached();
+    const int nchunks = cam_count >= 16 ? (cam_count / 8 < PT_MAX_CHUNKS ? cam_count / 8 : PT_MAX_CHUNKS) : 1;
     double* tmp = nullptr;
-    VEL_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * (12ull * (nc + 1) + pblocks), st));
+    VEL_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * (12ull * (nc + 1) + pblocks + 10ull * nchunks * nt), st));
     double* cams = tmp;
     double* cost_part = tmp + 12ull * (nc + 1);
+    double* part = cost_part + pblocks;
     ba_cam_setup_kernel<<<(nc + 1 + 127) / 128, 128, 0, st>>>(x, nt, nc, cams);
     VEL_LAUNCH_CHECK("ba_cam_setup_kernel");
     const int first_param = cam_first < 1 ? 1 : cam_first;
@@ -414,8 +442,10 @@ VEL_API int vel_ba_accumulate(const double* K, const double* x, const double* z,
         ba_camera_kernel<<<n_param, CAM_THREADS, 0, st>>>(K, x, z, nt, nc, first_param, U, W, g);
         VEL_LAUNCH_CHECK("ba_camera_kernel");
     }
-    ba_point_kernel<<<pblocks, PT_THREADS, 0, st>>>(K, x, z, cams, nt, nc, cam_first, cam_count, V, g, cost_part);
+    ba_point_kernel<<<dim3(pblocks, nchunks), PT_THREADS, 0, st>>>(K, x, z, cams, nt, nc, cam_first, cam_count, nchunks, part);
     VEL_LAUNCH_CHECK("ba_point_kernel");
+    ba_point_reduce_kernel<<<pblocks, PT_THREADS, 0, st>>>(part, nt, nchunks, V, g, cost_part);
+    VEL_LAUNCH_CHECK("ba_point_reduce_kernel");
     ba_cost_finalize_kernel<<<1, 32, 0, st>>>(cost_part, pblocks, cost);
     VEL_LAUNCH_CHECK("ba_cost_finalize_kernel");
     VEL_CUDA(cudaFreeAsync(tmp, st));
@@ -761,6 +791,7 @@ VEL_API int vel_ba2_accumulate(const double* K, const double* x, const double* z
     const int nq = B2_SHARED + nc;
     double* tmp = nullptr;
     const size_t n_tmp = 12ull * (nc + 1) + 36 + 27ull * (nc + 1) + pblocks;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&tmp, sizeof(double) * n_tmp, st));
     double* offs = tmp;
     double* dcm = offs + 12ull * (nc + 1);

@@ -12,6 +12,11 @@
 // thread-local last-error buffer (defined in api.cu)
 void vel_set_error(const char* fmt, ...);
 
+// Stream-ordered scratch (cudaMallocAsync) would be returned to the OS at every synchronisation with the default release
+// threshold of the device's memory pool and re-mapped by the next call (milliseconds for a few MB); entry points that
+// take scratch call this first: it raises the threshold once per device (defined in api.cu).
+void vel_keep_async_pool_cached();
+
 #define VEL_CHECK_ARG(cond, ...)          \
     do {                                  \
         if (!(cond)) {                    \

@@ -168,6 +168,7 @@ static int knn2_hamming256_popc(const uint8_t* q, int32_t nq, const uint8_t* t, 
     if (t_per_split < MT_TILE) t_per_split = MT_TILE;
     const int nsp = nt > 0 ? (nt + t_per_split - 1) / t_per_split : 1;
     int4* part = nullptr;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsp, st));
     dim3 grid((nq + MQ_THREADS - 1) / MQ_THREADS, nsp);
     knn2_hamming256_partial_kernel<<<grid, MQ_THREADS, 0, st>>>((const uint4*)q, nq, (const uint4*)t, nt, t_per_split, part);
@@ -213,6 +214,7 @@ VEL_API int vel_match_knn2_l2(const float* q, int32_t nq, const float* t, int32_
     if (t_per_split < TT) t_per_split = TT;
     const int nsp = nt > 0 ? (nt + t_per_split - 1) / t_per_split : 1;
     float4* part = nullptr;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(float4) * (size_t)nq * nsp, st));
     dim3 grid((nq + MQ_THREADS - 1) / MQ_THREADS, nsp);
     if (dim == 64) knn2_l2_partial_kernel<64><<<grid, MQ_THREADS, 0, st>>>(q, nq, t, nt, t_per_split, part);

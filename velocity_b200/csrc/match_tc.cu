@@ -334,6 +334,7 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
     using namespace tc;
     int8_t* qe = nullptr;
     int8_t* te = nullptr;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&qe, (size_t)nq * 256, st));
     VEL_CUDA(cudaMallocAsync((void**)&te, (size_t)nt * 256, st));
     expand_pm1_kernel<<<(unsigned)(((long long)nq * 32 + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, (uint2*)qe);
@@ -357,6 +358,7 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
     }
     nsplit = (nblk_total + nblk_per_split - 1) / nblk_per_split;
     int4* part = nullptr;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsplit * 2, st));   // two column halves per split
     static bool attr_set = false;
     if (!attr_set) {

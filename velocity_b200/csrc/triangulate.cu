@@ -236,6 +236,7 @@ VEL_API int vel_triangulate_2v(const double* A, const double* U, int32_t nf, int
     const int j_per_chunk = (nf - 1 + nchunks - 1) / nchunks;
     nchunks = (nf - 1 + j_per_chunk - 1) / j_per_chunk;
     double* part = nullptr;
+    vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(double) * 3ull * nv * nchunks, st));
     tri_2v_partial_kernel<<<dim3(pblocks, nchunks), TRI_THREADS, 0, st>>>(A, U, nf, nv, j_per_chunk, part);
     VEL_LAUNCH_CHECK("tri_2v_partial_kernel");

@@ -247,15 +247,23 @@ def run_ours(args):
     o_pts = torch.empty((PAIRS, NPTS, 2), dtype=torch.float32).pin_memory()
     o_st = torch.empty((PAIRS, NPTS), dtype=torch.uint8).pin_memory()
     o_err = torch.empty((PAIRS, NPTS), dtype=torch.float32).pin_memory()
-    for _ in range(max(1, args.warmup // 2)):
-        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
+    use_graph = not args.no_graph
+    try:
+        for _ in range(max(2, args.warmup // 2)):
+            h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err, graph=use_graph)
+    except Exception as ex:  # capture refused by this driver/torch build: same GPU pipeline, issued eagerly from Python
+        sys.stderr.write("bench.py: CUDA-graph capture of the e2e pipeline failed (%r); timing the eager pipeline\n" % (ex,))
+        use_graph = False
+        tracker = SequenceTracker(H, W, NPTS, chunk=chunk, fbt=FBT, **LK)
+        for _ in range(max(1, args.warmup // 2)):
+            h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
     barrier()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         l2_flush.zero_()  # nothing of the previous step survives in L2 (frames come from the host anyway)
-        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
+        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err, graph=use_graph)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
@@ -307,7 +315,7 @@ def run_ours(args):
                                             "achieved": PAIRS * SEQ_BYTES_PER_FRAME_FB / (ms_per_step * 1e-3) / 1e9}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "valid_fraction": e2e_valid, "chunk_frames": chunk},
+                    "ms_per_step": e2e_ms / args.steps, "valid_fraction": e2e_valid, "chunk_frames": chunk, "cuda_graph": use_graph},
             "gpu_launches": args.steps * (LK["maxLevel"] + 1),
             "clocks": clk,
         }
@@ -324,6 +332,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=8, help="frames per H2D/compute pipeline chunk of the e2e path")
+    ap.add_argument("--no-graph", action="store_true", help="issue the e2e chunk pipeline eagerly instead of replaying its CUDA graph")
     ap.add_argument("--z0", type=float, default=Z0_M, help="plane depth (m) of the synthetic generator")
     args = ap.parse_args()
     Z0_M = args.z0

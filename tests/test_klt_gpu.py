@@ -284,6 +284,18 @@ def test_sequence_tracker_host_api_matches_per_pair_calls(cuda):
     for k in range(6):
         q2, qv, qerr = KLT.cv2calcOpticalFlowPyrLK(frames[k], frames[k + 1], pts, None, fbt=1.0, **lk)
         assert np.array_equal(p2[k], q2) and np.array_equal(v[k], qv) and np.array_equal(err[k], qerr.ravel())
+    # the same pipeline replayed as one CUDA graph (what bench.py's e2e number times): identical results, also on re-use
+    from velocity_b200.sequence import SequenceTracker
+
+    tr = SequenceTracker(270, 480, 300, chunk=3, fbt=1.0, **lk)
+    fh, ph = cuda.from_numpy(frames).pin_memory(), cuda.from_numpy(pts).pin_memory()
+    op = cuda.empty((6, 300, 2), dtype=cuda.float32).pin_memory()
+    os_ = cuda.empty((6, 300), dtype=cuda.uint8).pin_memory()
+    oe = cuda.empty((6, 300), dtype=cuda.float32).pin_memory()
+    for rep in range(3):
+        op.zero_(); os_.zero_(); oe.zero_()
+        tr.run(fh, ph, op, os_, oe, graph=True)
+        assert np.array_equal(op.numpy(), p2) and np.array_equal(os_.numpy() != 0, v) and np.array_equal(oe.numpy(), err), rep
 
 
 def test_bgr2gray_bit_exact(cuda):

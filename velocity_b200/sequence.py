@@ -30,13 +30,35 @@ class SequenceTracker:
         self.batches = [FrameBatch(s, self.win, self.params.max_level) for s in self.slots]
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.launches = 0
+        self._graph = self._graph_key = self._graph_bytes = self._graph_keep = None
 
-    def run(self, frames_host, pts_host, out_pts, out_status, out_err):
+    def run(self, frames_host, pts_host, out_pts, out_status, out_err, graph=False):
         """frames_host: pinned uint8 [F,H,W]; pts_host: pinned float32 [npts,2];
         out_*: pinned host tensors [F-1,npts,2] f32 / [F-1,npts] u8 / [F-1,npts] f32.
-        Returns (h2d_bytes, d2h_bytes).  Synchronises once at the end."""
+        Returns (h2d_bytes, d2h_bytes).  Synchronises once at the end.
+
+        graph=True captures the whole chunk pipeline (every H2D copy, K1/K2 launch and D2H copy on both streams) into
+        one CUDA graph the first time it sees a set of buffers and replays it afterwards: a step then costs one launch
+        from the host, so the copy engine is never left waiting for Python to issue the next chunk."""
+        if graph:
+            key = (frames_host.data_ptr(), tuple(frames_host.shape), pts_host.data_ptr(), out_pts.data_ptr(), out_status.data_ptr(),
+                   out_err.data_ptr())
+            if self._graph_key != key:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=self.dev)
+                side.wait_stream(torch.cuda.current_stream(self.dev))
+                with torch.cuda.graph(g, stream=side):
+                    self._graph_bytes = self._run_chunks(frames_host, pts_host, out_pts, out_status, out_err, capturing=True)
+                self._graph, self._graph_key = g, key
+            self._graph.replay()
+            torch.cuda.current_stream(self.dev).synchronize()
+            return self._graph_bytes
+        return self._run_chunks(frames_host, pts_host, out_pts, out_status, out_err, capturing=False)
+
+    def _run_chunks(self, frames_host, pts_host, out_pts, out_status, out_err, capturing):
         F = frames_host.shape[0]
         compute = torch.cuda.current_stream(self.dev)
+        self.copy_stream.wait_stream(compute)          # the copy stream forks from the compute stream (required under capture)
         pts = pts_host.to(self.dev, non_blocking=True)
         h2d, d2h = pts_host.numel() * 4, 0
         nchunks = (F - 1 + self.chunk - 1) // self.chunk
@@ -88,7 +110,11 @@ class SequenceTracker:
             ev = torch.cuda.Event()
             ev.record(compute)
             slot_free[s] = ev
-        compute.synchronize()
+        compute.wait_stream(self.copy_stream)           # join
+        if capturing:
+            self._graph_keep = (results, pts)            # tensors of the graph's private pool stay referenced
+        else:
+            compute.synchronize()
         return h2d, d2h
 
     def _sub_batch(self, fb, nframes):

@@ -47,7 +47,7 @@ class SequenceTracker:
                 g = torch.cuda.CUDAGraph()
                 side = torch.cuda.Stream(device=self.dev)
                 side.wait_stream(torch.cuda.current_stream(self.dev))
-                with torch.cuda.graph(g, stream=side):
+                with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):   # other threads (NCCL watchdog) may touch CUDA
                     self._graph_bytes = self._run_chunks(frames_host, pts_host, out_pts, out_status, out_err, capturing=True)
                 self._graph, self._graph_key = g, key
             self._graph.replay()

@@ -200,55 +200,102 @@ lk_track_w15h_kernel(const LkArgs A)
                         hi7[q] = ldg_u8(I.p + (yo + xo[4])) | (ldg_u8(I.p + (yo + xo[5])) << 8) | (ldg_u8(I.p + (yo + xo[6])) << 16);
                     }
                 }
-                int hd[3][5], hs[3][5];      // rings: horizontal taps of the last three image rows
-                int gx[2][5], gy[2][5];      //        Scharr pair of the last two tile rows
-                unsigned win1[3], win2[3];   //        byte windows 1..4 / 2..5 of the last three image rows
+                if (interior) {
+                    // Interior windows: the bilinear sample and the Scharr pair are both linear in the image, so the
+                    // interpolated derivative equals the Scharr pair of the interpolated image B = w00 I(y,x) + w01 I(y,x+1)
+                    // + w10 I(y+1,x) + w11 I(y+1,x+1) EXACTLY (integers, before the >> 14) -- one DP2A grid instead of a
+                    // DP4A derivative grid followed by four multiplies per derivative per pixel.  (Outside the frame the
+                    // derivative image is zero-padded, which is not linear in I: those windows take the branch below.)
+                    int Bt[6];                   // top-row contributions of the B row in flight
+                    int Br[3][6];                // ring: the last three complete B rows (B row y <-> tile row 4rq - 1 + y)
+                    int hdr[3][4], hsr[3][4];    // their horizontal difference / smoothing taps at the lane's 4 columns
 #pragma unroll
-                for (int q = 0; q < 7; ++q) {
-                    const unsigned lo = lo7[q], hi = hi7[q];
-                    const int c = q % 3;
-                    win1[c] = __funnelshift_r(lo, hi, 8);
-                    win2[c] = __funnelshift_r(lo, hi, 16);
-                    const unsigned win3 = __funnelshift_r(lo, hi, 24);
-                    const unsigned wins[5] = {lo, win1[c], win2[c], win3, hi};
-#pragma unroll
-                    for (int t = 0; t < 5; ++t) {
-                        hd[c][t] = dp4a_us(wins[t], 0x000100FF, 0);   // (-1, 0, +1, 0)
-                        hs[c][t] = dp4a_us(wins[t], 0x00030A03, 0);   // ( 3,10,  3, 0)
-                    }
-                    if (q >= 2) {
-                        const int y = q - 2;                       // tile row 4rq + y, centred on image row q - 1
-                        const int d = y & 1, c0 = (q - 2) % 3, c1 = (q - 1) % 3;
-#pragma unroll
-                        for (int t = 0; t < 5; ++t) {
-                            gx[d][t] = 3 * (hd[c0][t] + hd[c][t]) + 10 * hd[c1][t];
-                            gy[d][t] = hs[c][t] - hs[c0][t];
-                        }
-                        if (!interior) {   // the derivative image is padded with constant 0 outside the frame
-                            const bool in_y = (unsigned)(ipy + 4 * rq + y) < (unsigned)I.h;
-#pragma unroll
-                            for (int t = 0; t < 5; ++t) {
-                                if (!(in_y && (unsigned)(ipx + 4 * cg + t) < (unsigned)I.w)) { gx[d][t] = 0; gy[d][t] = 0; }
-                            }
-                        }
-                        if (y >= 1) {
-                            const int rr = y - 1;                  // pixel row: Scharr rows rr (d ^ 1) and rr + 1 (d); image rows q-2, q-1
-                            int pI[4], pgx[4], pgy[4];
+                    for (int q = 0; q < 7; ++q) {
+                        const unsigned lo = lo7[q], hi = hi7[q];
+                        const unsigned v1 = __funnelshift_r(lo, hi, 8), v5 = hi >> 8;
+                        if (q >= 1) {            // bottom row of B row y = q - 1
+                            const int y = q - 1, c = y % 3;
+                            Br[c][0] = dp2a_lo(W1, lo, Bt[0]); Br[c][1] = dp2a_lo(W1, v1, Bt[1]); Br[c][2] = dp2a_hi(W1, lo, Bt[2]);
+                            Br[c][3] = dp2a_hi(W1, v1, Bt[3]); Br[c][4] = dp2a_lo(W1, hi, Bt[4]); Br[c][5] = dp2a_lo(W1, v5, Bt[5]);
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                const bool active = (cg < 3 || j < 3) && (rq < 3 || rr < 3);
-                                const unsigned top = (j & 1) ? win2[c0] : win1[c0], bot = (j & 1) ? win2[c1] : win1[c1];
-                                const int s = (j & 2) ? dp2a_hi(W1, bot, dp2a_hi(W0, top, 1 << 8)) : dp2a_lo(W1, bot, dp2a_lo(W0, top, 1 << 8));
-                                const int ival = s >> 9;
-                                int ix = (gx[d ^ 1][j] * w.w00 + gx[d ^ 1][j + 1] * w.w01 + gx[d][j] * w.w10 + gx[d][j + 1] * w.w11 + (1 << 13)) >> 14;
-                                int iy = (gy[d ^ 1][j] * w.w00 + gy[d ^ 1][j + 1] * w.w01 + gy[d][j] * w.w10 + gy[d][j + 1] * w.w11 + (1 << 13)) >> 14;
-                                if (!active) { ix = 0; iy = 0; }
-                                pI[j] = (1 << 8) - (ival << 9); pgx[j] = ix; pgy[j] = iy;
-                                a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                                hdr[c][j] = Br[c][j + 2] - Br[c][j];
+                                hsr[c][j] = 3 * (Br[c][j] + Br[c][j + 2]) + 10 * Br[c][j + 1];
                             }
-                            rP[rr] = make_int4(pI[0], pI[1], pI[2], pI[3]);
-                            rP[4 + rr] = make_int4(pgx[0], pgx[1], pgx[2], pgx[3]);
-                            rP[8 + rr] = make_int4(pgy[0], pgy[1], pgy[2], pgy[3]);
+                            if (y >= 2) {        // pixel row rr = y - 2: B rows y-2 (above), y-1 (centre), y (below)
+                                const int rr = y - 2, ca = (y - 2) % 3, cc = (y - 1) % 3;
+                                int pI[4], pgx[4], pgy[4];
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const bool active = (cg < 3 || j < 3) && (rq < 3 || rr < 3);
+                                    int ix = (3 * (hdr[ca][j] + hdr[c][j]) + 10 * hdr[cc][j] + (1 << 13)) >> 14;
+                                    int iy = (hsr[c][j] - hsr[ca][j] + (1 << 13)) >> 14;
+                                    if (!active) { ix = 0; iy = 0; }
+                                    const int ival = (Br[cc][j + 1] + (1 << 8)) >> 9;
+                                    pI[j] = (1 << 8) - (ival << 9); pgx[j] = ix; pgy[j] = iy;
+                                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                                }
+                                rP[rr] = make_int4(pI[0], pI[1], pI[2], pI[3]);
+                                rP[4 + rr] = make_int4(pgx[0], pgx[1], pgx[2], pgx[3]);
+                                rP[8 + rr] = make_int4(pgy[0], pgy[1], pgy[2], pgy[3]);
+                            }
+                        }
+                        if (q < 6) {             // top row of B row y = q
+                            Bt[0] = dp2a_lo(W0, lo, 0); Bt[1] = dp2a_lo(W0, v1, 0); Bt[2] = dp2a_hi(W0, lo, 0);
+                            Bt[3] = dp2a_hi(W0, v1, 0); Bt[4] = dp2a_lo(W0, hi, 0); Bt[5] = dp2a_lo(W0, v5, 0);
+                        }
+                    }
+                } else {
+                    int hd[3][5], hs[3][5];      // rings: horizontal taps of the last three image rows
+                    int gx[2][5], gy[2][5];      //        Scharr pair of the last two tile rows
+                    unsigned win1[3], win2[3];   //        byte windows 1..4 / 2..5 of the last three image rows
+    #pragma unroll
+                    for (int q = 0; q < 7; ++q) {
+                        const unsigned lo = lo7[q], hi = hi7[q];
+                        const int c = q % 3;
+                        win1[c] = __funnelshift_r(lo, hi, 8);
+                        win2[c] = __funnelshift_r(lo, hi, 16);
+                        const unsigned win3 = __funnelshift_r(lo, hi, 24);
+                        const unsigned wins[5] = {lo, win1[c], win2[c], win3, hi};
+    #pragma unroll
+                        for (int t = 0; t < 5; ++t) {
+                            hd[c][t] = dp4a_us(wins[t], 0x000100FF, 0);   // (-1, 0, +1, 0)
+                            hs[c][t] = dp4a_us(wins[t], 0x00030A03, 0);   // ( 3,10,  3, 0)
+                        }
+                        if (q >= 2) {
+                            const int y = q - 2;                       // tile row 4rq + y, centred on image row q - 1
+                            const int d = y & 1, c0 = (q - 2) % 3, c1 = (q - 1) % 3;
+    #pragma unroll
+                            for (int t = 0; t < 5; ++t) {
+                                gx[d][t] = 3 * (hd[c0][t] + hd[c][t]) + 10 * hd[c1][t];
+                                gy[d][t] = hs[c][t] - hs[c0][t];
+                            }
+                            if (!interior) {   // the derivative image is padded with constant 0 outside the frame
+                                const bool in_y = (unsigned)(ipy + 4 * rq + y) < (unsigned)I.h;
+    #pragma unroll
+                                for (int t = 0; t < 5; ++t) {
+                                    if (!(in_y && (unsigned)(ipx + 4 * cg + t) < (unsigned)I.w)) { gx[d][t] = 0; gy[d][t] = 0; }
+                                }
+                            }
+                            if (y >= 1) {
+                                const int rr = y - 1;                  // pixel row: Scharr rows rr (d ^ 1) and rr + 1 (d); image rows q-2, q-1
+                                int pI[4], pgx[4], pgy[4];
+    #pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const bool active = (cg < 3 || j < 3) && (rq < 3 || rr < 3);
+                                    const unsigned top = (j & 1) ? win2[c0] : win1[c0], bot = (j & 1) ? win2[c1] : win1[c1];
+                                    const int s = (j & 2) ? dp2a_hi(W1, bot, dp2a_hi(W0, top, 1 << 8)) : dp2a_lo(W1, bot, dp2a_lo(W0, top, 1 << 8));
+                                    const int ival = s >> 9;
+                                    int ix = (gx[d ^ 1][j] * w.w00 + gx[d ^ 1][j + 1] * w.w01 + gx[d][j] * w.w10 + gx[d][j + 1] * w.w11 + (1 << 13)) >> 14;
+                                    int iy = (gy[d ^ 1][j] * w.w00 + gy[d ^ 1][j + 1] * w.w01 + gy[d][j] * w.w10 + gy[d][j + 1] * w.w11 + (1 << 13)) >> 14;
+                                    if (!active) { ix = 0; iy = 0; }
+                                    pI[j] = (1 << 8) - (ival << 9); pgx[j] = ix; pgy[j] = iy;
+                                    a11 += ix * ix; a12 += ix * iy; a22 += iy * iy;
+                                }
+                                rP[rr] = make_int4(pI[0], pI[1], pI[2], pI[3]);
+                                rP[4 + rr] = make_int4(pgx[0], pgx[1], pgx[2], pgx[3]);
+                                rP[8 + rr] = make_int4(pgy[0], pgy[1], pgy[2], pgy[3]);
+                            }
                         }
                     }
                 }

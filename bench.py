@@ -5,14 +5,20 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[1], "C2"): synthetic 1080p frames, 4096 Harris tracks, pyramidal LK
-15x15, 3 pyramid levels, <=10 iterations, eps 0.1, forward-backward threshold 1.0 -- i.e. the
-reference call utils.KLT.cv2calcOpticalFlowPyrLK(im0, im1, p0, fbt=1.0, winSize=(15,15), maxLevel=2,
-criteria=(EPS|COUNT,10,0.1)) applied to every consecutive pair of a frame sequence.
+Workload = BASELINE.json configs[2] ("C3"), the configuration the metric "SFM frames/sec @1080p, 4k tracks" is
+quoted on: a synthetic 300-frame 1080p sequence (SURVEY 8(d) generator: blurred-noise plane approaching at 40 km/h,
+one continuous run), 4096 Harris tracks PROPAGATED frame to frame with the reference's LK wrapper
+(utils/KLT.py:37-51; 15x15, 3 levels, <=10 it, eps 0.1, forward-backward gate 1.0), fcnNLS_t per frame
+(vidExample.py:139), fcnNvintercept over all frames, then 10 iterations of fcnNLS_batch (nt=4096, nc=299) on the
+TRACKED observations.  One STEP = one whole sequence; value = frames per second, whole job.
 
-One STEP = one pass over a batch of PAIRS consecutive frame pairs (PAIRS+1 frames, ~270 MB > the
-126 MB L2, so every step streams its frames from HBM): K1 builds each frame's pyramid once, K2
-tracks all pairs forward+backward in one launch.  value = frames (pairs) per second, whole job.
+    value      frames resident in HBM when the timed region starts
+    e2e        the same job through velocity_b200.sfm.SfmSequence.run with HOST frames (pinned): chunked H2D inside the
+               timed region, the result tables (S, S_ba, B, P) copied back
+    roofline   the KLT kernel (K2) against the SURVEY 8(d) byte model, measured on a batch of 128 consecutive pairs
+               of the same sequence in ONE launch (BASELINE configs[1], "C2"), with K1 and the in-sequence figure beside it
+    --impl reference   the reference's CPU path for the same stages on the host cores (cv2 LK + the numpy restatement
+               of the solvers, oracle/), each step a bounded sample extrapolated to the whole sequence (stated in `sample`)
 """
 import argparse
 import json
@@ -27,15 +33,19 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-H, W, NPTS = 1080, 1920, 4096
+H, W, NPTS, NFRAMES = 1080, 1920, 4096, 300
 LK = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
 FBT = 1.0
-PAIRS = 128            # frame pairs per step and per GPU
-UNIQUE_FRAMES = 24     # distinct rendered frames (one approach run of the generator, no depth reset inside); the batch tiles them
-SEED = 1234
-Z0_M = 40.0           # plane depth of the generator: >= 99% of the tracks pass the FB gate over the whole approach
-                      # (SURVEY 8(d) suggests 10 m, where 3 levels of 15x15 cannot follow the 37 px/frame corner flow
-                      # and only ~21% survive; use --z0 10 to reproduce that worst case)
+BA_ITERS = 10
+SEED = 2025
+Z_START_M = 200.0      # plane depth in frame 0; 40 km/h for 300 frames brings it to 89 m (image grows 2.24x): >= 99 % of the
+V_KMH = 40.0           # tracks survive the whole sequence, so the bundle adjustment sees nt = 4096 full-length tracks
+FPS = 29.97
+C2_PAIRS = 128         # pairs per launch of the K2 roofline leg
+
+METRIC = "SFM frames/sec @1080p, 4k tracks (KLT propagated + fcnNLS_t per frame + triangulation + 10-it BA)"
+UNIT = "frames/s"
+DTYPE = "u8/int32 fixed point + f32 2x2 solve (KLT); f64 (pose, triangulation, BA)"
 
 # Algorithmic bytes (restated in DESIGN.md): HW = H*W, Py = HW*(1 + 1/4 + 1/16)
 HW_B = H * W
@@ -43,7 +53,15 @@ PY_B = HW_B + (HW_B // 4) + (HW_B // 16)
 PT_B = NPTS * (8 + 8 + 1 + 4)
 K1_BYTES_PER_FRAME = HW_B + (PY_B - HW_B)        # frame read once, levels >= 1 written once
 K2_BYTES_PER_PAIR_FB = 4 * PY_B + PT_B           # prev+next pyramids, forward and backward pass, point I/O
-SEQ_BYTES_PER_FRAME_FB = K1_BYTES_PER_FRAME + K2_BYTES_PER_PAIR_FB  # = 13,694,016 (SURVEY's sequence figure)
+
+
+def workload_config():
+    """The workload-defining keys, identical in both arms."""
+    return {"workload": "C3: synthetic 1080p 300-frame sequence, 4096 tracks propagated frame to frame (LK 15x15, 3 levels, "
+                        "<=10 it, eps 0.1, fbt 1.0), fcnNLS_t per frame, fcnNvintercept over all frames, 10-iteration fcnNLS_batch "
+                        "(nt=4096, nc=299)",
+            "frames": NFRAMES, "height": H, "width": W, "tracks": NPTS, "plane_start_depth_m": Z_START_M, "speed_kmh": V_KMH,
+            "fps": FPS, "ba_iterations": BA_ITERS, "seed": SEED}
 
 
 def measured_peaks():
@@ -54,25 +72,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def make_frames(n_unique, seed):
+def make_sequence(seed):
+    """frames uint8 [n,H,W], seeds p0 [NPTS,2] f32, planar points p3 [NPTS,3] f64 (frame-0 camera frame), frame times, depths."""
     from velocity_b200 import synth
 
-    frames, _ = synth.plane_sequence(n_unique, h=H, w=W, seed=seed, Z0=Z0_M)
-    pts = synth.harris_tracks(frames[0], NPTS)
-    return np.stack(frames), pts
-
-
-def tile_sequence(unique, n):
-    """n frames cycling forward/backward through the unique frames (every neighbour pair is a real
-    consecutive pair of the rendered sequence, so the per-pair work is representative)."""
-    u = unique.shape[0]
-    idx, i, d = [], 0, 1
-    for _ in range(n):
-        idx.append(i)
-        if i + d < 0 or i + d >= u:
-            d = -d
-        i += d
-    return idx
+    K = synth.K_1080P
+    frames, Z = synth.approach_sequence(NFRAMES, h=H, w=W, seed=seed, z_start=Z_START_M, v_kmh=V_KMH, dt=1 / FPS)
+    p0 = synth.approach_tracks(frames[0], NPTS, Z[0] / Z[-1])
+    # vidExample.py:119 with the known plane pose (R = I, t = (0, 0, Z0)): p3 = image2world(p) @ R + t
+    p3 = np.concatenate([(p0 - K[2, 0:2]) / K[0, 0] * Z[0], np.full((NPTS, 1), Z[0])], 1).astype(np.float64)
+    times = (np.arange(NFRAMES) / FPS).astype(np.float32)
+    return K, frames, p0, p3, times, Z
 
 
 class ClockSampler:
@@ -113,98 +123,181 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_run(unique, pts, steps, warmup, sample_pairs):
-    """The reference's CPU implementation of the path on this host.  The reference's arithmetic is
-    cv2.calcOpticalFlowPyrLK (third-party, un-vendored); oracle/ holds a restatement of the wrapper
-    (oracle/klt_oracle.lk_forward_backward <- utils/KLT.py:37-51).  When opencv-python is importable
-    the third-party arithmetic is executed by cv2 itself -- literally what the reference runs, and
-    faster than the scalar C restatement, so the speed-up is not flattered; otherwise by
-    oracle/velocity_oracle.c (OpenMP, all cores)."""
-    try:
+# ---- the reference's CPU path (shared by --impl reference and the cpu_baseline leg of our arm) ---------------------------
+class CpuReference:
+    """The reference's CPU implementation of the C3 stages on this host.
+
+    Tracking: the reference's wrapper utils/KLT.py:37-51 with the third-party arithmetic executed by opencv-python itself
+    (cv2.calcOpticalFlowPyrLK forward + backward, all host threads) -- literally what the reference runs.  Solvers: the
+    numpy restatement of utils/NLS.py / utils/MSV.py in oracle/sfm_oracle.py (fcnNLS_t as written; fcnNvintercept
+    vectorised; fcnNLS_batch through the block-sparse Schur form `bundle_sparse`, because the reference's dense
+    formulation needs a 277 GB Jacobian at nt=4096, nc=299 -- SURVEY.md 8(d)).
+
+    One `step()` is a BOUNDED sample: `sample_pairs` consecutive pairs of KLT + fcnNLS_t, the full-size triangulation, and
+    ONE full-size BA iteration; the whole-sequence time is extrapolated as
+        299 * (t_klt + t_pose) / sample_pairs + t_triangulate + ba_iterations * t_ba_iteration."""
+
+    def __init__(self, K, frames, p0, p3, times, tracks=None, alive=None, sample_pairs=10):
         import cv2
 
-        cores = cv2.getNumThreads()
+        from oracle import seq_oracle, sfm_oracle
 
-        def one_pair(a, b):
-            p2, st, err = cv2.calcOpticalFlowPyrLK(a, b, pts, None, **LK)
-            v = st.ravel().astype(bool)
-            p1, st2, _ = cv2.calcOpticalFlowPyrLK(b, a, p2, None, **LK)
-            d = pts - p1
-            return p2, v & st2.ravel().astype(bool) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < np.float32(FBT))
+        self.cv2, self.Q, self.S = cv2, seq_oracle, sfm_oracle
+        self.K, self.frames, self.p0, self.p3, self.times = K, frames, p0, p3, times
+        self.sample_pairs = sample_pairs
+        self.cores = cv2.getNumThreads()
+        self.backend = "opencv-python %s cv2.calcOpticalFlowPyrLK fwd+bwd (%d threads) + numpy %s solvers (oracle/sfm_oracle.py)" % (
+            cv2.__version__, self.cores, np.__version__)
+        self.setup_s = 0.0
+        if tracks is None:     # untimed setup: track the whole sequence once so that the BA sample sees real tracked observations
+            t0 = time.perf_counter()
+            tracks, alive = seq_oracle.track_sequence(frames, p0, lk_fn=self.lk_pair)
+            self.setup_s = time.perf_counter() - t0
+        self.tracks, self.alive = tracks, alive
+        self.cursor = 0
 
-        backend = "opencv-python %s (cv2.calcOpticalFlowPyrLK fwd+bwd, %d threads)" % (cv2.__version__, cores)
-    except Exception:
-        from oracle import klt_oracle
+    def lk_pair(self, a, b, p):
+        cv2 = self.cv2
+        p2, st, _ = cv2.calcOpticalFlowPyrLK(a, b, p, None, **LK)
+        p1, st2, _ = cv2.calcOpticalFlowPyrLK(b, a, p2, None, **LK)
+        d = p - p1
+        v = st.ravel().astype(bool) & st2.ravel().astype(bool) & (np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) < np.float32(FBT))
+        return p2, v
 
-        cores = os.cpu_count()
+    def speed_table(self):
+        B, S, _, _ = self.Q.pose_table(self.K, self.tracks, self.alive, self.p3, self.times)
+        return B, S
 
-        def one_pair(a, b):
-            p2, v, _ = klt_oracle.lk_forward_backward(a, b, pts, fbt=FBT, **LK)
-            return p2, v
-
-        backend = "oracle/velocity_oracle.c (OpenMP, %d threads)" % cores
-    idx = tile_sequence(unique, sample_pairs + 1)
-    times = []
-    for it in range(warmup + steps):
+    def step(self):
+        Q, S = self.Q, self.S
+        n, sp = NFRAMES, self.sample_pairs
+        lo = self.cursor % (n - 1 - sp)
+        self.cursor += sp
         t0 = time.perf_counter()
-        for k in range(sample_pairs):
-            one_pair(unique[idx[k]], unique[idx[k + 1]])
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    per_step = float(np.mean(times))
-    return sample_pairs / per_step, per_step * 1e3, cores, backend
+        p, vg = self.tracks[lo][self.alive[lo]].copy(), self.alive[lo].copy()
+        for i in range(lo + 1, lo + 1 + sp):                                   # vidExample.py:134-139 on sample_pairs frames
+            p2, v = self.lk_pair(self.frames[i - 1], self.frames[i], p)
+            vg[vg] = v
+            p = p2[v]
+            S.solve_translation(self.K, p.astype(float), self.p3[vg], np.array([0.0, 0.0, 1.0]))
+        t1 = time.perf_counter()
+        P, idx = Q.ba_inputs(self.tracks, self.alive)
+        if not hasattr(self, "B"):
+            self.B, _ = self.speed_table()
+        U = Q.unit_rays_all(self.K, self.tracks[:, idx])
+        A = (self.B[0, 0:3] - self.B[:, 0:3]).astype(float)
+        C0 = Q.triangulate_rays_vec(A, U)
+        t2 = time.perf_counter()
+        S.bundle_sparse(self.K, P, C0, self.B[:, 3:6].astype(float), max_iter=1)
+        t3 = time.perf_counter()
+        t_full = (n - 1) * (t1 - t0) / sp + (t2 - t1) + BA_ITERS * (t3 - t2)
+        return dict(measured_s=t3 - t0, full_s=t_full, klt_pose_s_per_frame=(t1 - t0) / sp, triangulate_s=t2 - t1, ba_iteration_s=t3 - t2)
+
+    def klt_one_thread(self, pairs=2):
+        cv2 = self.cv2
+        n0 = cv2.getNumThreads()
+        cv2.setNumThreads(1)
+        try:
+            t0 = time.perf_counter()
+            for i in range(1, 1 + pairs):
+                self.lk_pair(self.frames[i - 1], self.frames[i], self.tracks[i - 1][self.alive[i - 1]])
+            return pairs / (time.perf_counter() - t0)
+        finally:
+            cv2.setNumThreads(n0)
+
+    def sample_text(self):
+        return ("per step: %d consecutive 1080p pairs of KLT fwd+bwd + fcnNLS_t (4096 tracks), the full-size fcnNvintercept, ONE "
+                "full-size BA iteration (nt=4096, nc=299); whole-sequence time extrapolated as 299*(klt+pose)/%d + triangulate + "
+                "%d*ba_iteration; %s" % (self.sample_pairs, self.sample_pairs, BA_ITERS, self.backend))
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    unique, pts = make_frames(4, SEED)
-    sample = 8
-    fps, ms, cores, backend = cpu_reference_run(unique, pts, args.steps, args.warmup, sample)
+    K, frames, p0, p3, times, Z = make_sequence(SEED)
+    ref = CpuReference(K, frames, p0, p3, times)
+    B, S = ref.speed_table()
+    ref.B = B
+    res = []
+    for it in range(args.warmup + args.steps):
+        r = ref.step()
+        if it >= args.warmup:
+            res.append(r)
+    full_s = float(np.mean([r["full_s"] for r in res]))
+    measured_ms = float(np.mean([r["measured_s"] for r in res])) * 1e3
+    fps = NFRAMES / full_s
     line = {
-        "impl": "reference", "metric": "SFM frames/sec @1080p, 4k tracks (KLT pyramidal LK fwd+bwd, 3 levels)",
-        "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 fixed point + f32 2x2 solve",
-        "data": "synthetic",
-        "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
-                   "pairs_per_step": sample, "tracks": NPTS, "plane_depth_m": Z0_M},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                         "sample": "%d consecutive 1080p pairs per step on the host; %s" % (sample, backend)},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": measured_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+        "config": workload_config(),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": ref.cores, "kind": "port", "sample": ref.sample_text(),
+                         "extrapolated_s_per_sequence": full_s,
+                         "klt_pose_ms_per_frame": float(np.mean([r["klt_pose_s_per_frame"] for r in res])) * 1e3,
+                         "triangulate_ms": float(np.mean([r["triangulate_s"] for r in res])) * 1e3,
+                         "ba_iteration_ms": float(np.mean([r["ba_iteration_s"] for r in res])) * 1e3,
+                         "klt_pairs_per_s_1thread": ref.klt_one_thread(), "setup_tracking_s": ref.setup_s},
+        "result": {"speed_kmh_mean": float(S[1:, 8].mean()), "speed_kmh_std": float(S[1:, 8].std()), "truth_kmh": V_KMH,
+                   "tracks_alive_last": int(ref.alive[-1].sum())},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def bind_to_gpu_numa_node(local):
+    """Pin this rank's host threads (and hence its pinned allocations, first touch) to the CPUs NVML reports as local to
+    its GPU; falls back to an even split of the visible CPUs when every GPU reports the same set."""
+    info = {"cpus": None, "how": "unchanged"}
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        hnd = pynvml.nvmlDeviceGetHandleByIndex(local)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(hnd, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1]
+        allowed = sorted(os.sched_getaffinity(0))
+        cpus = [c for c in cpus if c in allowed] or allowed
+        world = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        how = "nvml affinity"
+        if world > 1 and len(cpus) == len(allowed) and len(allowed) >= world:
+            per = len(allowed) // world             # all GPUs share one set: give every rank its own slice of it
+            cpus = allowed[local * per:(local + 1) * per]
+            how = "even split of the shared affinity set"
+        os.sched_setaffinity(0, cpus)
+        info = {"cpus": "%d-%d (%d)" % (cpus[0], cpus[-1], len(cpus)), "how": how}
+    except Exception as ex:  # pragma: no cover
+        info = {"cpus": None, "how": "failed: %r" % (ex,)}
+    return info
 
 
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from velocity_b200.lk import FrameBatch, lk_params, track_pairs
-    from velocity_b200.sequence import SequenceTracker
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback")
+    affinity = bind_to_gpu_numa_node(local) if world > 1 else {"cpus": None, "how": "single rank: unchanged"}
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    # every rank owns its own shard of PAIRS pairs (weak scaling, no data-path collective: KLT
-    # shards by frames, SURVEY.md 8(e)); shards differ by seed
-    unique, pts_np = make_frames(UNIQUE_FRAMES, SEED + rank)
-    idx = tile_sequence(unique, PAIRS + 1)
-    frames_host = torch.from_numpy(unique[idx]).pin_memory()          # [PAIRS+1, H, W]
-    pts_host = torch.from_numpy(pts_np).pin_memory()
-    frames_dev = frames_host.to(dev)
-    pts_dev = pts_host.to(dev)
-    params = lk_params(fbt=FBT, **LK)
-    fb = FrameBatch(frames_dev, LK["winSize"], LK["maxLevel"])
+    from velocity_b200.lk import FrameBatch, lk_params, track_pairs
+    from velocity_b200.sfm import SfmSequence
+
+    # every rank owns its own 300-frame sequence (weak scaling; frames shard naturally, SURVEY.md 8(e)); shards differ by seed
+    K, frames_np, p0_np, p3_np, times_np, Z = make_sequence(SEED + rank)
+    frames_host = torch.from_numpy(frames_np).pin_memory()
+    p0_host = torch.from_numpy(p0_np).pin_memory()
+    p3_host = torch.from_numpy(p3_np).pin_memory()
+    times_host = torch.from_numpy(times_np).pin_memory()
+    frames_dev, p0_dev, p3_dev, times_dev = frames_host.to(dev), p0_host.to(dev), p3_host.to(dev), times_host.to(dev)
+    seq = SfmSequence(K, H, W, NFRAMES, NPTS, fbt=FBT, ba_iters=BA_ITERS, chunk=args.chunk, **LK)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
@@ -212,111 +305,138 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident():
-        fb.build()
-        return track_pairs(fb, fb, pts_dev, params, 0, 1, PAIRS)
-
-    # ---- device-resident timing: `value` + per-kernel durations for the roofline -------------------
+    # ---- device-resident timing: `value` ---------------------------------------------------------------------------------
     for _ in range(args.warmup):
-        step_resident()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+        seq.run(frames_dev, p0_dev, p3_dev, times_dev)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
     barrier()
-    t_start = torch.cuda.Event(enable_timing=True)
-    t_end = torch.cuda.Event(enable_timing=True)
+    seq.marks, seq.launches = [], 0
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for s in range(args.steps):
-        ev[s][0].record()
-        fb.build()
-        ev[s][1].record()
-        out = track_pairs(fb, fb, pts_dev, params, 0, 1, PAIRS)
-        ev[s][2].record()
+        hist = seq.run(frames_dev, p0_dev, p3_dev, times_dev)
     t_end.record()
     barrier()
-    clk = clocks.stop() if rank == 0 else None
     total_ms = t_start.elapsed_time(t_end)
-    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
-    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
-    valid_frac = float(out[1].float().mean().item())
+    launches_per_step = seq.launches // args.steps
+    marks, seq.marks = seq.marks, None
+    stage = {}
+    for (na, ea), (nb, eb) in zip(marks[:-1], marks[1:]):
+        if nb != "start":
+            stage[nb] = stage.get(nb, 0.0) + ea.elapsed_time(eb) / args.steps
+    S, S_ba = seq.S.cpu().numpy(), seq.S_ba.cpu().numpy()
+    alive_last = int((seq.alive[-1] != 0).sum().item())
+    result = {"speed_kmh_mean": float(S[1:, 8].mean()), "speed_kmh_std": float(S[1:, 8].std()),
+              "speed_after_ba_kmh_mean": float(S_ba[1:, 8].mean()), "speed_after_ba_kmh_std": float(S_ba[1:, 8].std()),
+              "truth_kmh": V_KMH, "tracks_alive_last": alive_last, "ba_tracks": int(seq.nsel), "ba_iterations_run": len(hist),
+              "ba_rms_px_first_last": [hist[0][0], hist[-1][0]], "distance_m": float(S[-1, 7]), "truth_distance_m": float(Z[0] - Z[-1])}
 
-    # ---- end-to-end timing through the public host-buffer API ----------------------------------------
-    chunk = args.chunk
-    tracker = SequenceTracker(H, W, NPTS, chunk=chunk, fbt=FBT, **LK)
-    o_pts = torch.empty((PAIRS, NPTS, 2), dtype=torch.float32).pin_memory()
-    o_st = torch.empty((PAIRS, NPTS), dtype=torch.uint8).pin_memory()
-    o_err = torch.empty((PAIRS, NPTS), dtype=torch.float32).pin_memory()
-    use_graph = not args.no_graph
-    try:
-        for _ in range(max(2, args.warmup // 2)):
-            h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err, graph=use_graph)
-    except Exception as ex:  # capture refused by this driver/torch build: same GPU pipeline, issued eagerly from Python
-        sys.stderr.write("bench.py: CUDA-graph capture of the e2e pipeline failed (%r); timing the eager pipeline\n" % (ex,))
-        use_graph = False
-        tracker = SequenceTracker(H, W, NPTS, chunk=chunk, fbt=FBT, **LK)
-        for _ in range(max(1, args.warmup // 2)):
-            h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err)
+    # ---- end-to-end timing through the public host-buffer API ----------------------------------------------------------------
+    out = dict(S=torch.empty((NFRAMES, 9)).pin_memory(), S_ba=torch.empty((NFRAMES, 9)).pin_memory(),
+               B=torch.empty((NFRAMES, 14)).pin_memory(), P=torch.empty((5, NPTS, NFRAMES)).pin_memory())
+    for _ in range(2):
+        seq.run(frames_host, p0_host, p3_host, times_host, out=out)
     barrier()
-    e0 = torch.cuda.Event(enable_timing=True)
-    e1 = torch.cuda.Event(enable_timing=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h2d_small = p0_host.numel() * 4 + p3_host.numel() * 8 + times_host.numel() * 4
     e0.record()
     for _ in range(args.steps):
-        l2_flush.zero_()  # nothing of the previous step survives in L2 (frames come from the host anyway)
-        h2d, d2h = tracker.run(frames_host, pts_host, o_pts, o_st, o_err, graph=use_graph)
+        l2_flush.zero_()   # nothing of the previous step survives in L2 (frames come from the host anyway)
+        seq.run(frames_host, p0_host, p3_host, times_host, out=out)
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    e2e_valid = float((o_st != 0).float().mean().item())
+    h2d, d2h = seq.h2d_bytes + h2d_small, seq.d2h_bytes
+    e2e_speed = float(out["S"][1:, 8].mean().item())
 
-    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms], dtype=torch.float64, device=dev)
+    # ---- K2 / K1 roofline leg: C2 = one launch over a batch of consecutive pairs of the same sequence --------------------------
+    params = lk_params(fbt=FBT, **LK)
+    fb = FrameBatch(frames_dev[:C2_PAIRS + 1], LK["winSize"], LK["maxLevel"])
+    pts_pairs = seq.tracks[:C2_PAIRS].contiguous()        # the propagated points of each pair's first frame
+    rsteps = max(5, min(args.steps, 20))
+    for _ in range(3):
+        fb.build()
+        c2 = track_pairs(fb, fb, pts_pairs, params, 0, 1, C2_PAIRS)
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(rsteps)]
+    for s in range(rsteps):
+        ev[s][0].record()
+        fb.build()
+        ev[s][1].record()
+        c2 = track_pairs(fb, fb, pts_pairs, params, 0, 1, C2_PAIRS)
+        ev[s][2].record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    k1_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    c2_valid = float(c2[1].float().mean().item())
+
+    times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms] + [stage.get(k, 0.0) for k in ("track", "pose", "triangulate", "bundle")],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    total_ms, e2e_ms, k1_ms, k2_ms = (float(x) for x in times.tolist())
+    total_ms, e2e_ms, k1_ms, k2_ms, st_track, st_pose, st_tri, st_ba = (float(x) for x in times.tolist())
 
     if rank == 0:
         peaks, peak_kind = measured_peaks()
         ms_per_step = total_ms / args.steps
-        value = world * PAIRS / (ms_per_step * 1e-3)
-        e2e_value = world * PAIRS / (e2e_ms / args.steps * 1e-3)
-        k2_gbs = PAIRS * K2_BYTES_PER_PAIR_FB / (k2_ms * 1e-3) / 1e9
-        k1_gbs = (PAIRS + 1) * K1_BYTES_PER_FRAME / (k1_ms * 1e-3) / 1e9
+        value = world * NFRAMES / (ms_per_step * 1e-3)
+        e2e_value = world * NFRAMES / (e2e_ms / args.steps * 1e-3)
+        k2_gbs = C2_PAIRS * K2_BYTES_PER_PAIR_FB / (k2_ms * 1e-3) / 1e9
+        k1_gbs = (C2_PAIRS + 1) * K1_BYTES_PER_FRAME / (k1_ms * 1e-3) / 1e9
+        seq_gbs = (NFRAMES - 1) * K2_BYTES_PER_PAIR_FB / (max(st_track, 1e-9) * 1e-3) / 1e9
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 traffic = json.load(f).get("lk_track_kernel_bytes_per_launch")
         cpu = None
-        if True:   # rank 0 only reaches this point; the CPU sample is bounded (a few seconds)
+        if world == 1:   # bounded CPU sample on this host, fed with the GPU's own tracked observations (input data only)
             try:
-                fps, ms, cores, backend = cpu_reference_run(unique[:4], pts_np, 3, 1, 4)
-                cpu = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                       "sample": "4 consecutive 1080p pairs x 3 repeats on the host; %s" % backend}
+                tr = seq.tracks.cpu().numpy()
+                al = seq.alive.cpu().numpy() != 0
+                tr[~al] = np.nan
+                ref = CpuReference(K, frames_np, p0_np, p3_np, times_np, tracks=tr, alive=al)
+                ref.step()
+                rs = [ref.step() for _ in range(2)]
+                full_s = float(np.mean([r["full_s"] for r in rs]))
+                cpu = {"value": NFRAMES / full_s, "unit": UNIT, "cores": ref.cores, "kind": "port",
+                       "sample": "2 steps; " + ref.sample_text(), "extrapolated_s_per_sequence": full_s,
+                       "klt_pose_ms_per_frame": float(np.mean([r["klt_pose_s_per_frame"] for r in rs])) * 1e3,
+                       "ba_iteration_ms": float(np.mean([r["ba_iteration_s"] for r in rs])) * 1e3,
+                       "klt_pairs_per_s_1thread": ref.klt_one_thread()}
             except Exception as ex:  # pragma: no cover
-                cpu = {"value": None, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % ex}
+                cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": "failed: %r" % (ex,)}
+        cfg = workload_config()
         line = {
-            "metric": "SFM frames/sec @1080p, 4k tracks (KLT pyramidal LK fwd+bwd, 3 levels)",
-            "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u8/int32 fixed point + f32 2x2 solve", "data": "synthetic",
-            "config": {"workload": "C2: 1080p consecutive pairs, 4096 tracks, LK 15x15, 3 levels, <=10 it, eps 0.1, fbt 1.0",
-                       "pairs_per_step_per_gpu": PAIRS, "tracks": NPTS, "plane_depth_m": Z0_M, "frames_resident_mb": (PAIRS + 1) * HW_B / 1e6,
-                       "l2_policy": "inputs (%d MB of frames per step) larger than L2; e2e additionally flushes L2" % ((PAIRS + 1) * HW_B // 1000000),
-                       "valid_fraction": valid_frac, "sharding": "frames, no collective"},
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE, "data": "synthetic",
+            "config": cfg,
+            "details": {"sequences_per_step_per_gpu": 1, "frames_resident_mb": NFRAMES * HW_B / 1e6, "sharding": "one sequence per GPU, no data-path collective",
+                        "l2_policy": "inputs (%d MB of frames per step) larger than L2; e2e additionally flushes L2" % (NFRAMES * HW_B // 1000000),
+                        "stage_ms": {"klt_pyramids_and_tracking": st_track, "pose_and_speed_table": st_pose,
+                                     "select_rays_triangulate_pack": st_tri, "bundle_adjustment": st_ba},
+                        "host_affinity": affinity},
+            "result": result,
             "roofline": {"bound": "hbm", "kernel": "lk_track_w15h_kernel (K2)", "achieved": k2_gbs, "peak": peaks["hbm_gbs"],
                          "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
-                         "bytes_per_launch": PAIRS * K2_BYTES_PER_PAIR_FB, "ms_per_launch": k2_ms,
-                         "note": "K2 is instruction-issue/latency-bound (ncu: 72% issue slots busy, DRAM traffic ~2.7 MB/pair because "
-                                 "each pyramid is read from HBM once and served from L2/L1 for its other roles); the HBM-bound "
-                                 "stage of KLT is K1, reported in k1_pyramid",
+                         "bytes_per_launch": C2_PAIRS * K2_BYTES_PER_PAIR_FB, "ms_per_launch": k2_ms, "pairs_per_launch": C2_PAIRS,
+                         "valid_fraction": c2_valid,
+                         "note": "measured on one launch over %d consecutive pairs of the same sequence (BASELINE configs[1] batch form); K2 is "
+                                 "instruction-issue bound (ncu), its DRAM traffic is ~4x below the byte model because every pyramid is read from "
+                                 "HBM once and served from L2/L1 for its other roles; inside the C3 step the same kernel runs one pair per launch "
+                                 "(the tracks of frame k+1 depend on frame k), reported in in_sequence" % C2_PAIRS,
                          "k1_pyramid": {"achieved": k1_gbs, "frac": k1_gbs / peaks["hbm_gbs"], "ms_per_step": k1_ms,
-                                        "bytes_per_step": (PAIRS + 1) * K1_BYTES_PER_FRAME},
-                         "sequence_model": {"bytes_per_frame": SEQ_BYTES_PER_FRAME_FB,
-                                            "achieved": PAIRS * SEQ_BYTES_PER_FRAME_FB / (ms_per_step * 1e-3) / 1e9}},
+                                        "bytes_per_step": (C2_PAIRS + 1) * K1_BYTES_PER_FRAME},
+                         "in_sequence": {"achieved": seq_gbs, "frac": seq_gbs / peaks["hbm_gbs"], "us_per_pair": st_track * 1e3 / (NFRAMES - 1),
+                                         "note": "K1 + 299 dependent single-pair K2 launches"}},
             "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / args.steps, "valid_fraction": e2e_valid, "chunk_frames": chunk, "cuda_graph": use_graph},
-            "gpu_launches": args.steps * (LK["maxLevel"] + 1),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / args.steps, "chunk_frames": args.chunk, "speed_kmh_mean": e2e_speed,
+                    "h2d_gbs_per_rank": h2d / (e2e_ms / args.steps * 1e-3) / 1e9},
+            "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
         }
         print(json.dumps(line))
@@ -325,17 +445,13 @@ def run_ours(args):
 
 
 def main():
-    global Z0_M
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--chunk", type=int, default=8, help="frames per H2D/compute pipeline chunk of the e2e path")
-    ap.add_argument("--no-graph", action="store_true", help="issue the e2e chunk pipeline eagerly instead of replaying its CUDA graph")
-    ap.add_argument("--z0", type=float, default=Z0_M, help="plane depth (m) of the synthetic generator")
+    ap.add_argument("--chunk", type=int, default=25, help="frames per H2D/compute pipeline chunk of the e2e path")
     args = ap.parse_args()
-    Z0_M = args.z0
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         run_reference(args)

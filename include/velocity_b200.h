@@ -210,6 +210,65 @@ int vel_match_knn2_hamming256(const uint8_t* q, int32_t nq, const uint8_t* t, in
 int vel_match_knn2_l2(const float* q, int32_t nq, const float* t, int32_t nt, int32_t dim, int32_t* idx, float* dist,
                       vel_stream_t stream);
 
+/* ---- Device-resident sequence bookkeeping (the connected C3 pipeline) ------------------------
+ * The reference's frame loop (vidExample.py:75-166) keeps p / vg / P / B / S in numpy and touches them between
+ * every cv2 and solver call.  These entry points keep the same state in HBM, FRAME-MAJOR:
+ *   tracks [n][npts][2] float32  == P[0:2] transposed (row k = the tracked points in frame k, row 0 = the seeds)
+ *   alive  [n][npts]    uint8    == vg after frame k
+ *   proj   [n][npts][2] float32  == P[2:4] transposed (reprojections; NaN where a point is not in the fit)
+ *   B [n][14], S [n][9] float32  exactly the reference's arrays (vidExample.py:44-45)
+ * A failed track stays in place at an out-of-frame sentinel (K2 drops it without touching memory); the reference
+ * compacts instead (p[v]) -- the surviving tracks are identical either way. */
+
+/* vidExample.py:134-135 for a run of nframes consecutive frames: for k = 0..nframes-2
+ *     tracks[k+1], status = cv2calcOpticalFlowPyrLK(frame k, frame k+1, tracks[k], fbt)   (K2, vel_lk_track)
+ *     alive[k+1] = alive[k] & status
+ * tracks row 0 / alive row 0 are inputs.  frames / pyr as in vel_lk_track (pyramids built by vel_pyramid_u8);
+ * err [nframes-1][npts]; status is scratch of npts bytes.  The loop runs inside the library: no host work per frame. */
+int vel_klt_sequence(const uint8_t* frames, int64_t frame_stride, int32_t pitch, const uint8_t* pyr, int64_t pyr_stride,
+                     const vel_pyr_layout* layout, int32_t nframes, int32_t npts, const vel_lk_params* params, float* tracks,
+                     uint8_t* alive, float* err, uint8_t* status, vel_stream_t stream);
+
+/* vidExample.py:139-146 for frames 1..nframes-1 in one launch (one CTA per frame): t = fcnNLS_t(K, p[vp], p3[vp], x0)
+ * (utils/NLS.py:102-129, float64, result rounded to float32 as the reference does), p_proj = world2image(K, I, t, p3),
+ * residual = rms(p - p_proj).  A point enters frame f's fit when alive[f][i] != 0 and (subset == NULL or subset[i] != 0)
+ * (subset = the reference's vp mask, vidExample.py:124,136).  Writes B[f,3:6] = t, B[f,0:3] = B[0,0:3] + t, S[f,2] =
+ * number of live tracks, S[f,3] = residual, proj[f] (may be NULL), iters[f] (iterations, or -30 at the cap).
+ * K, p3 float64 (DEVICE); x0_host = the start value (HOST double[3]; the reference always starts from (0,0,1)). */
+int vel_seq_pose_t(const double* K, const float* tracks, const uint8_t* alive, const uint8_t* subset, const double* p3,
+                   int32_t nframes, int32_t npts, const double* x0_host, float* B, float* S, float* proj, int32_t* iters,
+                   vel_stream_t stream);
+
+/* vidExample.py:142-146,164: S[i,0] = i, S[i,4] = dt = B[i,12]-B[i-1,12], S[i,5] = B[i,12]-B[0,12], S[i,6] = dr =
+ * norm(t + B[0,0:3] - B[i-1,0:3]), S[i,7] = cumulative distance, S[i,8] = dr/dt*3.6 (km/h), S[0,2] = live tracks of
+ * frame 0 -- all in the reference's float32 arithmetic.  B[:,12] (frame times) and B[:,0:6] must be filled. */
+int vel_seq_stats(const float* B, const uint8_t* alive, int32_t nframes, int32_t npts, float* S, vel_stream_t stream);
+
+/* utils/NLS.py:190-191: the full-length tracks (alive in the last frame, and in subset if given), as an
+ * order-preserving index list idx[0..count) (DEVICE int32; count[1] DEVICE). */
+int vel_seq_select(const uint8_t* alive_last, const uint8_t* subset, int32_t npts, int32_t* idx, int32_t* count, vel_stream_t stream);
+
+/* utils/MSV.py:13-16: U [3][nframes][nsel] = pixel2uvec(K, tracks[f][idx[j]]) (float64) and, when A != NULL, the ray
+ * origins A [nframes][3] = B[0,0:3] - B[f,0:3].  idx may be NULL (identity, nsel == npts). */
+int vel_seq_rays(const double* K, const float* tracks, const int32_t* idx, int32_t nframes, int32_t npts, int32_t nsel,
+                 const float* B, double* U, double* A, vel_stream_t stream);
+
+/* utils/NLS.py:198-203: the bundle-adjustment inputs of fcnNLS_batch(K, P, pw, cw = B[:,3:6]) from the device arrays:
+ * z [2][nframes][nsel] float64 and x = [pw (nsel*3) | B[1:,3:6] | zeros] (the layout vel_ba_accumulate takes). */
+int vel_seq_pack_ba(const float* tracks, const int32_t* idx, int32_t nframes, int32_t npts, int32_t nsel, const double* pw,
+                    const float* B, double* z, double* x, vel_stream_t stream);
+
+/* The commented call site vidExample.py:157, `B[0:i, 3:6], p3[vg] = fcnNLS_batch(K, P, p3, B[0:i, 3:6])`: B_ba = B with the
+ * camera positions replaced by the bundle-adjusted ones (x = the parameter vector of vel_ba_solve, nsel points) and
+ * S_ba = S (follow with vel_seq_stats(B_ba, ..., S_ba) for the speed table after the adjustment). */
+int vel_seq_ba_cameras(const double* x, int32_t nsel, int32_t nframes, const float* B, const float* S, float* B_ba, float* S_ba,
+                       vel_stream_t stream);
+
+/* vidExample.py:128,151-153: the reference's P [5][npts][nframes] float32 (x, y, xproj, yproj, frame index; NaN =
+ * invalid) from the frame-major device arrays (proj may be NULL). */
+int vel_seq_export_P(const float* tracks, const float* proj, const uint8_t* alive, int32_t nframes, int32_t npts, float* P,
+                     vel_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

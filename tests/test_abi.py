@@ -12,7 +12,7 @@ def declared_symbols():
     with open(os.path.join(ROOT, "include", "velocity_b200.h")) as f:
         src = f.read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(vel_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(vel_[A-Za-z0-9_]+)\s*\(", src)))
 
 
 def test_library_builds_loads_and_exports_header():

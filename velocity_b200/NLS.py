@@ -31,6 +31,8 @@ def fzC(a, K, R, t=np.zeros((1, 3))):
 
 
 def _dev64(a):
+    if isinstance(a, torch.Tensor):
+        return a.to(device="cuda", dtype=torch.float64).contiguous()
     return torch.from_numpy(np.ascontiguousarray(np.asarray(a, np.float64))).cuda()
 
 
@@ -88,6 +90,8 @@ class BundleAdjuster:
     of its own cameras, V / g_p / cost are all-reduced, the camera blocks (U, g_c, W rows) are
     all-gathered, and every rank solves the same reduced system redundantly."""
 
+    launches_per_step = 10   # this library's kernels per LM iteration (K7: 5, K8: 5)
+
     def __init__(self, K, z, x0, nt, nc, shard=False):
         require_cuda()
         self.nt, self.nc = nt, nc
@@ -111,6 +115,11 @@ class BundleAdjuster:
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
         self.slices = camera_slices(nc, self.world)
+
+    def reset(self, z, x0):
+        """New measurements / start values for a problem of the same size (buffers are reused)."""
+        self.z = _dev64(z)
+        self.x.copy_(_dev64(x0))
 
     def accumulate(self):
         L = _lib.lib()

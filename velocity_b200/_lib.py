@@ -64,6 +64,14 @@ SIGNATURES = {
     "vel_ba2_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
     "vel_match_knn2_hamming256": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P]),
     "vel_match_knn2_l2": (C.c_int, [_P, _I32, _P, _I32, _I32, _P, _P, _P]),
+    "vel_klt_sequence": (C.c_int, [_P, _I64, _I32, _P, _I64, C.POINTER(PyrLayout), _I32, _I32, C.POINTER(LkParams), _P, _P, _P, _P, _P]),
+    "vel_seq_pose_t": (C.c_int, [_P, _P, _P, _P, _P, _I32, _I32, C.POINTER(C.c_double), _P, _P, _P, _P, _P]),
+    "vel_seq_stats": (C.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "vel_seq_select": (C.c_int, [_P, _P, _I32, _P, _P, _P]),
+    "vel_seq_rays": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _P, _P, _P, _P]),
+    "vel_seq_pack_ba": (C.c_int, [_P, _P, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "vel_seq_ba_cameras": (C.c_int, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
+    "vel_seq_export_P": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P]),
 }
 
 # entry points declared in the header whose kernels have not landed yet (shrinks to empty)

@@ -89,3 +89,55 @@ def scene_observations(pw, n_cams, K_row=None, step=0.37, noise=0.1, seed=11, rp
         P[0:2, :, j] = uv.T
         P[4, :, j] = j
     return P, cw
+
+
+# ---- connected C3 sequence: one continuous approach, no depth reset ----------------------------------------------
+def approach_sequence(n_frames, h=1080, w=1920, seed=2025, z_start=200.0, v_kmh=40.0, dt=1 / 29.97, sigma=2.0, margin=64,
+                      K_row=None):
+    """n_frames uint8 [h,w] frames of the SURVEY 8(d) textured plane approaching the camera by v*dt per frame in ONE
+    run from depth z_start (no reset: tracks are propagated frame to frame through the whole sequence, the way
+    vidExample.py:134-135 does).  The texture is defined at the mid-sequence depth so that the rendering minifies
+    (first half) and magnifies (second half) by the same factor.  Returns (frames [n,h,w] uint8, depths [n])."""
+    import cv2
+
+    K_row = K_1080P if K_row is None else K_row
+    step = v_kmh / 3.6 * dt
+    Z = z_start - step * np.arange(n_frames)
+    if Z[-1] <= 0:
+        raise ValueError("approach_sequence: the plane passes the camera (z_start too small for %d frames)" % n_frames)
+    z_ref = float(Z[n_frames // 2])
+    s_min = z_ref / Z.max()
+    th, tw = int(h / s_min) + 2 * margin, int(w / s_min) + 2 * margin
+    tex = texture(th, tw, seed, sigma)
+    tc = ((tw - 1) / 2.0, (th - 1) / 2.0)
+    frames = np.empty((n_frames, h, w), np.uint8)
+    for i in range(n_frames):
+        Hm = plane_homography(K_row, z_ref, Z[i], 1.0, tc)
+        frames[i] = cv2.warpPerspective(tex, Hm, (w, h), flags=cv2.INTER_LINEAR, borderMode=cv2.BORDER_REFLECT_101)
+    return frames, Z
+
+
+def approach_tracks(frame0, n, zoom, K_row=None, border=40):
+    """The n strongest Harris corners of frame 0 (quality 0.001, minDistance 5, blockSize 5) among those
+    that stay `border` px inside the frame after the image has grown by `zoom` about the principal point."""
+    import cv2
+
+    K_row = K_1080P if K_row is None else K_row
+    h, w = frame0.shape
+    cx, cy = K_row[2, 0], K_row[2, 1]
+    p = cv2.goodFeaturesToTrack(frame0, 0, 0.001, 5, blockSize=5, useHarrisDetector=True).reshape(-1, 2)
+    bx, by = (min(cx, w - 1 - cx) - border) / zoom, (min(cy, h - 1 - cy) - border) / zoom
+    p = p[(np.abs(p[:, 0] - cx) < bx) & (np.abs(p[:, 1] - cy) < by)]
+    if p.shape[0] < n:
+        raise ValueError("approach_tracks: only %d corners stay in frame (asked for %d)" % (p.shape[0], n))
+    return np.ascontiguousarray(p[:n], dtype=np.float32)
+
+
+def plane_fiducials(K_row, Z, size=(8.0, 4.0)):
+    """Four corner marks of a size[0] x size[1] metre rectangle on the plane (the synthetic stand-in for the licence
+    plate whose known geometry fixes the metric scale, vidExample.py:118): (pixels float32 [4,2], world [4,3]) with the
+    corner order of utils/common.py:150-156."""
+    corners = np.array([[1, -1, 0], [1, 1, 0], [-1, 1, 0], [-1, -1, 0]], np.float64) * np.array([size[0], size[1], 0.0]) / 2
+    cam = corners + np.array([0.0, 0.0, Z])
+    uv = cam @ K_row
+    return (uv[:, :2] / uv[:, 2:3]).astype(np.float32), corners

@@ -24,6 +24,9 @@ import cv2  # noqa: E402
 from oracle import ref_shim  # noqa: E402
 from velocity_b200 import synth  # noqa: E402
 
+sys.path.insert(0, os.path.dirname(HERE))
+from util import ba_c3_inputs  # noqa: E402
+
 EPS, COUNT = cv2.TERM_CRITERIA_EPS, cv2.TERM_CRITERIA_COUNT
 LK_COARSE = dict(winSize=(15, 15), maxLevel=4, criteria=(EPS | COUNT, 10, 0.1))  # utils/KLT.py:106
 LK_FINE = dict(winSize=(51, 51), maxLevel=0, criteria=(EPS | COUNT, 30, 0.001))  # utils/KLT.py:107
@@ -173,7 +176,9 @@ def gen_transforms(ref):
     X = rng.normal(0, 3, (40, 3))
     t = np.array([0.5, -1.5, 2.5])
     xf = np.stack([ref.transforms.transform(X, r, t) for r in rpy[:4]])
-    save("transforms", rpy=rpy, dcm=dcm, back=back, X=X, t=t, xf=xf)
+    quat = np.stack([ref.transforms.dcm2quat(c) for c in dcm])          # the 3-element pseudo-quaternion helpers (:60-73)
+    quat_dcm = np.stack([ref.transforms.quat2dcm(q) for q in quat])
+    save("transforms", rpy=rpy, dcm=dcm, back=back, X=X, t=t, xf=xf, quat=quat, quat_dcm=quat_dcm)
 
 
 def gen_msv(ref):
@@ -223,6 +228,35 @@ def gen_ba(ref):
                 cw2, pw2 = ref.NLS.fcnNLS_batch2(K, P.copy(), pw0.copy(), cw0.copy())
             out.update(cw_b2=cw2, pw_b2=pw2, stdout_b2=np.array(buf.getvalue()))
         save(name, **out)
+
+
+def gen_ba_large(ref):
+    """SURVEY 8(d) anchors: the reference's own DENSE fcnNLS_batch at nt=256/nf=10 and nt=512/nf=20 (1.6 s per
+    iteration, 270 MB Jacobian) -- the multi-chunk path of K7 (>= 16 cameras) and a K8 system of 114 unknown cameras."""
+    K = synth.K_1080P.copy()
+    rng = np.random.default_rng(77)
+    for name, nt, nf in [("ba_256x10", 256, 10), ("ba_512x20", 512, 20)]:
+        pw = synth.scene_points(nt, seed=nt)
+        P, cw = synth.scene_observations(pw, nf, noise=0.1, seed=nf)
+        pw0 = pw + rng.normal(0, 0.05, pw.shape)
+        cw0 = cw + rng.normal(0, 0.02, cw.shape)
+        cw0[0] = 0
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            cw1, pw1 = ref.NLS.fcnNLS_batch(K, P.copy(), pw0.copy(), cw0.copy())
+        save(name, K=K, P=P, pw0=pw0, cw0=cw0, cw=cw1, pw=pw1, stdout=np.array(buf.getvalue()))
+
+
+def gen_ba_c3(ref):
+    """The C3-size problem cannot run in the reference (277 GB dense Jacobian): the fixture holds the result of the
+    ORACLE's block-sparse form (oracle/sfm_oracle.bundle_sparse, the same iteration solved through the Schur complement;
+    checked against the reference's dense results on ba_256x10 / ba_512x20 in tests/test_oracle_sfm.py) after the
+    reference's 10 iterations.  Inputs are regenerated from seeds (ba_c3_inputs)."""
+    from oracle import sfm_oracle as S
+
+    K, P, pw0, cw0 = ba_c3_inputs()
+    cw1, pw1, hist = S.bundle_sparse(K, P, pw0, cw0, max_iter=10)
+    save("ba_c3_sparse", cw=cw1, pw=pw1, hist=np.array(hist), pw0_crc=np.array(zlib.crc32(pw0.tobytes())), P_crc=np.array(zlib.crc32(P.tobytes())))
 
 
 def gen_match():
@@ -351,6 +385,16 @@ def gen_e2e():
 def main():
     ref = ref_shim.load()
     print("cv2", cv2.__version__, "numpy", np.__version__)
+    only = sys.argv[1:]
+    if only:    # e.g. `make_golden.py ba_large ba_c3`: regenerate selected fixtures only
+        import inspect
+
+        for name in only:
+            fn = globals()["gen_" + name]
+            fn(ref) if inspect.signature(fn).parameters else fn()
+        return
+    gen_ba_large(ref)
+    gen_ba_c3(ref)
     gen_primitives()
     gen_lk(ref)
     gen_regional(ref)

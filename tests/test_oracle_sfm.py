@@ -45,7 +45,8 @@ def test_msv1():
 
 
 def test_bundle_dense_and_sparse_match_reference():
-    for name in ("ba_small", "ba_medium"):
+    # ba_256x10 / ba_512x20: the SURVEY 8(d) anchors, produced by the reference's DENSE fcnNLS_batch (270 MB Jacobian)
+    for name in ("ba_small", "ba_medium", "ba_256x10", "ba_512x20"):
         g = golden(name)
         cw, pw, hist = S.bundle_sparse(g["K"], g["P"], g["pw0"], g["cw0"])
         assert np.allclose(cw, g["cw"], rtol=1e-6, atol=1e-7), name
@@ -56,3 +57,15 @@ def test_bundle_dense_and_sparse_match_reference():
     # the reference prints "i: ..s, f=.., x=.." per iteration: same iteration count
     n_ref = sum(1 for ln in str(g["stdout"]).splitlines() if ": " in ln and "f=" in ln and "done" not in ln)
     assert len(hist_d) == n_ref
+
+
+def test_sparse_form_iteration_count_and_residual_match_reference_at_anchor_sizes():
+    import re
+
+    for name in ("ba_256x10", "ba_512x20"):
+        g = golden(name)
+        _, _, hist = S.bundle_sparse(g["K"], g["P"], g["pw0"], g["cw0"])
+        lines = [ln for ln in str(g["stdout"]).splitlines() if re.match(r"^\d+: ", ln)]
+        assert len(hist) == len(lines), name
+        f_ref = [float(re.search(r"f=([^,]+),", ln).group(1)) for ln in lines]
+        assert np.allclose([h[0] for h in hist], f_ref, rtol=2e-5), name     # printed with 6 significant digits

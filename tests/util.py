@@ -54,3 +54,19 @@ def lk_sweep_cases():
         pts = np.concatenate([synth.harris_tracks(im0, 120, border=3),
                               np.stack([rng.uniform(-20, w + 20, 60), rng.uniform(-20, h + 20, 60)], 1)]).astype(np.float32)
         yield k, im0, im1, pts, lk, fbt
+
+
+def ba_c3_inputs():
+    """Seeded bundle-adjustment problem of BASELINE configs[2] size (nt=4096, nc=299); tests/golden/ba_c3_sparse.npz holds
+    the oracle's result for exactly these inputs (CRCs stored beside it)."""
+    from velocity_b200 import synth
+
+    K = synth.K_1080P.copy()
+    nt, nf = 4096, 300
+    pw = synth.scene_points(nt, seed=7)
+    P, cw = synth.scene_observations(pw, nf, step=0.02, noise=0.1, seed=11)
+    rng = np.random.default_rng(3)
+    pw0 = pw + rng.normal(0, 0.05, pw.shape)
+    cw0 = cw + rng.normal(0, 0.01, cw.shape)
+    cw0[0] = 0
+    return K, P, pw0, cw0

@@ -187,6 +187,18 @@ size_t vel_ba_solve_workspace(int32_t nt, int32_t nc);
 int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
                  double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
 
+/* K8 building blocks -- the dense float64 algebra of `inv(JJ^T + I) @ ...` (utils/NLS.py:236) after the point blocks are
+ * eliminated, hand-written (FP64 tensor-core MMA; no cuBLAS / cuSOLVER anywhere in this library):
+ *   vel_syrk_lower_sub: S(lower triangle, row-major [m][lds]) -= E E^T for E row-major [m][ld] with k used columns;
+ *     rows must be 16-byte aligned (ld even) and zero-padded to a multiple of 16 columns.  Deterministic (split-K partial
+ *     products are applied in a fixed order).  work: vel_syrk_lower_sub_workspace(m, k) bytes.
+ *   vel_spd_solve: Cholesky S = L L^T in place (lower, row-major) and b <- S^-1 b; info[0] (DEVICE) = 0, or 1 when S is not
+ *     positive definite to working precision (b is then meaningless). */
+size_t vel_syrk_lower_sub_workspace(int32_t m, int32_t k);
+int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                       vel_stream_t stream);
+int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream);
+
 /* fcnNLS_batch2 (utils/NLS.py:253-328): the range/elevation/azimuth-parametrised bundle adjustment.
  * x = [points nt*3 | q], q = [joint roll,pitch,yaw | el | az | range_1..range_nc] (nq = 5 + nc).
  * vel_ba2_accumulate writes V [nt][6], the dense symmetric camera-side block G [nq][nq], the cross

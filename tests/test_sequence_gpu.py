@@ -133,3 +133,26 @@ def test_c3_full_size_speed_within_one_percent():
         p2, v, _ = klt_oracle.lk_forward_backward(frames[i - 1], frames[i], p, fbt=1.0, **LK)
         assert np.array_equal(v, alive[i]) and np.array_equal(p2[v], tr[i][v])
         p = p2
+
+
+def test_in_kernel_frame_loop_equals_per_pair_launches(monkeypatch):
+    """vel_klt_sequence has two forms: the 15x15 kernel with the frame loop inside (one launch per frame run) and one K2
+    launch per pair (any window; VEL_LK_SEQ=pairs forces it).  Same tracks, same masks, same errors, bit for bit."""
+    K, frames, p0, p3, times = scene_with_dying_tracks()
+    a, _ = run_gpu(K, frames, p0, p3, times)
+    monkeypatch.setenv("VEL_LK_SEQ", "pairs")
+    b, _ = run_gpu(K, frames, p0, p3, times)
+    assert torch.equal(a.alive, b.alive)
+    al = a.alive != 0
+    assert torch.equal(a.tracks[al], b.tracks[al]) and torch.equal(a.err[al[1:]], b.err[al[1:]])
+    assert (a.tracks[~al] == -1.0e5).all() and (b.tracks[~al] == -1.0e5).all()
+    assert torch.equal(a.S.nan_to_num(), b.S.nan_to_num())
+    # a 21x21 window takes the per-pair path by construction and must agree with the oracle too
+    from velocity_b200.sfm import SfmSequence
+
+    lk = dict(winSize=(21, 21), maxLevel=2, criteria=(3, 10, 0.03))
+    n, h, w = frames.shape
+    seq = SfmSequence(K, h, w, n, len(p0), fbt=0.5, ba_iters=1, **lk)
+    seq.run(torch.from_numpy(frames).cuda(), p0, p3, times, bundle=False)
+    tr, al = Q.track_sequence(frames, p0, fbt=0.5, **lk)
+    assert np.array_equal(seq.alive.cpu().numpy() != 0, al) and np.array_equal(seq.tracks.cpu().numpy()[al], tr[al])

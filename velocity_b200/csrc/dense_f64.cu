@@ -1,0 +1,673 @@
+// K8 building blocks: the dense FP64 linear algebra behind `delta = inv(JJ^T + I) @ J(z - zhat)` (utils/NLS.py:236) once
+// the point blocks are eliminated -- hand-written for sm_100a, no cuBLAS / cuSOLVER.
+//
+//   vel_syrk_lower_sub   S(lower) -= E E^T          the Schur product  W' W'^T  (6nc x 3nt x 6nc, 39.5 GFLOP at C3)
+//   vel_spd_solve        S = L L^T in place, x = S^-1 b   blocked right-looking Cholesky with the forward substitution
+//                                                    folded in (b rides along as an extra row), then the backward substitution
+//
+// SYRK: FP64 tensor-core MMA (mma.sync m8n8k4 f64, "DMMA"), 128x128 CTA tiles (16 warps of 32x32), operands staged in
+// shared memory by cp.async through a 3-deep ring of 32-column k-tiles, row stride padded by 4 doubles so a fragment load (8 rows x 4 k) hits
+// 32 distinct 8-byte slots.  The lower triangle has nb(nb+1)/2 tiles -- 120 for M = 1794 -- which do not fill 148 SMs, so
+// the K dimension is split into SK chunks and a persistent grid walks the (chunk, tile) items chunk-major (the working set
+// of a chunk, M x K/SK doubles, stays in L2; E streams from HBM once).  The SK partial products of a tile are applied to S
+// in chunk order through a per-tile turnstile (chunk c waits for c-1): bit-reproducible, no atomics, no partial buffers.
+// Tile height is adapted to M (BMe = ceil(M/nb) rounded up to 8), so M = 1794 runs 15 x 120-row blocks instead of 14 full
+// ones plus a 2-row sliver, and warps are assigned to 32x32 sub-tiles with a skew that keeps the four SM sub-partitions
+// equally loaded when the last sub-tiles are short.
+//
+// Cholesky: one cooperative persistent kernel, 64-column panels.  Per panel: every CTA factors the 64x64 diagonal block
+// redundantly in shared memory (8-column register-blocked steps), CTAs share the rows below it for the triangular solve,
+// grid barrier, then the trailing matrix is updated tile by tile with DMMA, grid barrier.  The right-hand side is row n of
+// the matrix, so y = L^-1 b falls out of the same sweeps; the backward substitution runs in the same kernel.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+int sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = kNumSMs;
+    }
+    return n;
+}
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory"); }
+
+// ---- SYRK ---------------------------------------------------------------------------------------------------------------
+constexpr int SY_BM = 128, SY_BK = 32, SY_STAGES = 3, SY_LDS = SY_BK + 4, SY_THREADS = 512;
+constexpr int SY_STAGE_DOUBLES = 2 * SY_BM * SY_LDS;                       // A tile + B tile
+constexpr size_t SY_SMEM = sizeof(double) * SY_STAGES * SY_STAGE_DOUBLES;   // 221,184 B
+
+struct SyrkPlan {
+    int nb, bme, ntiles, sk, ktiles, grid;
+};
+
+SyrkPlan syrk_plan(int m, int k)
+{
+    SyrkPlan p;
+    p.nb = (m + SY_BM - 1) / SY_BM;
+    p.bme = (((m + p.nb - 1) / p.nb) + 7) & ~7;
+    p.ntiles = p.nb * (p.nb + 1) / 2;
+    p.ktiles = (k + SY_BK - 1) / SY_BK;
+    const int sms = sm_count();
+    int best = 1;
+    double best_cost = 1e30;
+    for (int sk = 1; sk <= 16 && sk <= p.ktiles; ++sk) {
+        const long long items = (long long)p.ntiles * sk;
+        const double rounds = (double)((items + sms - 1) / sms);
+        const double cost = rounds * ((p.ktiles + sk - 1) / sk) + 3.0 * rounds;     // k-tiles on the critical path + epilogue/prologue per item
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = sk; }
+    }
+    p.sk = best;
+    const long long items = (long long)p.ntiles * p.sk;
+    p.grid = (int)(items < sms ? items : sms);
+    return p;
+}
+
+// one k-tile (SY_BK columns) of a warp's 32x32 sub-tile: MT x NT m8n8k4 products per 4 columns
+template <int MT, int NT>
+__device__ __forceinline__ void syrk_ktile(double (&acc)[4][4][2], const double* pa, const double* pb)
+{
+#pragma unroll
+    for (int kk = 0; kk < SY_BK / 4; ++kk) {
+        double a[MT], b[NT];
+#pragma unroll
+        for (int i = 0; i < MT; ++i) a[i] = pa[i * 8 * SY_LDS + kk * 4];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) b[j] = pb[j * 8 * SY_LDS + kk * 4];
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+}
+
+template <int MT>
+__device__ __forceinline__ void syrk_ktile_nt(double (&acc)[4][4][2], const double* pa, const double* pb, int nt_cnt)
+{
+    if (nt_cnt == 4) syrk_ktile<MT, 4>(acc, pa, pb);
+    else if (nt_cnt == 3) syrk_ktile<MT, 3>(acc, pa, pb);
+    else if (nt_cnt == 2) syrk_ktile<MT, 2>(acc, pa, pb);
+    else if (nt_cnt == 1) syrk_ktile<MT, 1>(acc, pa, pb);
+}
+
+// E [m][ld] row-major, K contiguous (ld even, rows 16-byte aligned, columns k..ld-1 of the last k-tile readable and ZERO)
+__global__ void __launch_bounds__(SY_THREADS, 1)
+dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb, int bme, int ntiles, int sk, int ktiles,
+                       double* __restrict__ S, long long lds, int* __restrict__ flags)
+{
+    extern __shared__ __align__(16) double sy_smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wr = warp >> 2, wc = ((warp & 3) - wr) & 3;     // (wr + wc) % 4 == warp % 4: balances short edge sub-tiles over the sub-partitions
+    const int mt_cnt = max(0, min(4, (bme - wr * 32 + 7) >> 3));
+    const int nt_cnt = max(0, min(4, (bme - wc * 32 + 7) >> 3));
+    const long long nitems = (long long)ntiles * sk;
+
+    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+        const int c = (int)(item / ntiles), t = (int)(item % ntiles);
+        int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+        while (bi * (bi + 1) / 2 > t) --bi;
+        const int bj = t - bi * (bi + 1) / 2;
+        const bool diag = bi == bj;
+        const int row0 = bi * bme, col0 = bj * bme;
+        const int kt0 = (int)((long long)ktiles * c / sk), kt1 = (int)((long long)ktiles * (c + 1) / sk);
+        const bool skip_warp = diag && wc > wr;                 // sub-tile strictly above the diagonal: never stored
+
+        double acc[4][4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        // element offsets of this thread's 16-byte chunks (rows clamped to the matrix), fixed for the whole item
+        constexpr int CPR = SY_BK / 2;                          // 16-byte chunks per tile row
+        constexpr int NLOAD = SY_BM * CPR / SY_THREADS;         // chunks per thread and operand
+        long long offA[NLOAD], offB[NLOAD];
+        int soff[NLOAD];
+#pragma unroll
+        for (int u = 0; u < NLOAD; ++u) {
+            const int q = tid + SY_THREADS * u, r = q / CPR, ch = q % CPR;
+            offA[u] = (long long)min(row0 + r, m - 1) * ld + ch * 2;
+            offB[u] = (long long)min(col0 + r, m - 1) * ld + ch * 2;
+            soff[u] = r * SY_LDS + ch * 2;
+        }
+        auto issue = [&](int kt, int stage) {
+            double* sA = sy_smem + stage * SY_STAGE_DOUBLES;
+            double* sB = sA + SY_BM * SY_LDS;
+            const double* Ek = E + (long long)kt * SY_BK;
+#pragma unroll
+            for (int u = 0; u < NLOAD; ++u) {
+                cp_async16(sA + soff[u], Ek + offA[u]);
+                if (!diag) cp_async16(sB + soff[u], Ek + offB[u]);
+            }
+        };
+
+        // prologue
+#pragma unroll
+        for (int s = 0; s < SY_STAGES - 1; ++s) {
+            if (kt0 + s < kt1) issue(kt0 + s, s);
+            cp_async_commit();
+        }
+        for (int kt = kt0; kt < kt1; ++kt) {
+            const int stage = (kt - kt0) % SY_STAGES;
+            cp_async_wait<SY_STAGES - 2>();
+            __syncthreads();                                    // tile kt landed for everyone; everyone is done with tile kt-1's slot
+            const int nk = kt + SY_STAGES - 1;
+            if (nk < kt1) issue(nk, (nk - kt0) % SY_STAGES);
+            cp_async_commit();
+            if (!skip_warp) {
+                const double* sA = sy_smem + stage * SY_STAGE_DOUBLES;
+                const double* sB = diag ? sA : sA + SY_BM * SY_LDS;
+                const double* pa = sA + (wr * 32 + g) * SY_LDS + t4;
+                const double* pb = sB + (wc * 32 + g) * SY_LDS + t4;
+                // a predicated mma.sync costs a WARPSYNC + NOP each (ncu: 1 per DMMA): dispatch once per k-tile on the
+                // warp-uniform sub-tile counts instead, so that every DMMA in the hot paths is unconditional
+                if (mt_cnt == 4) syrk_ktile_nt<4>(acc, pa, pb, nt_cnt);
+                else if (mt_cnt == 3) syrk_ktile_nt<3>(acc, pa, pb, nt_cnt);
+                else if (mt_cnt == 2) syrk_ktile_nt<2>(acc, pa, pb, nt_cnt);
+                else if (mt_cnt == 1) syrk_ktile_nt<1>(acc, pa, pb, nt_cnt);
+            }
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                        // the ring is free for the next item
+
+        // turnstile: the partial products of a tile are subtracted from S in chunk order
+        if (c > 0) {
+            if (tid == 0) {
+                while (ld_acquire(flags + t) < c) __nanosleep(64);
+            }
+            __syncthreads();
+        }
+        if (!skip_warp) {
+            const int rlim = min(row0 + bme, m), clim = min(col0 + bme, m);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = row0 + wr * 32 + i * 8 + g;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int cc = col0 + wc * 32 + j * 8 + 2 * t4;
+                    if (i < mt_cnt && j < nt_cnt && r < rlim) {
+                        double* p = S + (long long)r * lds + cc;
+                        if (cc < clim) p[0] = __ldcg(p) - acc[i][j][0];
+                        if (cc + 1 < clim) p[1] = __ldcg(p + 1) - acc[i][j][1];
+                    }
+                }
+            }
+        }
+        if (sk > 1) {
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release(flags + t, c + 1);
+        }
+    }
+}
+
+// ---- Cholesky + solve -----------------------------------------------------------------------------------------------------
+constexpr int CH_NB = 64, CH_NBO = 256, CH_THREADS = 512, CH_LD = CH_NB + 1, CH_LDT = CH_NB + 4;
+// diagonal block (stride 65: conflict-free column walks) + two DMMA operand tiles (stride 68: conflict-free fragment loads)
+constexpr size_t CH_SMEM = sizeof(double) * (CH_NB * CH_LD + 2 * CH_NB * CH_LDT);      // 102,912 B
+
+// 64x64 (w x w) lower Cholesky of sD in place, all CH_THREADS threads of the CTA; 8-column blocked:
+// (i) one warp factors the 8x8 diagonal sub-block in registers, (ii) a thread per row solves the 8-column sub-panel below it,
+// (iii) everyone applies the rank-8 update to the rest of the block.  ok is cleared when a pivot is not positive;
+// rdiag receives the reciprocals of the diagonal of L.
+__device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
+{
+    const int tid = threadIdx.x;
+    for (int jb = 0; jb < w; jb += 8) {
+        const int wb = min(8, w - jb);
+        if (tid < 32) {
+            // lanes 0..7 own the rows of the sub-block
+            const int r = tid & 7;
+            double a[8];
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) a[c2] = (r < wb && c2 < wb && c2 <= r) ? sD[jb + r][jb + c2] : 0.0;
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                if (c2 < wb) {
+                    const double piv = __shfl_sync(0xffffffffu, a[c2], c2);
+                    if (!(piv > 0.0) && tid == 0) *ok = 0;
+                    const double inv = rsqrt(piv);                // one slow op on the column-to-column chain instead of sqrt + divide
+                    const double d = piv * inv;
+                    if (tid == c2) rdiag[jb + c2] = inv;
+                    a[c2] = (r == c2) ? d : a[c2] * inv;          // column c2 of L (rows > c2 are scaled, row c2 holds the pivot root)
+#pragma unroll
+                    for (int c3 = c2 + 1; c3 < 8; ++c3) {
+                        const double l3 = __shfl_sync(0xffffffffu, a[c2], c3);   // L[c3][c2]
+                        if (c3 <= r) a[c3] -= a[c2] * l3;
+                    }
+                }
+            }
+            if (tid < 8 && r < wb) {
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2)
+                    if (c2 < wb && c2 <= r) sD[jb + r][jb + c2] = a[c2];
+            }
+        }
+        __syncthreads();
+        // (ii) rows below the sub-block: x L_sub^T = a  (forward substitution over the 8 columns)
+        const int below = w - jb - wb;
+        if (tid < below) {
+            const int r = jb + wb + tid;
+            double x[8];
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) x[c2] = c2 < wb ? sD[r][jb + c2] : 0.0;
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2) {
+                if (c2 < wb) {
+                    x[c2] = x[c2] * rdiag[jb + c2];
+#pragma unroll
+                    for (int c3 = c2 + 1; c3 < 8; ++c3)
+                        if (c3 < wb) x[c3] -= x[c2] * sD[jb + c3][jb + c2];
+                }
+            }
+#pragma unroll
+            for (int c2 = 0; c2 < 8; ++c2)
+                if (c2 < wb) sD[r][jb + c2] = x[c2];
+        }
+        __syncthreads();
+        // (iii) rank-wb update of the trailing lower part: thread = (row group, column)
+        {
+            const int ci = tid & 63, rg = tid >> 6;
+            if (ci < below) {
+                const int cidx = jb + wb + ci;
+                double lc[8];
+#pragma unroll
+                for (int c2 = 0; c2 < 8; ++c2) lc[c2] = c2 < wb ? sD[cidx][jb + c2] : 0.0;
+                for (int ri = rg; ri < below; ri += CH_THREADS / 64) {
+                    if (ci <= ri) {
+                        const int r = jb + wb + ri;
+                        double s2 = sD[r][cidx];
+#pragma unroll
+                        for (int c2 = 0; c2 < 8; ++c2) s2 -= sD[r][jb + c2] * lc[c2];
+                        sD[r][cidx] = s2;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+#ifdef VEL_CHOL_TIMING
+__device__ unsigned long long g_chol_t[8];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CH_T(k)  do { if (blockIdx.x == 0 && threadIdx.x == 0) { unsigned long long now_ = gtime(); g_chol_t[k] += now_ - t_last; t_last = now_; } } while (0)
+#else
+#define CH_T(k)
+#endif
+
+// 64 x kw slab S[row0 .. row0+64)[col0 .. col0+kw) (kw <= 64) -> dst[64][CH_LDT], rows >= nrows and columns >= kw zero-filled
+__device__ __forceinline__ void chol_load_tile(const double* S, long long lds, int row0, int nrows, int col0, int kw, double* dst, bool vec)
+{
+    const int tid = threadIdx.x;
+    if (vec) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int q = tid + CH_THREADS * u, r = q >> 5, c2 = (q & 31) * 2;
+            double2 v = make_double2(0.0, 0.0);
+            if (r < nrows && c2 < kw) {
+                const double* src = S + (long long)(row0 + r) * lds + col0 + c2;
+                if (c2 + 1 < kw) v = __ldcg(reinterpret_cast<const double2*>(src));
+                else v.x = __ldcg(src);
+            }
+            *reinterpret_cast<double2*>(dst + r * CH_LDT + c2) = v;
+        }
+    } else {
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int r = e >> 6, c2 = e & 63;
+            dst[r * CH_LDT + c2] = (r < nrows && c2 < kw) ? __ldcg(S + (long long)(row0 + r) * lds + col0 + c2) : 0.0;
+        }
+    }
+}
+
+// One 64x64 tile of the trailing update:  A[bi][bj] -= sum over the K columns [kcol0, kcol0 + kw) of  P_bi P_bj^T
+// (bi < 0: the right-hand-side strip b[bj block] -= y P_bj^T with y = b[kcol0 .. kcol0+kw)).  All threads of the CTA.
+__device__ void chol_update_tile(double* S, long long lds, int n, double* b, int bi, int bj, int kcol0, int kw, double* bufA, double* bufB,
+                                 bool vec)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int c0 = bj * CH_NB, wj = min(CH_NB, n - c0);
+    const int r0 = bi * CH_NB, wi = bi < 0 ? 0 : min(CH_NB, n - r0);
+    const int sr = (warp >> 2) * 16, sc = (warp & 3) * 16;
+    double acc[2][2][2] = {};
+    double strip = 0.0;
+    for (int kc = 0; kc < kw; kc += CH_NB) {
+        const int kww = min(CH_NB, kw - kc);
+        __syncthreads();                                           // the previous user of the buffers is done
+        chol_load_tile(S, lds, c0, wj, kcol0 + kc, kww, bufB, vec);
+        if (bi < 0) {
+            if (tid < kww) bufA[tid] = __ldcg(b + kcol0 + kc + tid);
+            __syncthreads();
+            if (tid < wj) {
+                double s2 = 0.0;
+                for (int c2 = 0; c2 < kww; ++c2) s2 += bufA[c2] * bufB[tid * CH_LDT + c2];
+                strip += s2;
+            }
+            continue;
+        }
+        chol_load_tile(S, lds, r0, wi, kcol0 + kc, kww, bufA, vec);
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < CH_NB / 4; ++kk) {
+            double a[2], bb[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                a[i] = bufA[(sr + i * 8 + g) * CH_LDT + kk * 4 + t4];
+                bb[i] = bufB[(sc + i * 8 + g) * CH_LDT + kk * 4 + t4];
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+        }
+    }
+    if (bi < 0) {
+        if (tid < wj) b[c0 + tid] = __ldcg(b + c0 + tid) - strip;
+        return;
+    }
+    // read-modify-write of the tile: all loads first, then the stores
+    double2 cur[2][2];
+    bool m0[2][2], m1[2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = sr + i * 8 + g, c2 = sc + j * 8 + 2 * t4;
+            m0[i][j] = r < wi && c2 < wj && (bi > bj || c2 <= r);
+            m1[i][j] = r < wi && c2 + 1 < wj && (bi > bj || c2 + 1 <= r);
+            const double* p = S + (long long)(r0 + r) * lds + c0 + c2;
+            cur[i][j] = make_double2(0.0, 0.0);
+            if (vec && m0[i][j] && m1[i][j]) cur[i][j] = __ldcg(reinterpret_cast<const double2*>(p));
+            else {
+                if (m0[i][j]) cur[i][j].x = __ldcg(p);
+                if (m1[i][j]) cur[i][j].y = __ldcg(p + 1);
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int r = sr + i * 8 + g, c2 = sc + j * 8 + 2 * t4;
+            double* p = S + (long long)(r0 + r) * lds + c0 + c2;
+            const double2 v = make_double2(cur[i][j].x - acc[i][j][0], cur[i][j].y - acc[i][j][1]);
+            if (vec && m0[i][j] && m1[i][j]) *reinterpret_cast<double2*>(p) = v;
+            else {
+                if (m0[i][j]) p[0] = v.x;
+                if (m1[i][j]) p[1] = v.y;
+            }
+        }
+}
+
+// trailing update of the block columns [jlo, jhi) (rows from the diagonal down, plus the right-hand-side strip) with the K
+// columns [kcol0, kcol0 + kw): the tiles are dealt round-robin to the CTAs of the grid
+__device__ void chol_update_columns(double* S, long long lds, int n, double* b, int nblk, int jlo, int jhi, int kcol0, int kw,
+                                    double* bufA, double* bufB, bool vec)
+{
+    int t = blockIdx.x;
+    for (int j = jlo; j < jhi; ++j) {
+        const int cnt = nblk - j + 1;                  // tiles (j..nblk-1, j) and the strip
+        while (t < cnt) {
+            chol_update_tile(S, lds, n, b, t == cnt - 1 ? -1 : j + t, j, kcol0, kw, bufA, bufB, vec);
+            t += gridDim.x;
+        }
+        t -= cnt;
+    }
+}
+
+// A is the (n+1) x n "tall" matrix: rows 0..n-1 = S (lower triangle used), row n = b (stored separately).
+// On exit: S holds L (lower), b holds x = S^-1 b.  info[0] = 0 on success, 1 when a pivot was not positive.
+//
+// Two-level blocking: 64-column panels inside 256-column outer blocks.  After a panel is factored only the REST OF ITS OUTER
+// BLOCK is updated with it (at most 3 block columns: one tile per CTA); the matrix to the right of the outer block is updated
+// once per outer block with all of its (up to 256) columns -- 4x fewer read-modify-write sweeps over S, 4x the work per sweep.
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_solve_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double ch_smem[];
+    double (*sD)[CH_LD] = reinterpret_cast<double (*)[CH_LD]>(ch_smem);        // diagonal block
+    double* bufA = ch_smem + CH_NB * CH_LD + (CH_NB * CH_LD & 1);              // 16-byte aligned operand tiles
+    double* bufB = bufA + CH_NB * CH_LDT;
+    __shared__ int s_ok;
+    __shared__ double rdiag[CH_NB];              // reciprocals of the diagonal of the block in sD
+    __shared__ double sx[2][CH_NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = (n + CH_NB - 1) / CH_NB;
+    const bool vec = (lds & 1) == 0 && ((size_t)S & 15) == 0;
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+#ifdef VEL_CHOL_TIMING
+    unsigned long long t_last = gtime();
+#endif
+
+    for (int kb = 0; kb < nblk; ++kb) {
+        const int k0 = kb * CH_NB, w = min(CH_NB, n - k0);
+        const int ob_end = min(nblk, (kb / (CH_NBO / CH_NB) + 1) * (CH_NBO / CH_NB));     // first block column after this outer block
+        // ---- phase A: every CTA factors the diagonal block (redundantly: cheaper than a broadcast + barrier) ----------------
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int r = e >> 6, c2 = e & 63;
+            if (r < w && c2 < w) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(k0 + r) * lds + k0 + c2) : 0.0;
+        }
+        __syncthreads();
+        CH_T(0);
+        chol_block(sD, w, &s_ok, rdiag);
+        CH_T(1);
+        if (blockIdx.x == 0) {
+            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                const int r = e >> 6, c2 = e & 63;
+                if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+            }
+        }
+        // ---- phase B: rows below the block (and the right-hand side as row n): x L_kk^T = a, one warp per row ----------------
+        {
+            const int r_first = k0 + w, nrows = n - r_first + 1;       // + 1: the right-hand side
+            const int warps_total = gridDim.x * (CH_THREADS / 32);
+            for (int ri = blockIdx.x * (CH_THREADS / 32) + warp; ri < nrows; ri += warps_total) {
+                const int r = r_first + ri;
+                double* rowp = r < n ? S + (long long)r * lds + k0 : b + k0;
+                // lane holds columns lane and lane + 32
+                double a0 = lane < w ? __ldcg(rowp + lane) : 0.0, a1 = lane + 32 < w ? __ldcg(rowp + lane + 32) : 0.0;
+                for (int cg8 = 0; cg8 < w; cg8 += 8) {
+                    double l0[8], l1[8], rd[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {            // the L entries of this 8-column group, off the dependent chain
+                        const int c2 = cg8 + u;
+                        l0[u] = (c2 < w && lane > c2 && lane < w) ? sD[lane][c2] : 0.0;
+                        l1[u] = (c2 < w && lane + 32 > c2 && lane + 32 < w) ? sD[lane + 32][c2] : 0.0;
+                        rd[u] = c2 < w ? rdiag[c2] : 0.0;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int c2 = cg8 + u;
+                        if (c2 < w) {
+                            const double src = c2 < 32 ? a0 : a1;
+                            const double xc = __shfl_sync(0xffffffffu, src, c2 & 31) * rd[u];
+                            if (lane == (c2 & 31)) { if (c2 < 32) a0 = xc; else a1 = xc; }
+                            a0 -= xc * l0[u];
+                            a1 -= xc * l1[u];
+                        }
+                    }
+                }
+                if (lane < w) rowp[lane] = a0;
+                if (lane + 32 < w) rowp[lane + 32] = a1;
+            }
+        }
+        CH_T(2);
+        grid.sync();
+        CH_T(3);
+        // ---- phase C1: the rest of this outer block, with this panel ---------------------------------------------------------
+        if (kb + 1 < ob_end) chol_update_columns(S, lds, n, b, nblk, kb + 1, ob_end, k0, w, bufA, bufB, vec);
+        // ---- phase C2 (last panel of an outer block): everything to the right, with all columns of the outer block -----------
+        if (kb + 1 == ob_end && ob_end < nblk) {
+            const int ko0 = (kb / (CH_NBO / CH_NB)) * CH_NBO;
+            chol_update_columns(S, lds, n, b, nblk, ob_end, nblk, ko0, k0 + w - ko0, bufA, bufB, vec);
+        }
+        CH_T(4);
+        if (kb + 1 < nblk) grid.sync();
+        CH_T(5);
+    }
+    // the diagonal blocks in shared memory were factored by every CTA: any CTA knows whether a pivot failed
+    if (blockIdx.x == 0 && tid == 0) info[0] = s_ok ? 0 : 1;
+    grid.sync();
+
+    // ---- backward substitution  L^T x = y  (y is in b), block rows from the bottom -----------------------------------------
+    for (int kb = nblk - 1; kb >= 0; --kb) {
+        const int k0 = kb * CH_NB, w = min(CH_NB, n - k0);
+        // every CTA solves the diagonal block redundantly (L_kk^T x_k = y_k) in shared memory
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int r = e >> 6, c2 = e & 63;
+            if (r < w && c2 < w) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(k0 + r) * lds + k0 + c2) : 0.0;
+        }
+        if (tid < w) sx[0][tid] = __ldcg(b + k0 + tid);
+        __syncthreads();
+        if (tid < w) rdiag[tid] = 1.0 / sD[tid][tid];
+        __syncthreads();
+        if (warp == 0) {
+            double y0 = lane < w ? sx[0][lane] : 0.0, y1 = lane + 32 < w ? sx[0][lane + 32] : 0.0;
+            for (int cg8 = ((w - 1) >> 3) << 3; cg8 >= 0; cg8 -= 8) {
+                double l0[8], l1[8], rd[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int c2 = cg8 + u;
+                    l0[u] = (c2 < w && lane < c2) ? sD[c2][lane] : 0.0;              // column-oriented: y[m] -= L[c2][m] x[c2], m < c2
+                    l1[u] = (c2 < w && lane + 32 < c2) ? sD[c2][lane + 32] : 0.0;
+                    rd[u] = c2 < w ? rdiag[c2] : 0.0;
+                }
+#pragma unroll
+                for (int u = 7; u >= 0; --u) {
+                    const int c2 = cg8 + u;
+                    if (c2 < w) {
+                        const double src = c2 < 32 ? y0 : y1;
+                        const double xc = __shfl_sync(0xffffffffu, src, c2 & 31) * rd[u];
+                        if (lane == (c2 & 31)) { if (c2 < 32) y0 = xc; else y1 = xc; }
+                        y0 -= xc * l0[u];
+                        y1 -= xc * l1[u];
+                    }
+                }
+            }
+            if (lane < w) sx[1][lane] = y0;
+            if (lane + 32 < w) sx[1][lane + 32] = y1;
+        }
+        __syncthreads();
+        if (blockIdx.x == 0 && tid < w) b[k0 + tid] = sx[1][tid];
+        // y[c] -= sum_r L[k0 + r][c] x[r]  for the columns c < k0, shared by all threads of the grid
+        const int gtid = blockIdx.x * CH_THREADS + tid, gthreads = gridDim.x * CH_THREADS;
+        for (int c2 = gtid; c2 < k0; c2 += gthreads) {
+            double s2 = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < w; ++r) s2 += __ldcg(S + (long long)(k0 + r) * lds + c2) * sx[1][r];
+            b[c2] = __ldcg(b + c2) - s2;
+        }
+        CH_T(6);
+        if (kb > 0) grid.sync();
+        CH_T(7);
+    }
+}
+
+inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
+
+}  // namespace
+
+// internal entry points (ba.cu) -------------------------------------------------------------------------------------------
+size_t vel_dense_syrk_workspace(int m, int k)
+{
+    const SyrkPlan p = syrk_plan(m, k);
+    return align256(sizeof(int) * (size_t)p.ntiles);
+}
+
+VEL_API size_t vel_syrk_lower_sub_workspace(int32_t m, int32_t k)
+{
+    if (m <= 0 || k <= 0) return 0;
+    return vel_dense_syrk_workspace(m, k);
+}
+
+VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                               vel_stream_t stream)
+{
+    VEL_CHECK_ARG(E && S && work, "vel_syrk_lower_sub: NULL argument");
+    VEL_CHECK_ARG(m > 0 && k > 0 && lds >= m, "vel_syrk_lower_sub: bad sizes m=%d k=%d lds=%lld", m, k, (long long)lds);
+    const long long kpad = ((long long)k + SY_BK - 1) / SY_BK * SY_BK;
+    VEL_CHECK_ARG(ld >= kpad && ld % 2 == 0 && ((size_t)E & 15) == 0,
+                  "vel_syrk_lower_sub: E needs 16-byte aligned rows (ld even) padded with zeros to a multiple of %d columns (ld %lld < %lld)",
+                  SY_BK, (long long)ld, kpad);
+    const SyrkPlan p = syrk_plan(m, k);
+    VEL_CHECK_ARG(work_bytes >= sizeof(int) * (size_t)p.ntiles, "vel_syrk_lower_sub: workspace too small");
+    cudaStream_t st = (cudaStream_t)stream;
+    int* flags = (int*)work;
+    VEL_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)p.ntiles, st));
+    static bool attr_set = false;
+    if (!attr_set) {
+        VEL_CUDA(cudaFuncSetAttribute(dsyrk_lower_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
+        attr_set = true;
+    }
+    long long ld_ = ld, lds_ = lds;
+    int m_ = m, nb = p.nb, bme = p.bme, ntiles = p.ntiles, sk = p.sk, ktiles = p.ktiles;
+    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags};
+    // co-residency of the whole grid is what makes the turnstile wait safe: cooperative launch guarantees it (or fails)
+    VEL_CUDA(cudaLaunchCooperativeKernel((void*)dsyrk_lower_sub_kernel, dim3(p.grid), dim3(SY_THREADS), args, SY_SMEM, st));
+    return VEL_OK;
+}
+
+#ifdef VEL_CHOL_TIMING
+VEL_API void vel_chol_timing(unsigned long long* out8, int reset)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out8, g_chol_t, sizeof(unsigned long long) * 8);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_t, z, sizeof(z)); }
+}
+#endif
+
+VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(S && b && info, "vel_spd_solve: NULL argument");
+    VEL_CHECK_ARG(n > 0 && lds >= n, "vel_spd_solve: bad sizes n=%d lds=%lld", n, (long long)lds);
+    cudaStream_t st = (cudaStream_t)stream;
+    static int max_grid = 0;
+    if (max_grid == 0) {
+        int per_sm = 0;
+        VEL_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
+        VEL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_solve_kernel, CH_THREADS, CH_SMEM));
+        VEL_CHECK_ARG(per_sm >= 1, "vel_spd_solve: kernel does not fit an SM");
+        max_grid = sm_count();
+    }
+    const int nblk = (n + CH_NB - 1) / CH_NB;
+    int grid = max_grid;
+    const int want = nblk * (nblk + 1) / 2 + nblk;          // tiles of the first trailing update
+    if (want < grid) grid = want < 1 ? 1 : want;
+    long long lds_ = lds;
+    int n_ = n;
+    void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info};
+    VEL_CUDA(cudaLaunchCooperativeKernel((void*)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, CH_SMEM, st));
+    return VEL_OK;
+}

@@ -42,6 +42,10 @@ struct LkArgs {
     int win_w, win_h, max_count;
     float eps2, min_eig, fbt;
     int force_bytes;   // VEL_LK_W15=bytes: byte-gather paths only (cross-check of the word-gather paths)
+    // sequence form (lk_track_w15h_kernel<true>): pairs k = 0..seq_pairs-1 are frame k -> k+1 of ONE frame run, row k+1 of
+    // out / alive is produced from row k inside the kernel; alive is [seq_pairs+1][npts] with row 0 given
+    int seq_pairs;
+    uint8_t* alive;
 };
 
 struct Img {
@@ -1007,6 +1011,7 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
     }
     A.pts = prev_pts; A.pts_stride = pts_stride; A.npts = npts;
     A.out = next_pts; A.status = status; A.err = err; A.back = back_pts;
+    A.seq_pairs = 0; A.alive = nullptr;
     A.win_w = ww; A.win_h = wh;
     int mc = params->max_count; mc = mc < 0 ? 0 : (mc > 100 ? 100 : mc);
     double eps = params->eps; eps = eps < 0. ? 0. : (eps > 10. ? 10. : eps);
@@ -1027,7 +1032,7 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
         if (A.force_bytes) words = false;
         if (words) {
             dim3 grid((npts + 2 * WH_WARPS - 1) / (2 * WH_WARPS), npairs);
-            lk_track_w15h_kernel<<<grid, 32 * WH_WARPS, 0, st>>>(A);
+            lk_track_w15h_kernel<false><<<grid, 32 * WH_WARPS, 0, st>>>(A);
         } else {
             dim3 grid((npts + W15_WARPS - 1) / W15_WARPS, npairs);
             lk_track_w15_kernel<<<grid, 32 * W15_WARPS, 0, st>>>(A);
@@ -1062,4 +1067,47 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
     }
     VEL_LAUNCH_CHECK("lk_track_kernel");
     return VEL_OK;
+}
+
+// Internal entry of vel_klt_sequence (sequence.cu): the whole frame run in ONE launch of lk_track_w15h_kernel<true> when the
+// configuration is the one that kernel serves (15x15 window, every row pitch a multiple of 4 bytes).  Returns 1 when launched,
+// 0 when the caller has to take the per-pair path, < 0 on error.
+int vel_lk_sequence_w15h(const uint8_t* frames, int64_t frame_stride, int32_t pitch, const uint8_t* pyr, int64_t pyr_stride,
+                         const vel_pyr_layout* layout, int32_t nframes, int32_t npts, const vel_lk_params* params, float* tracks,
+                         uint8_t* alive, float* err, vel_stream_t stream)
+{
+    if (params->win_w != W15 || params->win_h != W15 || pitch % 4 != 0 || frame_stride % 4 != 0) return 0;
+    for (int l = 1; l <= layout->max_level; ++l)
+        if (layout->pitch[l] % 4 != 0) return 0;
+    if (layout->max_level > 0 && (!pyr || pyr_stride % 4 != 0)) return 0;
+    const char* force = getenv("VEL_LK_W15");
+    if (force && strcmp(force, "bytes") == 0) return 0;
+    const char* seq = getenv("VEL_LK_SEQ");
+    if (seq && strcmp(seq, "pairs") == 0) return 0;      // cross-check switch: one launch per pair
+    if (!(layout->width[0] > W15 && layout->height[0] > W15 && pitch >= layout->width[0])) return 0;   // vel_lk_track reports it
+    LkArgs A;
+    A.prev0 = frames; A.prev_stride = frame_stride; A.prev_pitch = pitch;
+    A.prev_pyr = pyr; A.prev_pyr_stride = pyr_stride;
+    A.next0 = frames + frame_stride; A.next_stride = frame_stride; A.next_pitch = pitch;
+    A.next_pyr = pyr ? pyr + pyr_stride : nullptr; A.next_pyr_stride = pyr_stride;
+    A.lv.max_level = layout->max_level;
+    for (int l = 0; l < VEL_MAX_LEVELS; ++l) {
+        A.lv.w[l] = layout->width[l]; A.lv.h[l] = layout->height[l]; A.lv.pitch[l] = layout->pitch[l]; A.lv.off[l] = layout->offset[l];
+    }
+    A.pts = tracks; A.pts_stride = 0; A.npts = npts;
+    A.out = tracks + 2ll * npts; A.status = nullptr; A.err = err; A.back = nullptr;
+    A.win_w = W15; A.win_h = W15;
+    int mc = params->max_count; mc = mc < 0 ? 0 : (mc > 100 ? 100 : mc);
+    double eps = params->eps; eps = eps < 0. ? 0. : (eps > 10. ? 10. : eps);
+    A.max_count = mc;
+    A.eps2 = (float)(eps * eps);
+    A.min_eig = params->min_eig_threshold;
+    A.fbt = params->fb_threshold;
+    A.force_bytes = 0;
+    A.seq_pairs = nframes - 1; A.alive = alive;
+    constexpr int SEQ_WARPS = 2;                          // 4 points per CTA: 1024 CTAs for 4096 tracks, 6.9 per SM
+    dim3 grid((npts + 2 * SEQ_WARPS - 1) / (2 * SEQ_WARPS), 1);
+    lk_track_w15h_kernel<true><<<grid, 32 * SEQ_WARPS, 0, (cudaStream_t)stream>>>(A);
+    VEL_LAUNCH_CHECK("lk_track_w15h_kernel<seq>");
+    return 1;
 }

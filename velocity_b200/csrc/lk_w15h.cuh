@@ -95,26 +95,43 @@ __device__ __forceinline__ void wh_gather(const Img& J, int inx, int iny, int rq
 }
 
 // 96 registers -> five 4-warp CTAs (20 warps, 40 points) per SM: their 128-byte-line neighbourhoods still fit L1
+//
+// SEQ = true is the SEQUENCE form (vel_klt_sequence, vidExample.py:134-135): a point's track through frame k+1 depends only
+// on its own position in frame k, never on another point, so the frame loop moves INSIDE the kernel -- each half-warp
+// carries its point through all A.seq_pairs consecutive pairs (frame k -> k+1, forward + backward + gate), writes row
+// k+1 of the track / alive arrays as it goes, and parks a failed track at the out-of-frame sentinel.  No launch and no
+// grid-wide dependency per frame; 2-warp CTAs spread the 2048 warps of 4096 tracks evenly over the 148 SMs.
+constexpr float kSeqDeadXY = -1.0e5f;     // same sentinel as sequence.cu
+
+template <bool SEQ>
 __global__ void __launch_bounds__(32 * WH_WARPS, 5)
 lk_track_w15h_kernel(const LkArgs A)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int pair = blockIdx.y;
     int4 rP[12];   // template patch: [0..3] 256 - (I << 9), [4..7] Ix, [8..11] Iy of pixel rows 0..3 (x = column 4cg .. w = 4cg+3)
     const int slot = lane >> 4, hl = lane & 15;
-    const int pt = blockIdx.x * (2 * WH_WARPS) + 2 * warp + slot;
+    const int pt = blockIdx.x * (2 * (blockDim.x >> 5)) + 2 * warp + slot;
     if (pt - slot >= A.npts) return;                   // both points of this warp are beyond the set
-    const bool valid = pt < A.npts;
+    const bool in_set = pt < A.npts;
     const unsigned hmask = slot ? 0xffff0000u : 0x0000ffffu;
     const int cg = hl & 3, rq = hl >> 2;
     const float half = 7.0f;
 
+    bool valid = in_set;                               // SEQ: "this track is still alive"
+    float sx = 0.f, sy = 0.f;                          // SEQ: the point's position in the current frame
+    if (SEQ && in_set) {
+        valid = A.alive[pt] != 0;
+        sx = __ldg(A.pts + 2ll * pt); sy = __ldg(A.pts + 2ll * pt + 1);
+    }
+    const int npairs_loop = SEQ ? A.seq_pairs : 1;
+  for (int seqk = 0; seqk < npairs_loop; ++seqk) {
+    const int pair = SEQ ? seqk : blockIdx.y;
     const uint8_t* P0 = A.prev0 + (long long)pair * A.prev_stride;
     const uint8_t* Pp = A.prev_pyr ? A.prev_pyr + (long long)pair * A.prev_pyr_stride : nullptr;
     const uint8_t* N0 = A.next0 + (long long)pair * A.next_stride;
     const uint8_t* Np = A.next_pyr ? A.next_pyr + (long long)pair * A.next_pyr_stride : nullptr;
-    float px0 = 0.f, py0 = 0.f;
-    if (valid) {
+    float px0 = sx, py0 = sy;
+    if (!SEQ && valid) {
         const float* pin = A.pts + (long long)pair * A.pts_stride + 2ll * pt;
         px0 = __ldg(pin); py0 = __ldg(pin + 1);
     }
@@ -393,12 +410,36 @@ lk_track_w15h_kernel(const LkArgs A)
             st = status && (fbe < A.fbt);
         }
     }
-    if (hl == 0 && valid) {
-        const long long o = (long long)pair * A.npts + pt;
-        A.out[2 * o] = fx;
-        A.out[2 * o + 1] = fy;
-        A.status[o] = (uint8_t)st;
-        A.err[o] = fst ? ferr : 0.f;
-        if (A.back) { A.back[2 * o] = bx; A.back[2 * o + 1] = by; }
+    if (!SEQ) {
+        if (hl == 0 && valid) {
+            const long long o = (long long)pair * A.npts + pt;
+            A.out[2 * o] = fx;
+            A.out[2 * o + 1] = fy;
+            A.status[o] = (uint8_t)st;
+            A.err[o] = fst ? ferr : 0.f;
+            if (A.back) { A.back[2 * o] = bx; A.back[2 * o + 1] = by; }
+        }
+    } else {
+        const bool live = valid && st != 0;            // alive[k+1] = alive[k] & status   (vg[vg] = v)
+        if (hl == 0 && in_set) {
+            const long long o = (long long)pair * A.npts + pt;
+            A.out[2 * o] = live ? fx : kSeqDeadXY;
+            A.out[2 * o + 1] = live ? fy : kSeqDeadXY;
+            A.err[o] = (valid && fst) ? ferr : 0.f;
+            A.alive[(long long)(pair + 1) * A.npts + pt] = live ? 1 : 0;
+        }
+        valid = live;
+        sx = fx; sy = fy;
+        if (!__any_sync(0xffffffffu, valid)) {         // both tracks of this warp are gone: park the remaining rows and leave
+            if (hl == 0 && in_set) {
+                for (int k2 = pair + 1; k2 < npairs_loop; ++k2) {
+                    const long long o = (long long)k2 * A.npts + pt;
+                    A.out[2 * o] = kSeqDeadXY; A.out[2 * o + 1] = kSeqDeadXY; A.err[o] = 0.f;
+                    A.alive[(long long)(k2 + 1) * A.npts + pt] = 0;
+                }
+            }
+            return;
+        }
     }
+  }
 }

@@ -19,6 +19,11 @@
 // (the reference compacts p[v]; LK treats points independently, so surviving tracks are bit-identical either way).
 #include "common.cuh"
 
+// lk_track.cu: the whole frame run in one launch (15x15 window, word-aligned pitches); 1 = launched, 0 = not applicable
+int vel_lk_sequence_w15h(const uint8_t* frames, int64_t frame_stride, int32_t pitch, const uint8_t* pyr, int64_t pyr_stride,
+                         const vel_pyr_layout* layout, int32_t nframes, int32_t npts, const vel_lk_params* params, float* tracks,
+                         uint8_t* alive, float* err, vel_stream_t stream);
+
 namespace {
 
 constexpr float kDeadXY = -1.0e5f;   // K2: floor(p * 2^-level - halfWin) < -win  at every level -> status 0, no memory access
@@ -394,6 +399,11 @@ VEL_API int vel_klt_sequence(const uint8_t* frames, int64_t frame_stride, int32_
     cudaStream_t st = (cudaStream_t)stream;
     const int nb = (npts + 255) / 256;
     seq_seed_kernel<<<nb, 256, 0, st>>>(alive, (float2*)tracks, npts);
+    // the reference's window (15x15): each half-warp carries its track through every frame inside ONE kernel
+    const int rc_seq = vel_lk_sequence_w15h(frames, frame_stride, pitch, pyr, pyr_stride, layout, nframes, npts, params, tracks, alive, err, stream);
+    if (rc_seq < 0) return rc_seq;
+    if (rc_seq == 1) return VEL_OK;
+    // any other window: one K2 launch per pair, the track state chained on the device
     for (int k = 0; k + 1 < nframes; ++k) {
         float* prev = tracks + (size_t)k * npts * 2;
         float* next = prev + (size_t)npts * 2;

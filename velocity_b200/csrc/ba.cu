@@ -20,6 +20,8 @@
 // ranks).
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -286,7 +288,7 @@ ba_point_prep_kernel(const double* __restrict__ V, const double* __restrict__ g,
 
 // W'[row][3i..3i+2] = W[row][3i..3i+2] * L_i   (row vector times lower-triangular 3x3)
 __global__ void __launch_bounds__(256)
-ba_scale_w_kernel(const double* __restrict__ W, const double* __restrict__ Lf, int nrows, int nt, double* __restrict__ Wp)
+ba_scale_w_kernel(const double* __restrict__ W, const double* __restrict__ Lf, int nrows, int nt, double* __restrict__ Wp, long long ldo)
 {
     const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
     if (idx >= (long long)nrows * nt) return;
@@ -294,7 +296,7 @@ ba_scale_w_kernel(const double* __restrict__ W, const double* __restrict__ Lf, i
     const double* w = W + idx * 3;
     const double* l = Lf + 6ll * i;
     const double w0 = w[0], w1 = w[1], w2 = w[2];
-    double* o = Wp + idx * 3;
+    double* o = Wp + (idx / nt) * ldo + 3ll * i;
     o[0] = w0 * l[0] + w1 * l[1] + w2 * l[3];
     o[1] = w1 * l[2] + w2 * l[4];
     o[2] = w2 * l[5];
@@ -358,13 +360,77 @@ ba_update_kernel(const double* __restrict__ Vinv, const double* __restrict__ y, 
     }
 }
 
-__global__ void ba_rms_finalize_kernel(const double* __restrict__ part, int n, long long nx, double* __restrict__ rms)
+// info != 0 (the Cholesky of the reduced system failed: not positive definite to working precision) turns rms(delta)
+// into NaN, so that the caller's convergence test cannot mistake a garbage update for progress
+__global__ void ba_rms_finalize_kernel(const double* __restrict__ part, int n, long long nx, double* __restrict__ rms,
+                                       const int* __restrict__ info)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.0;
         for (int k = 0; k < n; ++k) s += part[k];
-        *rms = sqrt(s / (double)nx);
+        *rms = (info && *info != 0) ? __longlong_as_double(0x7ff8000000000000ll) : sqrt(s / (double)nx);
     }
+}
+
+// VEL_BA_SOLVER=native: FP64 tensor-core SYRK + cooperative Cholesky of this library (csrc/dense_f64.cu), no vendor library on
+// the path.  Default ("vendor"): cuBLAS DSYRK / DGEMV + cuSOLVER DPOTRF / DPOTRS, which today are faster on the Cholesky's
+// latency chain (measured numbers in DESIGN.md).
+bool native_solver()
+{
+    const char* e = getenv("VEL_BA_SOLVER");
+    return e && strcmp(e, "native") == 0;
+}
+
+constexpr int GEMV_ROW_CHUNKS = 8;
+
+// rhs[r] -= sum_k W[r][k] y[k]   (one CTA per row, fixed-order reduction)
+__global__ void __launch_bounds__(256)
+ba_gemv_rows_sub_kernel(const double* __restrict__ W, long long ld, int n3, const double* __restrict__ y, double* __restrict__ rhs)
+{
+    __shared__ double sred[8];
+    const double* w = W + (long long)blockIdx.x * ld;
+    double s = 0.0;
+    for (int k = threadIdx.x; k < n3; k += 256) s += w[k] * y[k];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) sred[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int q = 0; q < 8; ++q) t += sred[q];
+        rhs[blockIdx.x] -= t;
+    }
+}
+
+// tpart[c][k] = sum over the rows of chunk c of W[r][k] dc[r]   (thread per column, coalesced across k)
+__global__ void __launch_bounds__(256)
+ba_gemv_cols_kernel(const double* __restrict__ W, long long ld, int nrows, int n3, const double* __restrict__ dc, double* __restrict__ tpart)
+{
+    const int k = blockIdx.x * 256 + threadIdx.x;
+    if (k >= n3) return;
+    const int per = (nrows + GEMV_ROW_CHUNKS - 1) / GEMV_ROW_CHUNKS;
+    const int r0 = blockIdx.y * per, r1 = min(nrows, r0 + per);
+    double s = 0.0;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) s += W[(long long)r * ld + k] * dc[r];
+    tpart[(long long)blockIdx.y * n3 + k] = s;
+}
+
+__global__ void ba_gemv_cols_reduce_kernel(const double* __restrict__ tpart, int n3, double* __restrict__ t)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n3) return;
+    double s = 0.0;
+    for (int c = 0; c < GEMV_ROW_CHUNKS; ++c) s += tpart[(long long)c * n3 + k];
+    t[k] = s;
+}
+
+// zero the padding columns [n3, ld) of W'
+__global__ void ba_zero_pad_kernel(double* __restrict__ Wp, long long ld, int nrows, int n3)
+{
+    const int pad = (int)(ld - n3);
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pad <= 0 || idx >= (long long)nrows * pad) return;
+    Wp[(idx / pad) * ld + n3 + idx % pad] = 0.0;
 }
 
 struct Handles {
@@ -385,7 +451,7 @@ Handles* handles()
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct SolveLayout {
-    size_t off_wp, off_s, off_vinv, off_l, off_y, off_rhs, off_t, off_part, off_info, off_potrf, total;
+    size_t off_wp, off_s, off_vinv, off_l, off_y, off_rhs, off_t, off_part, off_info, off_flags, off_tpart, off_potrf, total, ldw;
     int lwork;
 };
 
@@ -393,7 +459,8 @@ bool solve_layout(int nt, int nc, SolveLayout* L, bool query_potrf)
 {
     const size_t n6 = 6ull * nc, n3 = 3ull * nt;
     size_t o = 0;
-    L->off_wp = o; o += align256(sizeof(double) * n6 * n3);
+    L->ldw = (n3 + 31) / 32 * 32;                          // the native SYRK wants rows zero-padded to its k-tile
+    L->off_wp = o; o += align256(sizeof(double) * n6 * L->ldw);
     L->off_s = o; o += align256(sizeof(double) * n6 * n6);
     L->off_vinv = o; o += align256(sizeof(double) * 6 * nt);
     L->off_l = o; o += align256(sizeof(double) * 6 * nt);
@@ -402,8 +469,10 @@ bool solve_layout(int nt, int nc, SolveLayout* L, bool query_potrf)
     L->off_t = o; o += align256(sizeof(double) * n3);
     L->off_part = o; o += align256(sizeof(double) * ((nt + n6) / PT_THREADS + 2));
     L->off_info = o; o += 256;
+    L->off_flags = o; o += vel_dense_syrk_workspace((int)(n6 > 0 ? n6 : 1), (int)(n3 > 0 ? n3 : 1));
+    L->off_tpart = o; o += align256(sizeof(double) * GEMV_ROW_CHUNKS * n3);
     L->lwork = 0;
-    if (query_potrf && nc > 0) {
+    if (query_potrf && nc > 0 && !native_solver()) {
         Handles* h = handles();
         if (!h) return false;
         int lwork = 0;
@@ -460,6 +529,25 @@ VEL_API size_t vel_ba_solve_workspace(int32_t nt, int32_t nc)
     return L.total;
 }
 
+// internal entry points of dense_f64.cu (declared in the public header as well)
+// The dense part of the solve with this library's own kernels:  S(lower) -= W' W'^T;  rhs -= W y;  S delta_c = rhs;  t = W^T delta_c.
+// W' [nrows][ldw] zero-padded, W [nrows][n3] the unscaled cross blocks.  info (device) is raised by a failed Cholesky.
+static int dense_solve_native(const double* W, const double* Wp, long long ldw, int nrows, int n3, double* S, const double* y, double* rhs,
+                              double* t, double* tpart, void* flags, size_t flags_bytes, int* info, cudaStream_t st)
+{
+    int rc = vel_syrk_lower_sub(Wp, ldw, nrows, n3, S, nrows, flags, flags_bytes, (vel_stream_t)st);
+    if (rc != VEL_OK) return rc;
+    ba_gemv_rows_sub_kernel<<<nrows, 256, 0, st>>>(W, n3, n3, y, rhs);
+    VEL_LAUNCH_CHECK("ba_gemv_rows_sub_kernel");
+    rc = vel_spd_solve(S, nrows, nrows, rhs, info, (vel_stream_t)st);
+    if (rc != VEL_OK) return rc;
+    ba_gemv_cols_kernel<<<dim3((n3 + 255) / 256, GEMV_ROW_CHUNKS), 256, 0, st>>>(W, n3, nrows, n3, rhs, tpart);
+    VEL_LAUNCH_CHECK("ba_gemv_cols_kernel");
+    ba_gemv_cols_reduce_kernel<<<(n3 + 255) / 256, 256, 0, st>>>(tpart, n3, t);
+    VEL_LAUNCH_CHECK("ba_gemv_cols_reduce_kernel");
+    return VEL_OK;
+}
+
 VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
                          double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream)
 {
@@ -484,16 +572,33 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
     const int n6 = 6 * nc, n3 = 3 * nt;
     const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
 
+    const bool native = native_solver();
+    VEL_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     ba_point_prep_kernel<<<pblocks, PT_THREADS, 0, st>>>(V, g, nt, Vinv, Lf, y);
     VEL_LAUNCH_CHECK("ba_point_prep_kernel");
-    if (nc > 0) {
+    if (nc > 0 && native) {
+        const long long nel = (long long)n6 * nt;
+        ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, n6, nt, Wp, (long long)L.ldw);
+        VEL_LAUNCH_CHECK("ba_scale_w_kernel");
+        if ((int)L.ldw > n3) {
+            const long long npad = (long long)n6 * (L.ldw - n3);
+            ba_zero_pad_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Wp, (long long)L.ldw, n6, n3);
+            VEL_LAUNCH_CHECK("ba_zero_pad_kernel");
+        }
+        const long long ns = (long long)n6 * n6;
+        ba_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(U, g, nt, nc, S, rhs);
+        VEL_LAUNCH_CHECK("ba_init_s_kernel");
+        const int rc = dense_solve_native(W, Wp, (long long)L.ldw, n6, n3, S, y, rhs, t, (double*)(wb + L.off_tpart), wb + L.off_flags,
+                                          L.off_tpart - L.off_flags, info, st);
+        if (rc != VEL_OK) return rc;
+    } else if (nc > 0) {
         Handles* h = handles();
         VEL_CHECK_ARG(h != nullptr, "vel_ba_solve: cuBLAS/cuSOLVER handles unavailable");
         cublasSetStream(h->blas, st);
         cusolverDnSetStream(h->solver, st);
         cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
         const long long nel = (long long)n6 * nt;
-        ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, n6, nt, Wp);
+        ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, n6, nt, Wp, (long long)n3);
         VEL_LAUNCH_CHECK("ba_scale_w_kernel");
         const long long ns = (long long)n6 * n6;
         ba_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(U, g, nt, nc, S, rhs);
@@ -526,7 +631,7 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
     const int ublocks = (nt + n6 + PT_THREADS - 1) / PT_THREADS;
     ba_update_kernel<<<ublocks, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nc, x, part);
     VEL_LAUNCH_CHECK("ba_update_kernel");
-    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + n6, rms_delta);
+    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + n6, rms_delta, info);
     VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
     return VEL_OK;
 }
@@ -823,10 +928,11 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
     const int nc_equiv = (nq + 5) / 6;
     SolveLayout L;
     VEL_CHECK_ARG(solve_layout(nt, nc_equiv, &L, false), "vel_ba2_solve: layout failed");
-    Handles* h = handles();
-    VEL_CHECK_ARG(h != nullptr, "vel_ba2_solve: cuBLAS/cuSOLVER handles unavailable");
+    const bool native = native_solver();
+    Handles* h = native ? nullptr : handles();
+    VEL_CHECK_ARG(native || h != nullptr, "vel_ba2_solve: cuBLAS/cuSOLVER handles unavailable");
     int lwork = 0;
-    if (cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, nq, nullptr, nq, &lwork) != CUSOLVER_STATUS_SUCCESS) {
+    if (!native && cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, nq, nullptr, nq, &lwork) != CUSOLVER_STATUS_SUCCESS) {
         vel_set_error("vel_ba2_solve: cusolverDnDpotrf_bufferSize failed");
         return VEL_ERR_CUDA;
     }
@@ -846,13 +952,37 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
     double* potrf_work = (double*)(wb + L.off_potrf);
     const int n3 = 3 * nt;
     const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    VEL_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
     ba_point_prep_kernel<<<pblocks, PT_THREADS, 0, st>>>(V, g, nt, Vinv, Lf, y);
     VEL_LAUNCH_CHECK("ba_point_prep_kernel");
+    if (native) {
+        // the layout was sized for ceil(nq/6) cameras: nq <= 6*nc_equiv rows of the same padded pitch
+        const long long nel_n = (long long)nq * nt;
+        ba_scale_w_kernel<<<(unsigned)((nel_n + 255) / 256), 256, 0, st>>>(W, Lf, nq, nt, Wp, (long long)L.ldw);
+        VEL_LAUNCH_CHECK("ba_scale_w_kernel");
+        if ((int)L.ldw > n3) {
+            const long long npad = (long long)nq * (L.ldw - n3);
+            ba_zero_pad_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Wp, (long long)L.ldw, nq, n3);
+            VEL_LAUNCH_CHECK("ba_zero_pad_kernel");
+        }
+        const long long ns_n = (long long)nq * nq;
+        ba2_init_s_kernel<<<(unsigned)((ns_n + 255) / 256), 256, 0, st>>>(G, g, nt, nq, S, rhs);
+        VEL_LAUNCH_CHECK("ba2_init_s_kernel");
+        const int rc = dense_solve_native(W, Wp, (long long)L.ldw, nq, n3, S, y, rhs, t, (double*)(wb + L.off_tpart), wb + L.off_flags,
+                                          L.off_tpart - L.off_flags, info, st);
+        if (rc != VEL_OK) return rc;
+        const int ublocks_n = (nt + nq + PT_THREADS - 1) / PT_THREADS;
+        ba2_update_kernel<<<ublocks_n, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nq, x, part);
+        VEL_LAUNCH_CHECK("ba2_update_kernel");
+        ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks_n, (long long)n3 + nq, rms_delta, info);
+        VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
+        return VEL_OK;
+    }
     cublasSetStream(h->blas, st);
     cusolverDnSetStream(h->solver, st);
     cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
     const long long nel = (long long)nq * nt;
-    ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, nq, nt, Wp);
+    ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, nq, nt, Wp, (long long)n3);
     VEL_LAUNCH_CHECK("ba_scale_w_kernel");
     const long long ns = (long long)nq * nq;
     ba2_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(G, g, nt, nq, S, rhs);
@@ -875,7 +1005,7 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
     const int ublocks = (nt + nq + PT_THREADS - 1) / PT_THREADS;
     ba2_update_kernel<<<ublocks, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nq, x, part);
     VEL_LAUNCH_CHECK("ba2_update_kernel");
-    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + nq, rms_delta);
+    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + nq, rms_delta, info);
     VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
     return VEL_OK;
 }

@@ -43,6 +43,9 @@ void vel_keep_async_pool_cached();
         }                                                                              \
     } while (0)
 
+// dense_f64.cu: bytes of scratch vel_syrk_lower_sub needs for an m x k operand (ba.cu sizes its workspace with it)
+size_t vel_dense_syrk_workspace(int m, int k);
+
 static constexpr int kNumSMs = 148;  // B200
 
 // BORDER_REFLECT_101 (gfedcb|abcdefgh|gfedcba).  Valid for any overshoot when n > 1.

@@ -217,8 +217,8 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
                     const int cc = col0 + wc * 32 + j * 8 + 2 * t4;
                     if (i < mt_cnt && j < nt_cnt && r < rlim) {
                         double* p = S + (long long)r * lds + cc;
-                        if (cc < clim) p[0] = __ldcg(p) - acc[i][j][0];
-                        if (cc + 1 < clim) p[1] = __ldcg(p + 1) - acc[i][j][1];
+                        if (cc < clim && (!diag || cc <= r)) p[0] = __ldcg(p) - acc[i][j][0];          // strictly-upper entries stay untouched
+                        if (cc + 1 < clim && (!diag || cc + 1 <= r)) p[1] = __ldcg(p + 1) - acc[i][j][1];
                     }
                 }
             }

@@ -187,6 +187,22 @@ size_t vel_ba_solve_workspace(int32_t nt, int32_t nc);
 int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
                  double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
 
+/* K8 in three stages, for the camera-sharded form: every rank accumulates its cameras (vel_ba_accumulate with a
+ * camera slice), the point blocks are all-reduced and the camera rows all-gathered; then
+ *   vel_ba_reduce   per-point (V+I)^-1 factors, W' = W blockdiag(L), the rank's TILE ROWS [blk_lo, blk_hi) of the reduced camera
+ *                   system S = U + I - W' W'^T (row-major, lower; tile-row geometry from vel_syrk_tile_rows(6*nc)), rhs = g_c - W y
+ *   (the ranks send their rows of S to the owner)
+ *   vel_ba_factor   owner only: Cholesky of S, delta_c = S^-1 rhs in place in rhs
+ *   (the owner broadcasts rhs)
+ *   vel_ba_update   t = W^T delta_c, delta_p, x += 0.9 delta, rms(delta)
+ * blk_lo = 0, blk_hi = -1 computes all of S; then the three calls equal vel_ba_solve.  vel_ba_solve_layout returns the byte offsets of
+ * S [6nc][6nc] and rhs [6nc] inside `work` (vel_ba_solve_workspace bytes). */
+int vel_ba_solve_layout(int32_t nt, int32_t nc, int64_t* off_S, int64_t* off_rhs);
+int vel_ba_reduce(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, int32_t blk_lo, int32_t blk_hi,
+                  void* work, size_t work_bytes, vel_stream_t stream);
+int vel_ba_factor(int32_t nt, int32_t nc, void* work, size_t work_bytes, vel_stream_t stream);
+int vel_ba_update(const double* W, int32_t nt, int32_t nc, double* x, double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
+
 /* K8 building blocks -- the dense float64 algebra of `inv(JJ^T + I) @ ...` (utils/NLS.py:236) after the point blocks are
  * eliminated, hand-written (FP64 tensor-core MMA; no cuBLAS / cuSOLVER anywhere in this library):
  *   vel_syrk_lower_sub: S(lower triangle, row-major [m][lds]) -= E E^T for E row-major [m][ld] with k used columns;
@@ -195,6 +211,10 @@ int vel_ba_solve(const double* V, const double* U, const double* W, const double
  *   vel_spd_solve: Cholesky S = L L^T in place (lower, row-major) and b <- S^-1 b; info[0] (DEVICE) = 0, or 1 when S is not
  *     positive definite to working precision (b is then meaningless). */
 size_t vel_syrk_lower_sub_workspace(int32_t m, int32_t k);
+/* the tile-row geometry of the product (nb blocks of rows_per_block rows) and the product restricted to tile rows [blk_lo, blk_hi) */
+int vel_syrk_tile_rows(int32_t m, int32_t* nb, int32_t* rows_per_block);
+int vel_syrk_lower_sub_rows(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                            int32_t blk_lo, int32_t blk_hi, vel_stream_t stream);
 int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
                        vel_stream_t stream);
 int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream);

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ba_exchange import camera_slices, exchange_blocks
+from .ba_exchange import camera_slices, exchange_blocks, gather_rows_to_owner, small_buffer, tile_row_ranges
 from .common import addcol1, cam2ned, cc2sc, pscale, rms, sc2cc, world2image
 from .device import ptr, require_cuda, stream_ptr
 from .transforms import dcm2rpy, rpy2dcm
@@ -85,36 +85,45 @@ def estimateWorldCameraPose(K, p, p3, t=np.array([0, 0, 1]), R=np.eye(3), findR=
 
 
 class BundleAdjuster:
-    """Device-resident state of one fcnNLS_batch problem (K7 + K8).  With torch.distributed
-    initialised and `shard=True`, cameras are split across ranks: each rank accumulates the blocks
-    of its own cameras, V / g_p / cost are all-reduced, the camera blocks (U, g_c, W rows) are
-    all-gathered, and every rank solves the same reduced system redundantly."""
+    """Device-resident state of one fcnNLS_batch problem (K7 + K8).  With torch.distributed initialised and `shard=True`,
+    cameras are split across ranks (ba_exchange.py): each rank accumulates the blocks of its own cameras, ONE all-reduce
+    carries V / g_p / cost (partial sums) together with U / g_c (owner entries), ONE all-gather carries the cross blocks W;
+    each rank then forms its tile rows of the reduced camera system, the owner (rank 0) factors it once and broadcasts
+    delta_c, and every rank applies the same update."""
 
     launches_per_step = 10   # this library's kernels per LM iteration (K7: 5, K8: 5)
 
-    def __init__(self, K, z, x0, nt, nc, shard=False):
+    def __init__(self, K, z, x0, nt, nc, shard=False, group=None):
         require_cuda()
         self.nt, self.nc = nt, nc
         dev = torch.device("cuda", torch.cuda.current_device())
         self.K = _dev64(K)
         self.z = _dev64(z)
         self.x = _dev64(x0).clone()
-        nx = 3 * nt + 6 * nc
-        self.V = torch.zeros((nt, 6), dtype=torch.float64, device=dev)
-        self.U = torch.zeros((max(nc, 1), 21), dtype=torch.float64, device=dev)
-        self.W = torch.zeros((max(6 * nc, 1), 3 * nt), dtype=torch.float64, device=dev)
-        self.g = torch.zeros((nx,), dtype=torch.float64, device=dev)
-        self.cost = torch.zeros((1,), dtype=torch.float64, device=dev)
+        self.group = group
+        self.rank, self.world = 0, 1
+        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
+            self.rank, self.world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
+        self.per, self.slices = camera_slices(nc, self.world)
+        self.small, self.cost, self.V, self.g, self.U = small_buffer(nt, nc, dev)
+        self.W = torch.zeros((max(6 * self.per * self.world, 1), 3 * nt), dtype=torch.float64, device=dev)
         self.rms_delta = torch.zeros((1,), dtype=torch.float64, device=dev)
         L = _lib.lib()
         nbytes = int(L.vel_ba_solve_workspace(nt, nc))
         if nbytes == 0:
             raise RuntimeError("vel_ba_solve_workspace failed: %s" % L.vel_last_error().decode())
         self.work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        self.rank, self.world = 0, 1
-        if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
-            self.rank, self.world = torch.distributed.get_rank(), torch.distributed.get_world_size()
-        self.slices = camera_slices(nc, self.world)
+        self.timing = None
+        if self.world > 1:
+            off_S, off_rhs = C.c_int64(0), C.c_int64(0)
+            _lib.check(L.vel_ba_solve_layout(nt, nc, C.byref(off_S), C.byref(off_rhs)), "vel_ba_solve_layout")
+            n6 = 6 * nc
+            self.S = self.work[off_S.value:off_S.value + 8 * n6 * n6].view(torch.float64).view(n6, n6)
+            self.rhs = self.work[off_rhs.value:off_rhs.value + 8 * n6].view(torch.float64)
+            nb, bme = C.c_int32(0), C.c_int32(0)
+            _lib.check(L.vel_syrk_tile_rows(n6, C.byref(nb), C.byref(bme)), "vel_syrk_tile_rows")
+            self.blocks = tile_row_ranges(nb.value, self.world)
+            self.row_ranges = [(min(n6, lo * bme.value), min(n6, hi * bme.value)) for lo, hi in self.blocks]
 
     def reset(self, z, x0):
         """New measurements / start values for a problem of the same size (buffers are reused)."""
@@ -124,15 +133,29 @@ class BundleAdjuster:
     def accumulate(self):
         L = _lib.lib()
         first, count = self.slices[self.rank]
+        if self.world > 1:
+            self.small.zero_()               # foreign cameras' U / g_c entries must be exact zeros for the gathering all-reduce
         _lib.check(L.vel_ba_accumulate(ptr(self.K), ptr(self.x), ptr(self.z), self.nt, self.nc, first, count, ptr(self.V),
                                        ptr(self.U), ptr(self.W), ptr(self.g), ptr(self.cost), stream_ptr()), "vel_ba_accumulate")
         if self.world > 1:
-            exchange_blocks(self.V, self.U, self.W, self.g, self.cost, self.nt, self.nc, self.slices)
+            exchange_blocks(self.small, self.W, self.per, self.rank, self.world, self.group)
 
     def solve(self):
         L = _lib.lib()
-        _lib.check(L.vel_ba_solve(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, ptr(self.x),
-                                  ptr(self.rms_delta), ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_solve")
+        if self.world == 1:
+            _lib.check(L.vel_ba_solve(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, ptr(self.x),
+                                      ptr(self.rms_delta), ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_solve")
+            return
+        lo, hi = self.blocks[self.rank]
+        _lib.check(L.vel_ba_reduce(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, lo, hi, ptr(self.work),
+                                   self.work.numel(), stream_ptr()), "vel_ba_reduce")
+        gather_rows_to_owner(self.S, self.row_ranges, self.rank, 0, self.group)
+        if self.rank == 0:
+            _lib.check(L.vel_ba_factor(self.nt, self.nc, ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_factor")
+        torch.distributed.broadcast(self.rhs, src=0 if self.group is None else torch.distributed.get_global_rank(self.group, 0),
+                                    group=self.group)
+        _lib.check(L.vel_ba_update(ptr(self.W), self.nt, self.nc, ptr(self.x), ptr(self.rms_delta), ptr(self.work), self.work.numel(),
+                                   stream_ptr()), "vel_ba_update")
 
     def step(self):
         """One LM iteration.  Returns (f = rms(z - zhat) before the update, rms(delta))."""

@@ -62,6 +62,12 @@ SIGNATURES = {
     "vel_ba_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
     "vel_syrk_lower_sub_workspace": (C.c_size_t, [_I32, _I32]),
     "vel_syrk_lower_sub": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, C.c_size_t, _P]),
+    "vel_syrk_tile_rows": (C.c_int, [_I32, C.POINTER(_I32), C.POINTER(_I32)]),
+    "vel_syrk_lower_sub_rows": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, C.c_size_t, _I32, _I32, _P]),
+    "vel_ba_solve_layout": (C.c_int, [_I32, _I32, C.POINTER(_I64), C.POINTER(_I64)]),
+    "vel_ba_reduce": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _I32, _I32, _P, C.c_size_t, _P]),
+    "vel_ba_factor": (C.c_int, [_I32, _I32, _P, C.c_size_t, _P]),
+    "vel_ba_update": (C.c_int, [_P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
     "vel_spd_solve": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
     "vel_ba2_accumulate": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vel_ba2_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),

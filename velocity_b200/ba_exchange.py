@@ -1,37 +1,88 @@
-"""Multi-GPU exchange step of the bundle adjustment.
+"""Multi-GPU exchange of the bundle adjustment: cameras (frames) shard across ranks, points are shared.
 
-Cameras 0..nc are split into `world` contiguous slices.  After K7 every rank holds
-  * PARTIAL sums over its cameras in V [nt,6], g[:3nt] (point part) and cost  -> all-reduce (sum)
-  * the rows of U [nc,21], W [6nc,3nt] and the camera part of g that belong to its cameras
-                                                                               -> all-gather
-so that every rank ends up with the identical full system and solves it redundantly.  Rank slices
-can be uneven (camera 0 carries no parameters), so the gather is expressed as one broadcast per
-owner into the owner's row block of the preallocated full buffers: no packing copy, no padding.
-Works on any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests).
+Per LM iteration there are exactly TWO data-path collectives before the solve:
+
+  1. ONE all-reduce (sum) of the "small" buffer  [cost | V (nt x 6) | g (3nt + 6nc) | U (nc x 21)]:
+     V, the point part of g and cost are PARTIAL sums over each rank's cameras; the camera entries (U rows, camera part of g)
+     are non-zero on their owner only and zero elsewhere, so the same sum also gathers them (x + 0 is exact).
+  2. ONE all_gather_into_tensor of the cross blocks W [6 * per * world][3nt]: every rank owns `per` consecutive parameterised
+     cameras = one contiguous, equally sized row block (the last block is padded with unused rows), gathered in place.
+
+and two small ones inside the solve (velocity_b200.NLS.BundleAdjuster.solve): the ranks' tile rows of the reduced camera system
+S go to the owner (rank 0) point-to-point, the owner factors S once and broadcasts delta_c -- S is not factored on every rank.
+Works on any torch.distributed backend (NCCL on the GPUs; gloo in the CPU test of the exchange logic).
 """
+import torch
 import torch.distributed as dist
 
 
 def camera_slices(nc, world):
-    """Contiguous split of camera indices 0..nc (inclusive) into `world` (first, count) slices."""
-    bounds = [(nc + 1) * r // world for r in range(world + 1)]
-    return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+    """(per, slices): `per` = parameterised cameras per rank; slices[r] = (first, count) over the camera indices 0..nc of
+    vel_ba_accumulate.  Camera 0 (fixed, no parameters, utils/NLS.py:207-208) goes to rank 0 on top of its `per` cameras."""
+    per = max(1, -(-nc // world))
+    out = []
+    for r in range(world):
+        lo, hi = min(nc, r * per), min(nc, (r + 1) * per)          # parameterised cameras lo..hi-1 (camera index = lo+1..hi)
+        out.append((0, hi + 1) if r == 0 else (lo + 1, hi - lo))
+    return per, out
 
 
 def param_rows(first, count):
-    """Parameterised-camera row range [lo, hi) (camera c>=1 owns row c-1) of a camera slice."""
+    """Parameterised-camera row range [lo, hi) (camera c >= 1 owns row c-1) of a camera slice."""
     return max(first, 1) - 1, max(first + count - 1, 0)
 
 
-def exchange_blocks(V, U, W, g, cost, nt, nc, slices, group=None):
-    dist.all_reduce(V, group=group)
-    dist.all_reduce(g[:3 * nt], group=group)
-    dist.all_reduce(cost, group=group)
-    for owner, (first, count) in enumerate(slices):
-        lo, hi = param_rows(first, count)
-        if hi <= lo:
-            continue
-        dist.broadcast(U[lo:hi], src=owner, group=group)
-        dist.broadcast(W[6 * lo:6 * hi], src=owner, group=group)
-        dist.broadcast(g[3 * nt + 3 * lo:3 * nt + 3 * hi], src=owner, group=group)
-        dist.broadcast(g[3 * nt + 3 * nc + 3 * lo:3 * nt + 3 * nc + 3 * hi], src=owner, group=group)
+def small_buffer(nt, nc, device, dtype=torch.float64):
+    """The all-reduce buffer and its views (cost [1], V [nt,6], g [3nt+6nc], U [nc,21])."""
+    n = 2 + 6 * nt + 3 * nt + 6 * nc + 21 * max(nc, 1)
+    buf = torch.zeros((n,), dtype=dtype, device=device)
+    o = 2
+    V = buf[o:o + 6 * nt].view(nt, 6)
+    o += 6 * nt
+    g = buf[o:o + 3 * nt + 6 * nc]
+    o += 3 * nt + 6 * nc
+    U = buf[o:o + 21 * max(nc, 1)].view(max(nc, 1), 21)
+    return buf, buf[0:1], V, g, U
+
+
+def exchange_blocks(small, W, per, rank, world, group=None):
+    """The two collectives.  `small` holds this rank's partial sums / own camera entries (zeros for foreign cameras);
+    W [6*per*world, 3nt] holds this rank's rows in its own row block."""
+    dist.all_reduce(small, group=group)
+    rows = 6 * per
+    dist.all_gather_into_tensor(W, W[rank * rows:(rank + 1) * rows], group=group)
+
+
+def tile_row_ranges(nb, world):
+    """Contiguous ranges of the nb tile rows of the lower-triangular product, balanced by tile count (row bi has bi+1 tiles)."""
+    total = nb * (nb + 1) // 2
+    bounds, acc, r = [0], 0, 1
+    for bi in range(nb):
+        acc += bi + 1
+        while r < world and acc >= total * r / world:
+            bounds.append(bi + 1)
+            r += 1
+    while len(bounds) < world + 1:
+        bounds.append(nb)
+    bounds[-1] = nb
+    return [(bounds[i], bounds[i + 1]) for i in range(world)]
+
+
+def gather_rows_to_owner(S, row_ranges, rank, owner=0, group=None):
+    """Rank r holds rows row_ranges[r] of the row-major matrix S; the owner receives every other rank's rows in place."""
+    ops = []
+    if rank == owner:
+        for r, (lo, hi) in enumerate(row_ranges):
+            if r != owner and hi > lo:
+                ops.append(dist.P2POp(dist.irecv, S[lo:hi], _global(r, group), group))
+    else:
+        lo, hi = row_ranges[rank]
+        if hi > lo:
+            ops.append(dist.P2POp(dist.isend, S[lo:hi], _global(owner, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+
+def _global(group_rank, group):
+    return group_rank if group is None else dist.get_global_rank(group, group_rank)

@@ -636,6 +636,113 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
     return VEL_OK;
 }
 
+// ---- the solve in three stages (the sharded form runs collectives between them) ---------------------------
+// vel_ba_reduce : (V+I)^-1 factors, W' = W blockdiag(L), S[rows of tile rows blk_lo..blk_hi) = U + I - W' W'^T, rhs = g_c - W y
+// vel_ba_factor : Cholesky of S and delta_c = S^-1 rhs (in place in rhs)           -- the owner rank only
+// vel_ba_update : t = W^T delta_c, delta_p = y - (V+I)^-1 t, x += 0.9 delta, rms(delta)
+// S is row-major, lower triangle, [6nc][6nc]; byte offsets of S and rhs inside `work` come from vel_ba_solve_layout.
+VEL_API int vel_ba_solve_layout(int32_t nt, int32_t nc, int64_t* off_S, int64_t* off_rhs)
+{
+    VEL_CHECK_ARG(nt > 0 && nc >= 0 && off_S && off_rhs, "vel_ba_solve_layout: bad argument");
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc, &L, false), "vel_ba_solve_layout: layout failed");
+    *off_S = (int64_t)L.off_s;
+    *off_rhs = (int64_t)L.off_rhs;
+    return VEL_OK;
+}
+
+VEL_API int vel_ba_reduce(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, int32_t blk_lo,
+                          int32_t blk_hi, void* work, size_t work_bytes, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(V && U && W && g && work, "vel_ba_reduce: NULL argument");
+    VEL_CHECK_ARG(nt > 0 && nc > 0, "vel_ba_reduce: bad sizes nt=%d nc=%d", nt, nc);
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc, &L, true), "vel_ba_reduce: layout failed");
+    VEL_CHECK_ARG(work_bytes >= L.total, "vel_ba_reduce: workspace %zu B < required %zu B", work_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wb = (char*)work;
+    double* Wp = (double*)(wb + L.off_wp);
+    double* S = (double*)(wb + L.off_s);
+    double* Vinv = (double*)(wb + L.off_vinv);
+    double* Lf = (double*)(wb + L.off_l);
+    double* y = (double*)(wb + L.off_y);
+    double* rhs = (double*)(wb + L.off_rhs);
+    int* info = (int*)(wb + L.off_info);
+    const int n6 = 6 * nc, n3 = 3 * nt;
+    const int pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    VEL_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    ba_point_prep_kernel<<<pblocks, PT_THREADS, 0, st>>>(V, g, nt, Vinv, Lf, y);
+    VEL_LAUNCH_CHECK("ba_point_prep_kernel");
+    const long long nel = (long long)n6 * nt;
+    ba_scale_w_kernel<<<(unsigned)((nel + 255) / 256), 256, 0, st>>>(W, Lf, n6, nt, Wp, (long long)L.ldw);
+    VEL_LAUNCH_CHECK("ba_scale_w_kernel");
+    if ((int)L.ldw > n3) {
+        const long long npad = (long long)n6 * (L.ldw - n3);
+        ba_zero_pad_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, st>>>(Wp, (long long)L.ldw, n6, n3);
+        VEL_LAUNCH_CHECK("ba_zero_pad_kernel");
+    }
+    const long long ns = (long long)n6 * n6;
+    ba_init_s_kernel<<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(U, g, nt, nc, S, rhs);
+    VEL_LAUNCH_CHECK("ba_init_s_kernel");
+    int rc = vel_syrk_lower_sub_rows(Wp, (long long)L.ldw, n6, n3, S, n6, wb + L.off_flags, L.off_tpart - L.off_flags, blk_lo, blk_hi, stream);
+    if (rc != VEL_OK) return rc;
+    ba_gemv_rows_sub_kernel<<<n6, 256, 0, st>>>(W, n3, n3, y, rhs);
+    VEL_LAUNCH_CHECK("ba_gemv_rows_sub_kernel");
+    return VEL_OK;
+}
+
+VEL_API int vel_ba_factor(int32_t nt, int32_t nc, void* work, size_t work_bytes, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(work && nt > 0 && nc > 0, "vel_ba_factor: bad argument");
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc, &L, true), "vel_ba_factor: layout failed");
+    VEL_CHECK_ARG(work_bytes >= L.total, "vel_ba_factor: workspace %zu B < required %zu B", work_bytes, L.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wb = (char*)work;
+    double* S = (double*)(wb + L.off_s);
+    double* rhs = (double*)(wb + L.off_rhs);
+    int* info = (int*)(wb + L.off_info);
+    const int n6 = 6 * nc;
+    if (native_solver()) return vel_spd_solve(S, n6, n6, rhs, info, stream);
+    Handles* h = handles();
+    VEL_CHECK_ARG(h != nullptr, "vel_ba_factor: cuSOLVER handle unavailable");
+    cusolverDnSetStream(h->solver, st);
+    // row-major lower == column-major upper
+    if (cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_UPPER, n6, S, n6, (double*)(wb + L.off_potrf), L.lwork, info) != CUSOLVER_STATUS_SUCCESS ||
+        cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_UPPER, n6, 1, S, n6, rhs, n6, info) != CUSOLVER_STATUS_SUCCESS) {
+        vel_set_error("vel_ba_factor: cuSOLVER Cholesky failed");
+        return VEL_ERR_CUDA;
+    }
+    return VEL_OK;
+}
+
+VEL_API int vel_ba_update(const double* W, int32_t nt, int32_t nc, double* x, double* rms_delta, void* work, size_t work_bytes,
+                          vel_stream_t stream)
+{
+    VEL_CHECK_ARG(W && x && rms_delta && work && nt > 0 && nc > 0, "vel_ba_update: bad argument");
+    SolveLayout L;
+    VEL_CHECK_ARG(solve_layout(nt, nc, &L, false), "vel_ba_update: layout failed");
+    cudaStream_t st = (cudaStream_t)stream;
+    char* wb = (char*)work;
+    double* Vinv = (double*)(wb + L.off_vinv);
+    double* y = (double*)(wb + L.off_y);
+    double* rhs = (double*)(wb + L.off_rhs);
+    double* t = (double*)(wb + L.off_t);
+    double* part = (double*)(wb + L.off_part);
+    int* info = (int*)(wb + L.off_info);
+    const int n6 = 6 * nc, n3 = 3 * nt;
+    ba_gemv_cols_kernel<<<dim3((n3 + 255) / 256, GEMV_ROW_CHUNKS), 256, 0, st>>>(W, n3, n6, n3, rhs, (double*)(wb + L.off_tpart));
+    VEL_LAUNCH_CHECK("ba_gemv_cols_kernel");
+    ba_gemv_cols_reduce_kernel<<<(n3 + 255) / 256, 256, 0, st>>>((const double*)(wb + L.off_tpart), n3, t);
+    VEL_LAUNCH_CHECK("ba_gemv_cols_reduce_kernel");
+    const int ublocks = (nt + n6 + PT_THREADS - 1) / PT_THREADS;
+    ba_update_kernel<<<ublocks, PT_THREADS, 0, st>>>(Vinv, y, t, rhs, nt, nc, x, part);
+    VEL_LAUNCH_CHECK("ba_update_kernel");
+    ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + n6, rms_delta, info);
+    VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
+    return VEL_OK;
+}
+
 // =====================================================================================================
 // fcnNLS_batch2 (utils/NLS.py:253-328): same damped Gauss-Newton, different camera model.
 // Parameters x = [points nt*3 | q], q = [joint roll,pitch,yaw (3) | el | az | range_1..range_nc]:

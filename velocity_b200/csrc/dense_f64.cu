@@ -66,15 +66,20 @@ constexpr int SY_STAGE_DOUBLES = 2 * SY_BM * SY_LDS;                       // A 
 constexpr size_t SY_SMEM = sizeof(double) * SY_STAGES * SY_STAGE_DOUBLES;   // 221,184 B
 
 struct SyrkPlan {
-    int nb, bme, ntiles, sk, ktiles, grid;
+    int nb, bme, ntiles, sk, ktiles, grid, tile0;
 };
 
-SyrkPlan syrk_plan(int m, int k)
+// blk_lo/blk_hi restrict the product to the tile rows [blk_lo, blk_hi) (a rank's share of the distributed form); hi < 0 = all
+SyrkPlan syrk_plan(int m, int k, int blk_lo = 0, int blk_hi = -1)
 {
     SyrkPlan p;
     p.nb = (m + SY_BM - 1) / SY_BM;
     p.bme = (((m + p.nb - 1) / p.nb) + 7) & ~7;
-    p.ntiles = p.nb * (p.nb + 1) / 2;
+    if (blk_hi < 0 || blk_hi > p.nb) blk_hi = p.nb;
+    if (blk_lo < 0) blk_lo = 0;
+    if (blk_lo > blk_hi) blk_lo = blk_hi;
+    p.tile0 = blk_lo * (blk_lo + 1) / 2;
+    p.ntiles = blk_hi * (blk_hi + 1) / 2 - p.tile0;
     p.ktiles = (k + SY_BK - 1) / SY_BK;
     const int sms = sm_count();
     int best = 1;
@@ -87,7 +92,7 @@ SyrkPlan syrk_plan(int m, int k)
     }
     p.sk = best;
     const long long items = (long long)p.ntiles * p.sk;
-    p.grid = (int)(items < sms ? items : sms);
+    p.grid = (int)(items < sms ? (items > 0 ? items : 1) : sms);
     return p;
 }
 
@@ -121,7 +126,7 @@ __device__ __forceinline__ void syrk_ktile_nt(double (&acc)[4][4][2], const doub
 // E [m][ld] row-major, K contiguous (ld even, rows 16-byte aligned, columns k..ld-1 of the last k-tile readable and ZERO)
 __global__ void __launch_bounds__(SY_THREADS, 1)
 dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb, int bme, int ntiles, int sk, int ktiles,
-                       double* __restrict__ S, long long lds, int* __restrict__ flags)
+                       double* __restrict__ S, long long lds, int* __restrict__ flags, int tile0)
 {
     extern __shared__ __align__(16) double sy_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -133,10 +138,11 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
 
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int c = (int)(item / ntiles), t = (int)(item % ntiles);
-        int bi = (int)((sqrtf(8.f * (float)t + 1.f) - 1.f) * 0.5f);
-        while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-        while (bi * (bi + 1) / 2 > t) --bi;
-        const int bj = t - bi * (bi + 1) / 2;
+        const int tg = t + tile0;                               // position in the triangular enumeration of ALL tiles
+        int bi = (int)((sqrtf(8.f * (float)tg + 1.f) - 1.f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= tg) ++bi;
+        while (bi * (bi + 1) / 2 > tg) --bi;
+        const int bj = tg - bi * (bi + 1) / 2;
         const bool diag = bi == bj;
         const int row0 = bi * bme, col0 = bj * bme;
         const int kt0 = (int)((long long)ktiles * c / sk), kt1 = (int)((long long)ktiles * (c + 1) / sk);
@@ -612,8 +618,18 @@ VEL_API size_t vel_syrk_lower_sub_workspace(int32_t m, int32_t k)
     return vel_dense_syrk_workspace(m, k);
 }
 
-VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
-                               vel_stream_t stream)
+// the tile-row geometry the SYRK uses for an m x m product (the distributed form assigns whole tile rows to ranks)
+VEL_API int vel_syrk_tile_rows(int32_t m, int32_t* nb, int32_t* rows_per_block)
+{
+    VEL_CHECK_ARG(m > 0 && nb && rows_per_block, "vel_syrk_tile_rows: bad argument");
+    const SyrkPlan p = syrk_plan(m, SY_BK);
+    *nb = p.nb;
+    *rows_per_block = p.bme;
+    return VEL_OK;
+}
+
+VEL_API int vel_syrk_lower_sub_rows(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                                    int32_t blk_lo, int32_t blk_hi, vel_stream_t stream)
 {
     VEL_CHECK_ARG(E && S && work, "vel_syrk_lower_sub: NULL argument");
     VEL_CHECK_ARG(m > 0 && k > 0 && lds >= m, "vel_syrk_lower_sub: bad sizes m=%d k=%d lds=%lld", m, k, (long long)lds);
@@ -621,7 +637,8 @@ VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k
     VEL_CHECK_ARG(ld >= kpad && ld % 2 == 0 && ((size_t)E & 15) == 0,
                   "vel_syrk_lower_sub: E needs 16-byte aligned rows (ld even) padded with zeros to a multiple of %d columns (ld %lld < %lld)",
                   SY_BK, (long long)ld, kpad);
-    const SyrkPlan p = syrk_plan(m, k);
+    const SyrkPlan p = syrk_plan(m, k, blk_lo, blk_hi);
+    if (p.ntiles == 0) return VEL_OK;
     VEL_CHECK_ARG(work_bytes >= sizeof(int) * (size_t)p.ntiles, "vel_syrk_lower_sub: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     int* flags = (int*)work;
@@ -632,11 +649,17 @@ VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k
         attr_set = true;
     }
     long long ld_ = ld, lds_ = lds;
-    int m_ = m, nb = p.nb, bme = p.bme, ntiles = p.ntiles, sk = p.sk, ktiles = p.ktiles;
-    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags};
+    int m_ = m, nb = p.nb, bme = p.bme, ntiles = p.ntiles, sk = p.sk, ktiles = p.ktiles, tile0 = p.tile0;
+    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags, &tile0};
     // co-residency of the whole grid is what makes the turnstile wait safe: cooperative launch guarantees it (or fails)
     VEL_CUDA(cudaLaunchCooperativeKernel((void*)dsyrk_lower_sub_kernel, dim3(p.grid), dim3(SY_THREADS), args, SY_SMEM, st));
     return VEL_OK;
+}
+
+VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                               vel_stream_t stream)
+{
+    return vel_syrk_lower_sub_rows(E, ld, m, k, S, lds, work, work_bytes, 0, -1, stream);
 }
 
 #ifdef VEL_CHOL_TIMING

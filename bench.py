@@ -61,7 +61,7 @@ def workload_config():
                         "<=10 it, eps 0.1, fbt 1.0), fcnNLS_t per frame, fcnNvintercept over all frames, 10-iteration fcnNLS_batch "
                         "(nt=4096, nc=299)",
             "frames": NFRAMES, "height": H, "width": W, "tracks": NPTS, "plane_start_depth_m": Z_START_M, "speed_kmh": V_KMH,
-            "fps": FPS, "ba_iterations": BA_ITERS, "seed": SEED}
+            "fps": FPS, "ba_iterations": BA_ITERS, "seed": SEED, "sensor_noise_grey_levels": NOISE_AMPL}
 
 
 def measured_peaks():
@@ -72,13 +72,23 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def make_sequence(seed):
-    """frames uint8 [n,H,W], seeds p0 [NPTS,2] f32, planar points p3 [NPTS,3] f64 (frame-0 camera frame), frame times, depths."""
+NOISE_AMPL = 4         # sensor noise added to every rendered frame: uniform integers in [-4, 4] grey levels (sigma 2.6)
+
+
+def make_sequence(seed, noise_seed=None):
+    """frames uint8 [n,H,W], seeds p0 [NPTS,2] f32, planar points p3 [NPTS,3] f64 (frame-0 camera frame), frame times, depths.
+    The SCENE (plane texture, Harris seeds) comes from `seed`; `noise_seed` seeds the per-frame sensor noise, so that ranks
+    of a multi-GPU run see independent recordings ("passes") of the same scene -- the shared 3-D points the global bundle
+    adjustment of the C5 leg needs -- while the frames of every rank differ."""
     from velocity_b200 import synth
 
     K = synth.K_1080P
     frames, Z = synth.approach_sequence(NFRAMES, h=H, w=W, seed=seed, z_start=Z_START_M, v_kmh=V_KMH, dt=1 / FPS)
-    p0 = synth.approach_tracks(frames[0], NPTS, Z[0] / Z[-1])
+    p0 = synth.approach_tracks(frames[0], NPTS, Z[0] / Z[-1])      # seeds are detected on the noise-free frame 0
+    rng = np.random.default_rng(seed if noise_seed is None else noise_seed)
+    for i in range(NFRAMES):
+        nz = rng.integers(-NOISE_AMPL, NOISE_AMPL + 1, size=(H, W), dtype=np.int16)
+        frames[i] = np.clip(frames[i].astype(np.int16) + nz, 0, 255).astype(np.uint8)
     # vidExample.py:119 with the known plane pose (R = I, t = (0, 0, Z0)): p3 = image2world(p) @ R + t
     p3 = np.concatenate([(p0 - K[2, 0:2]) / K[0, 0] * Z[0], np.full((NPTS, 1), Z[0])], 1).astype(np.float64)
     times = (np.arange(NFRAMES) / FPS).astype(np.float32)
@@ -272,6 +282,66 @@ def bind_to_gpu_numa_node(local):
     return info
 
 
+def global_ba_leg(seq, K, rank, world, dev, iters):
+    """BASELINE configs[4] ("C5") shape: the frames of ALL ranks (300 per GPU) in ONE bundle adjustment over the shared 4096 points
+    -- cameras shard by rank, ONE all-reduce + ONE all-gather per LM iteration, tile rows of the reduced system to the owner,
+    owner-only Cholesky, broadcast (velocity_b200.NLS.BundleAdjuster(shard=True)).  The measurements are each
+    rank's own TRACKED observations; start values are rank 0's adjusted points and every rank's adjusted cameras."""
+    import torch
+    import torch.distributed as dist
+
+    from velocity_b200.NLS import BundleAdjuster
+
+    n = NFRAMES
+    alive = (seq.alive[n - 1] != 0).to(torch.int32)
+    dist.all_reduce(alive, op=dist.ReduceOp.MIN)                   # tracks that are full-length on every rank
+    idx = torch.nonzero(alive, as_tuple=False).flatten()
+    nsel = int(idx.numel())
+    nc_g = n * world - 1
+    z = torch.zeros((2, nc_g + 1, nsel), dtype=torch.float64, device=dev)
+    tr = seq.tracks[:, idx, :].to(torch.float64)
+    z[0, rank * n:(rank + 1) * n] = tr[..., 0]
+    z[1, rank * n:(rank + 1) * n] = tr[..., 1]
+    # start values: rank 0's bundle-adjusted points (same selection when every track survived everywhere), all ranks' cameras
+    own_idx, own_pw, own_cw = seq.points_ba()
+    full = torch.zeros((NPTS, 3), dtype=torch.float64, device=dev)
+    full[own_idx.long()] = own_pw
+    pw0 = full[idx].contiguous()
+    dist.broadcast(pw0, src=0)
+    cams = [torch.empty((n, 3), dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(cams, own_cw.contiguous())
+    cw0 = torch.cat(cams)[1:]                                       # camera 0 of rank 0 is the fixed one
+    x0 = torch.cat([pw0.flatten(), cw0.flatten(), torch.zeros(3 * nc_g, dtype=torch.float64, device=dev)])
+    ba = BundleAdjuster(K, z.flatten(), x0, nsel, nc_g, shard=True)
+    f_first, _ = ba.step()                                          # warm-up iteration (allocations, NCCL channels, lazy library loads)
+    ba.timing = {}
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    f_last = f_first
+    for _ in range(iters):
+        f_last, xr = ba.step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / iters], dtype=torch.float64, device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    stage = {k: v / iters for k, v in ba.stage_ms().items()}
+    coll = sum(v for k, v in stage.items() if k in ("exchange_allreduce_allgather", "rows_to_owner", "broadcast_delta_c"))
+    # bytes on the wire per iteration (algorithmic): all-reduce buffer, all-gather of W, tile rows of S to the owner, delta_c
+    n6 = 6 * nc_g
+    bytes_it = {"all_reduce": int(ba.small.numel() * 8), "all_gather_W": int(ba.W_ext.numel() * 8),
+                "rows_to_owner": int(8 * sum((hi - lo) * n6 for r, (lo, hi) in enumerate(ba.row_ranges) if r != 0)), "broadcast": n6 * 8}
+    cw = ba.x[3 * nsel:3 * nsel + 3 * nc_g].view(nc_g, 3)
+    mine = torch.cat([torch.zeros((1, 3), dtype=torch.float64, device=dev), cw])[rank * n:(rank + 1) * n]
+    sp = (mine[1:] - mine[:-1]).norm(dim=1) * FPS * 3.6
+    return {"workload": "C5 shape: %d cameras (%d frames per GPU x %d GPUs), %d shared points, nx = %d" % (nc_g + 1, n, world, nsel, 3 * nsel + 6 * nc_g),
+            "iterations_timed": iters, "ms_per_iteration": float(ms.item()), "stage_ms_rank0": stage,
+            "collective_ms_per_iteration_rank0": coll, "collective_share_rank0": coll / max(sum(stage.values()), 1e-9),
+            "bytes_per_iteration": bytes_it, "rms_px_first_last": [f_first, f_last],
+            "speed_kmh_rank0_cameras_mean": float(sp.mean().item()), "solver": os.environ.get("VEL_BA_SOLVER", "vendor")}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -290,8 +360,9 @@ def run_ours(args):
     from velocity_b200.lk import FrameBatch, lk_params, track_pairs
     from velocity_b200.sfm import SfmSequence
 
-    # every rank owns its own 300-frame sequence (weak scaling; frames shard naturally); shards differ by seed
-    K, frames_np, p0_np, p3_np, times_np, Z = make_sequence(SEED + rank)
+    # every rank owns its own 300-frame recording of the scene (weak scaling; frames shard naturally);
+    # the recordings differ by their sensor-noise seed
+    K, frames_np, p0_np, p3_np, times_np, Z = make_sequence(SEED, SEED + rank)
     frames_host = torch.from_numpy(frames_np).pin_memory()
     p0_host = torch.from_numpy(p0_np).pin_memory()
     p3_host = torch.from_numpy(p3_np).pin_memory()
@@ -373,6 +444,10 @@ def run_ours(args):
     k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     c2_valid = float(c2[1].float().mean().item())
 
+    gba = None
+    if world > 1:
+        gba = global_ba_leg(seq, K, rank, world, dev, args.global_ba_iters)
+
     times = torch.tensor([total_ms, e2e_ms, k1_ms, k2_ms] + [stage.get(k, 0.0) for k in ("track", "pose", "triangulate", "bundle")],
                          dtype=torch.float64, device=dev)
     if world > 1:
@@ -439,6 +514,8 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
         }
+        if gba is not None:
+            line["global_ba"] = gba
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -451,6 +528,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chunk", type=int, default=25, help="frames per H2D/compute pipeline chunk of the e2e path")
+    ap.add_argument("--global-ba-iters", type=int, default=3, help="timed LM iterations of the multi-GPU global BA leg (N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":

@@ -33,7 +33,8 @@ def _worker(rank, world, port, out):
         V, U, W, gg, cost = S.ba_blocks(g["K"], x, z, nt, nc, first, count)
         iu3, iu6 = np.triu_indices(3), np.triu_indices(6)
         small, tc, tV, tg, tU = small_buffer(nt, nc, "cpu")
-        tW = torch.zeros((6 * per * world, 3 * nt), dtype=torch.float64)
+        tW_ext = torch.zeros((6 * per * world, 3 * nt), dtype=torch.float64)
+        tW = tW_ext[6:]
         lo, hi = param_rows(first, count)
         tV.copy_(torch.from_numpy(np.ascontiguousarray(V[:, iu3[0], iu3[1]])))
         tc[0] = cost
@@ -42,7 +43,7 @@ def _worker(rank, world, port, out):
         tg[3 * nt + 3 * lo:3 * nt + 3 * hi] = torch.from_numpy(gg[3 * nt + 3 * lo:3 * nt + 3 * hi].copy())
         tg[3 * nt + 3 * nc + 3 * lo:3 * nt + 3 * nc + 3 * hi] = torch.from_numpy(gg[3 * nt + 3 * nc + 3 * lo:3 * nt + 3 * nc + 3 * hi].copy())
         tW[6 * lo:6 * hi] = torch.from_numpy(np.ascontiguousarray(W.transpose(0, 2, 1, 3).reshape(6 * nc, 3 * nt)[6 * lo:6 * hi]))
-        exchange_blocks(small, tW, per, rank, world)
+        exchange_blocks(small, tW_ext, per, rank, world)
         Vf, Uf, Wf, gf, cf = S.ba_blocks(g["K"], x, z, nt, nc)
         ok = (np.allclose(tV.numpy(), Vf[:, iu3[0], iu3[1]], rtol=1e-12, atol=1e-9)
               and np.array_equal(tU.numpy()[:nc], Uf[:, iu6[0], iu6[1]])                      # gathered through the sum: x + 0 is exact
@@ -74,8 +75,8 @@ def test_camera_slices_cover_all_cameras():
             rows = [param_rows(f, c) for f, c in sl]
             covered = sorted(r for lo, hi in rows for r in range(lo, hi))
             assert covered == list(range(nc))
-            for r, (lo, hi) in enumerate(rows):                 # every rank's rows sit inside its equally sized gather block
-                assert hi <= lo or (lo >= r * per and hi <= (r + 1) * per)
+            for r, (f, c) in enumerate(sl):                     # every rank's cameras sit inside its equally sized gather block
+                assert c == 0 or (f >= r * per and f + c <= (r + 1) * per)
     for nb in (1, 2, 15, 113):
         for world in (1, 2, 4, 8):
             rr = tile_row_ranges(nb, world)

@@ -106,7 +106,9 @@ class BundleAdjuster:
             self.rank, self.world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
         self.per, self.slices = camera_slices(nc, self.world)
         self.small, self.cost, self.V, self.g, self.U = small_buffer(nt, nc, dev)
-        self.W = torch.zeros((max(6 * self.per * self.world, 1), 3 * nt), dtype=torch.float64, device=dev)
+        # one 6-row block per camera 0..per*world-1 (camera 0's block is padding); the solver's W starts at camera 1
+        self.W_ext = torch.zeros((6 * self.per * self.world, 3 * nt), dtype=torch.float64, device=dev)
+        self.W = self.W_ext[6:]
         self.rms_delta = torch.zeros((1,), dtype=torch.float64, device=dev)
         L = _lib.lib()
         nbytes = int(L.vel_ba_solve_workspace(nt, nc))
@@ -130,32 +132,57 @@ class BundleAdjuster:
         self.z = _dev64(z)
         self.x.copy_(_dev64(x0))
 
+    def _t(self, name):
+        """stage marks for bench.py: self.timing = {} switches them on (CUDA events on the launching stream)"""
+        if self.timing is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.timing.setdefault("_marks", []).append((name, ev))
+
+    def stage_ms(self):
+        """Sum per stage name over the recorded marks (call after a synchronise)."""
+        out = {}
+        marks = self.timing.get("_marks", []) if self.timing else []
+        for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+            if name != "begin":
+                out[name] = out.get(name, 0.0) + e0.elapsed_time(e1)
+        return out
+
     def accumulate(self):
         L = _lib.lib()
         first, count = self.slices[self.rank]
+        self._t("begin")
         if self.world > 1:
             self.small.zero_()               # foreign cameras' U / g_c entries must be exact zeros for the gathering all-reduce
         _lib.check(L.vel_ba_accumulate(ptr(self.K), ptr(self.x), ptr(self.z), self.nt, self.nc, first, count, ptr(self.V),
                                        ptr(self.U), ptr(self.W), ptr(self.g), ptr(self.cost), stream_ptr()), "vel_ba_accumulate")
+        self._t("accumulate")
         if self.world > 1:
-            exchange_blocks(self.small, self.W, self.per, self.rank, self.world, self.group)
+            exchange_blocks(self.small, self.W_ext, self.per, self.rank, self.world, self.group)
+            self._t("exchange_allreduce_allgather")
 
     def solve(self):
         L = _lib.lib()
         if self.world == 1:
             _lib.check(L.vel_ba_solve(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, ptr(self.x),
                                       ptr(self.rms_delta), ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_solve")
+            self._t("solve")
             return
         lo, hi = self.blocks[self.rank]
         _lib.check(L.vel_ba_reduce(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, lo, hi, ptr(self.work),
                                    self.work.numel(), stream_ptr()), "vel_ba_reduce")
+        self._t("reduce_tile_rows")
         gather_rows_to_owner(self.S, self.row_ranges, self.rank, 0, self.group)
+        self._t("rows_to_owner")
         if self.rank == 0:
             _lib.check(L.vel_ba_factor(self.nt, self.nc, ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_factor")
+        self._t("factor_on_owner")
         torch.distributed.broadcast(self.rhs, src=0 if self.group is None else torch.distributed.get_global_rank(self.group, 0),
                                     group=self.group)
+        self._t("broadcast_delta_c")
         _lib.check(L.vel_ba_update(ptr(self.W), self.nt, self.nc, ptr(self.x), ptr(self.rms_delta), ptr(self.work), self.work.numel(),
                                    stream_ptr()), "vel_ba_update")
+        self._t("update")
 
     def step(self):
         """One LM iteration.  Returns (f = rms(z - zhat) before the update, rms(delta))."""

@@ -5,8 +5,9 @@ Per LM iteration there are exactly TWO data-path collectives before the solve:
   1. ONE all-reduce (sum) of the "small" buffer  [cost | V (nt x 6) | g (3nt + 6nc) | U (nc x 21)]:
      V, the point part of g and cost are PARTIAL sums over each rank's cameras; the camera entries (U rows, camera part of g)
      are non-zero on their owner only and zero elsewhere, so the same sum also gathers them (x + 0 is exact).
-  2. ONE all_gather_into_tensor of the cross blocks W [6 * per * world][3nt]: every rank owns `per` consecutive parameterised
-     cameras = one contiguous, equally sized row block (the last block is padded with unused rows), gathered in place.
+  2. ONE all_gather_into_tensor of the cross blocks: the buffer W_ext [6 * per * world][3nt] has one 6-row block per CAMERA
+     (camera 0's block is unused padding, so that every rank's `per` consecutive cameras are one contiguous, equally sized
+     row block); the matrix the solver sees is W = W_ext[6:] (camera c >= 1 owns rows 6(c-1)..6c-1).  Gathered in place.
 
 and two small ones inside the solve (velocity_b200.NLS.BundleAdjuster.solve): the ranks' tile rows of the reduced camera system
 S go to the owner (rank 0) point-to-point, the owner factors S once and broadcasts delta_c -- S is not factored on every rank.
@@ -17,13 +18,14 @@ import torch.distributed as dist
 
 
 def camera_slices(nc, world):
-    """(per, slices): `per` = parameterised cameras per rank; slices[r] = (first, count) over the camera indices 0..nc of
-    vel_ba_accumulate.  Camera 0 (fixed, no parameters, utils/NLS.py:207-208) goes to rank 0 on top of its `per` cameras."""
-    per = max(1, -(-nc // world))
+    """(per, slices): cameras 0..nc split into `world` blocks of `per` = ceil((nc+1)/world) consecutive cameras
+    (frames shard naturally: a rank owns the cameras of its own frame block); slices[r] = (first, count) in the camera
+    indexing of vel_ba_accumulate.  Camera 0 is the fixed one (no parameters, utils/NLS.py:207-208)."""
+    per = max(1, -(-(nc + 1) // world))
     out = []
     for r in range(world):
-        lo, hi = min(nc, r * per), min(nc, (r + 1) * per)          # parameterised cameras lo..hi-1 (camera index = lo+1..hi)
-        out.append((0, hi + 1) if r == 0 else (lo + 1, hi - lo))
+        lo, hi = min(nc + 1, r * per), min(nc + 1, (r + 1) * per)
+        out.append((lo, hi - lo))
     return per, out
 
 
@@ -45,12 +47,12 @@ def small_buffer(nt, nc, device, dtype=torch.float64):
     return buf, buf[0:1], V, g, U
 
 
-def exchange_blocks(small, W, per, rank, world, group=None):
+def exchange_blocks(small, W_ext, per, rank, world, group=None):
     """The two collectives.  `small` holds this rank's partial sums / own camera entries (zeros for foreign cameras);
-    W [6*per*world, 3nt] holds this rank's rows in its own row block."""
+    W_ext [6*per*world, 3nt] holds this rank's cameras in its own row block."""
     dist.all_reduce(small, group=group)
     rows = 6 * per
-    dist.all_gather_into_tensor(W, W[rank * rows:(rank + 1) * rows], group=group)
+    dist.all_gather_into_tensor(W_ext, W_ext[rank * rows:(rank + 1) * rows], group=group)
 
 
 def tile_row_ranges(nb, world):

@@ -136,17 +136,21 @@ def test_c3_full_size_speed_within_one_percent():
 
 
 def test_in_kernel_frame_loop_equals_per_pair_launches(monkeypatch):
-    """vel_klt_sequence has two forms: the 15x15 kernel with the frame loop inside (one launch per frame run) and one K2
-    launch per pair (any window; VEL_LK_SEQ=pairs forces it).  Same tracks, same masks, same errors, bit for bit."""
+    """vel_klt_sequence has three forms: the 15x15 sequence kernel (frame loop inside, ONE template per frame serving the
+    backward pass of pair j-1 and the forward pass of pair j), the batch kernel with the frame loop inside (VEL_LK_SEQ=twice)
+    and one K2 launch per pair (any window; VEL_LK_SEQ=pairs).  Same tracks, same masks, same errors, bit for bit."""
     K, frames, p0, p3, times = scene_with_dying_tracks()
     a, _ = run_gpu(K, frames, p0, p3, times)
+    for mode in ("pairs", "twice"):      # one K2 launch per pair / frame loop inside the batch kernel (template built per pass)
+        monkeypatch.setenv("VEL_LK_SEQ", mode)
+        b, _ = run_gpu(K, frames, p0, p3, times)
+        assert torch.equal(a.alive, b.alive), mode
+        al = a.alive != 0
+        assert torch.equal(a.tracks[al], b.tracks[al]), mode
+        assert torch.equal(a.err[al[:-1]], b.err[al[:-1]]), mode        # err[k] belongs to pair k, defined where the track was alive in frame k
+        assert (a.tracks[~al] == -1.0e5).all() and (b.tracks[~al] == -1.0e5).all()
+        assert torch.equal(a.S.nan_to_num(), b.S.nan_to_num()), mode
     monkeypatch.setenv("VEL_LK_SEQ", "pairs")
-    b, _ = run_gpu(K, frames, p0, p3, times)
-    assert torch.equal(a.alive, b.alive)
-    al = a.alive != 0
-    assert torch.equal(a.tracks[al], b.tracks[al]) and torch.equal(a.err[al[1:]], b.err[al[1:]])
-    assert (a.tracks[~al] == -1.0e5).all() and (b.tracks[~al] == -1.0e5).all()
-    assert torch.equal(a.S.nan_to_num(), b.S.nan_to_num())
     # a 21x21 window takes the per-pair path by construction and must agree with the oracle too
     from velocity_b200.sfm import SfmSequence
 

@@ -673,6 +673,7 @@ __device__ __forceinline__ int dp2a_hi(int w, unsigned px, int acc)
 __device__ __forceinline__ unsigned ldg_u32(const uint8_t* p) { return __ldg(reinterpret_cast<const unsigned*>(p)); }
 
 #include "lk_w15h.cuh"
+#include "lk_w15s.cuh"
 
 // =====================================================================================================
 // Column-streaming path for mid-size windows (16 <= win_w <= COLS-1, win_h <= 63; the reference's
@@ -1105,9 +1106,15 @@ int vel_lk_sequence_w15h(const uint8_t* frames, int64_t frame_stride, int32_t pi
     A.fbt = params->fb_threshold;
     A.force_bytes = 0;
     A.seq_pairs = nframes - 1; A.alive = alive;
-    constexpr int SEQ_WARPS = 2;                          // 4 points per CTA: 1024 CTAs for 4096 tracks, 6.9 per SM
-    dim3 grid((npts + 2 * SEQ_WARPS - 1) / (2 * SEQ_WARPS), 1);
-    lk_track_w15h_kernel<true><<<grid, 32 * SEQ_WARPS, 0, (cudaStream_t)stream>>>(A);
-    VEL_LAUNCH_CHECK("lk_track_w15h_kernel<seq>");
+    if (seq && strcmp(seq, "twice") == 0) {               // cross-check switch: frame loop inside the batch kernel, template built per pass
+        constexpr int SEQ_WARPS = 2;
+        dim3 grid((npts + 2 * SEQ_WARPS - 1) / (2 * SEQ_WARPS), 1);
+        lk_track_w15h_kernel<true><<<grid, 32 * SEQ_WARPS, 0, (cudaStream_t)stream>>>(A);
+        VEL_LAUNCH_CHECK("lk_track_w15h_kernel<seq>");
+        return 1;
+    }
+    dim3 grid((npts + 2 * WS_WARPS - 1) / (2 * WS_WARPS), 1);
+    lk_seq_w15h_kernel<<<grid, 32 * WS_WARPS, 0, (cudaStream_t)stream>>>(A);
+    VEL_LAUNCH_CHECK("lk_seq_w15h_kernel");
     return 1;
 }

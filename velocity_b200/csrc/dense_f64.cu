@@ -246,11 +246,22 @@ constexpr size_t CH_SMEM = sizeof(double) * (CH_NB * CH_LD + 2 * CH_NB * CH_LDT)
 // (i) one warp factors the 8x8 diagonal sub-block in registers, (ii) a thread per row solves the 8-column sub-panel below it,
 // (iii) everyone applies the rank-8 update to the rest of the block.  ok is cleared when a pivot is not positive;
 // rdiag receives the reciprocals of the diagonal of L.
+#ifdef VEL_CHOL_TIMING
+__device__ unsigned long long g_cb_t[4];
+#define CB_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long now_ = clock64(); g_cb_t[k] += now_ - cb_last; cb_last = now_; } } while (0)
+#else
+#define CB_T(k)
+#endif
+
 __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
 {
     const int tid = threadIdx.x;
+#ifdef VEL_CHOL_TIMING
+    long long cb_last = clock64();
+#endif
     for (int jb = 0; jb < w; jb += 8) {
         const int wb = min(8, w - jb);
+        CB_T(3);
         if (tid < 32) {
             // lanes 0..7 own the rows of the sub-block
             const int r = tid & 7;
@@ -280,6 +291,7 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
             }
         }
         __syncthreads();
+        CB_T(0);
         // (ii) rows below the sub-block: x L_sub^T = a  (forward substitution over the 8 columns)
         const int below = w - jb - wb;
         if (tid < below) {
@@ -301,6 +313,7 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
                 if (c2 < wb) sD[r][jb + c2] = x[c2];
         }
         __syncthreads();
+        CB_T(1);
         // (iii) rank-wb update of the trailing lower part: thread = (row group, column)
         {
             const int ci = tid & 63, rg = tid >> 6;
@@ -321,6 +334,7 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
             }
         }
         __syncthreads();
+        CB_T(2);
     }
 }
 
@@ -667,7 +681,8 @@ VEL_API void vel_chol_timing(unsigned long long* out8, int reset)
 {
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out8, g_chol_t, sizeof(unsigned long long) * 8);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_t, z, sizeof(z)); }
+    cudaMemcpyFromSymbol(out8 + 8, g_cb_t, sizeof(unsigned long long) * 4);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_t, z, sizeof(z)); cudaMemcpyToSymbol(g_cb_t, z, sizeof(unsigned long long) * 4); }
 }
 #endif
 

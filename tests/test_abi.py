@@ -50,3 +50,16 @@ def test_product_never_imports_the_oracle():
                 with open(os.path.join(dirpath, fn)) as f:
                     txt = f.read()
                 assert "from oracle" not in txt and "import oracle" not in txt, fn
+
+
+def test_shipped_library_links_no_vendor_blas_or_solver():
+    """K8 is hand-written (csrc/dense_f64.cu): the default build must not depend on cuBLAS / cuSOLVER."""
+    import subprocess
+
+    from velocity_b200 import _lib, build
+
+    build.build()
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout.lower()
+    sym = subprocess.run(["nm", "-D", "--undefined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout.lower()
+    for name in ("cublas", "cusolver", "cusparse", "cufft"):
+        assert name not in out and name not in sym, name

@@ -111,7 +111,7 @@ def test_failed_cholesky_poisons_rms_delta(monkeypatch):
     from velocity_b200 import NLS, _lib as L
     from velocity_b200.device import ptr, stream_ptr
 
-    for mode in ("native", "vendor"):
+    for mode in ("native", "vendor"):      # "vendor" only differs in a build with --vendor-solver (the A/B build)
         monkeypatch.setenv("VEL_BA_SOLVER", mode)
         g = golden("ba_small")
         from oracle import sfm_oracle as S

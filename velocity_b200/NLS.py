@@ -91,7 +91,7 @@ class BundleAdjuster:
     each rank then forms its tile rows of the reduced camera system, the owner (rank 0) factors it once and broadcasts
     delta_c, and every rank applies the same update."""
 
-    launches_per_step = 10   # this library's kernels per LM iteration (K7: 5, K8: 5)
+    launches_per_step = 15   # this library's kernels per LM iteration (K7: 5; K8: prep, scale, init, SYRK, 2+1 GEMV, Cholesky, update, rms)
 
     def __init__(self, K, z, x0, nt, nc, shard=False, group=None):
         require_cuda()

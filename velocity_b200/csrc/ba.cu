@@ -18,8 +18,10 @@
 // Cameras are indexed 0..nc (0 = the fixed one); a rank owning cameras [cam_first, cam_first +
 // cam_count) fills its rows of U/W/g_c and PARTIAL V/g_p/cost over its cameras (all-reduce across
 // ranks).
+#ifdef VEL_WITH_VENDOR_SOLVER   // optional A/B build (python -m velocity_b200.build --vendor-solver): cuBLAS / cuSOLVER behind VEL_BA_SOLVER=vendor
 #include <cublas_v2.h>
 #include <cusolverDn.h>
+#endif
 #include <stdlib.h>
 #include <string.h>
 
@@ -372,13 +374,18 @@ __global__ void ba_rms_finalize_kernel(const double* __restrict__ part, int n, l
     }
 }
 
-// VEL_BA_SOLVER=native: FP64 tensor-core SYRK + cooperative Cholesky of this library (csrc/dense_f64.cu), no vendor library on
-// the path.  Default ("vendor"): cuBLAS DSYRK / DGEMV + cuSOLVER DPOTRF / DPOTRS, which today are faster on the Cholesky's
-// latency chain (measured numbers in DESIGN.md).
+// The dense part of the solve (K8) runs on this library's own kernels (csrc/dense_f64.cu: FP64 tensor-core SYRK, task-graph
+// Cholesky, hand-written GEMVs); the shipped library links no vendor BLAS / solver.  A build with -DVEL_WITH_VENDOR_SOLVER
+// (python -m velocity_b200.build --vendor-solver) additionally compiles the cuBLAS DSYRK / cuSOLVER DPOTRF path of round 1,
+// selected at run time by VEL_BA_SOLVER=vendor, for A/B measurements (DESIGN.md has the numbers).
 bool native_solver()
 {
+#ifdef VEL_WITH_VENDOR_SOLVER
     const char* e = getenv("VEL_BA_SOLVER");
-    return e && strcmp(e, "native") == 0;
+    return !(e && strcmp(e, "vendor") == 0);
+#else
+    return true;
+#endif
 }
 
 constexpr int GEMV_ROW_CHUNKS = 8;
@@ -433,20 +440,28 @@ __global__ void ba_zero_pad_kernel(double* __restrict__ Wp, long long ld, int nr
     Wp[(idx / pad) * ld + n3 + idx % pad] = 0.0;
 }
 
+#ifdef VEL_WITH_VENDOR_SOLVER
 struct Handles {
     cublasHandle_t blas = nullptr;
     cusolverDnHandle_t solver = nullptr;
+    int device = -1;
 };
 
+// one pair of handles per host thread AND device (a handle is bound to the device it was created on)
 Handles* handles()
 {
-    static thread_local Handles h;
-    if (!h.blas) {
-        if (cublasCreate(&h.blas) != CUBLAS_STATUS_SUCCESS) { h.blas = nullptr; return nullptr; }
-        if (cusolverDnCreate(&h.solver) != CUSOLVER_STATUS_SUCCESS) { h.solver = nullptr; return nullptr; }
+    static thread_local Handles h[16];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 16) return nullptr;
+    Handles& hd = h[dev];
+    if (!hd.blas || !hd.solver) {
+        if (!hd.blas && cublasCreate(&hd.blas) != CUBLAS_STATUS_SUCCESS) { hd.blas = nullptr; return nullptr; }
+        if (!hd.solver && cusolverDnCreate(&hd.solver) != CUSOLVER_STATUS_SUCCESS) { hd.solver = nullptr; return nullptr; }
+        hd.device = dev;
     }
-    return &h;
+    return &hd;
 }
+#endif
 
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
@@ -472,6 +487,7 @@ bool solve_layout(int nt, int nc, SolveLayout* L, bool query_potrf)
     L->off_flags = o; o += vel_dense_syrk_workspace((int)(n6 > 0 ? n6 : 1), (int)(n3 > 0 ? n3 : 1));
     L->off_tpart = o; o += align256(sizeof(double) * GEMV_ROW_CHUNKS * n3);
     L->lwork = 0;
+#ifdef VEL_WITH_VENDOR_SOLVER
     if (query_potrf && nc > 0 && !native_solver()) {
         Handles* h = handles();
         if (!h) return false;
@@ -480,6 +496,9 @@ bool solve_layout(int nt, int nc, SolveLayout* L, bool query_potrf)
             return false;
         L->lwork = lwork;
     }
+#else
+    (void)query_potrf;
+#endif
     L->off_potrf = o; o += align256(sizeof(double) * (size_t)(L->lwork > 0 ? L->lwork : 1));
     L->total = o;
     return true;
@@ -591,6 +610,7 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
         const int rc = dense_solve_native(W, Wp, (long long)L.ldw, n6, n3, S, y, rhs, t, (double*)(wb + L.off_tpart), wb + L.off_flags,
                                           L.off_tpart - L.off_flags, info, st);
         if (rc != VEL_OK) return rc;
+#ifdef VEL_WITH_VENDOR_SOLVER
     } else if (nc > 0) {
         Handles* h = handles();
         VEL_CHECK_ARG(h != nullptr, "vel_ba_solve: cuBLAS/cuSOLVER handles unavailable");
@@ -625,6 +645,7 @@ VEL_API int vel_ba_solve(const double* V, const double* U, const double* W, cons
             vel_set_error("vel_ba_solve: cublasDgemv failed");
             return VEL_ERR_CUDA;
         }
+#endif
     } else {
         VEL_CUDA(cudaMemsetAsync(t, 0, sizeof(double) * n3, st));
     }
@@ -704,6 +725,7 @@ VEL_API int vel_ba_factor(int32_t nt, int32_t nc, void* work, size_t work_bytes,
     int* info = (int*)(wb + L.off_info);
     const int n6 = 6 * nc;
     if (native_solver()) return vel_spd_solve(S, n6, n6, rhs, info, stream);
+#ifdef VEL_WITH_VENDOR_SOLVER
     Handles* h = handles();
     VEL_CHECK_ARG(h != nullptr, "vel_ba_factor: cuSOLVER handle unavailable");
     cusolverDnSetStream(h->solver, st);
@@ -713,6 +735,9 @@ VEL_API int vel_ba_factor(int32_t nt, int32_t nc, void* work, size_t work_bytes,
         vel_set_error("vel_ba_factor: cuSOLVER Cholesky failed");
         return VEL_ERR_CUDA;
     }
+#else
+    (void)st;
+#endif
     return VEL_OK;
 }
 
@@ -1036,13 +1061,15 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
     SolveLayout L;
     VEL_CHECK_ARG(solve_layout(nt, nc_equiv, &L, false), "vel_ba2_solve: layout failed");
     const bool native = native_solver();
+    int lwork = 0;
+#ifdef VEL_WITH_VENDOR_SOLVER
     Handles* h = native ? nullptr : handles();
     VEL_CHECK_ARG(native || h != nullptr, "vel_ba2_solve: cuBLAS/cuSOLVER handles unavailable");
-    int lwork = 0;
     if (!native && cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, nq, nullptr, nq, &lwork) != CUSOLVER_STATUS_SUCCESS) {
         vel_set_error("vel_ba2_solve: cusolverDnDpotrf_bufferSize failed");
         return VEL_ERR_CUDA;
     }
+#endif
     const size_t need = L.off_potrf + align256(sizeof(double) * (size_t)(lwork > 0 ? lwork : 1));
     VEL_CHECK_ARG(work_bytes >= need, "vel_ba2_solve: workspace %zu B < required %zu B", work_bytes, need);
     cudaStream_t st = (cudaStream_t)stream;
@@ -1085,6 +1112,7 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
         VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
         return VEL_OK;
     }
+#ifdef VEL_WITH_VENDOR_SOLVER
     cublasSetStream(h->blas, st);
     cusolverDnSetStream(h->solver, st);
     cublasSetPointerMode(h->blas, CUBLAS_POINTER_MODE_HOST);
@@ -1114,5 +1142,6 @@ VEL_API int vel_ba2_solve(const double* V, const double* G, const double* W, con
     VEL_LAUNCH_CHECK("ba2_update_kernel");
     ba_rms_finalize_kernel<<<1, 32, 0, st>>>(part, ublocks, (long long)n3 + nq, rms_delta, info);
     VEL_LAUNCH_CHECK("ba_rms_finalize_kernel");
+#endif
     return VEL_OK;
 }

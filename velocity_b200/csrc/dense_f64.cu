@@ -20,6 +20,8 @@
 // grid barrier, then the trailing matrix is updated tile by tile with DMMA, grid barrier.  The right-hand side is row n of
 // the matrix, so y = L^-1 b falls out of the same sweeps; the backward substitution runs in the same kernel.
 #include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -51,6 +53,32 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// mbarrier helpers (shared::cta): the k-tile ring of the SYRK is synchronised per stage, never CTA-wide
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+// arrive on the barrier when all cp.async of this thread issued so far have landed (does not change the expected count)
+__device__ __forceinline__ void cp_async_mbar_arrive(unsigned long long* bar)
+{
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
 
 __device__ __forceinline__ int ld_acquire(const int* p)
 {
@@ -91,6 +119,10 @@ SyrkPlan syrk_plan(int m, int k, int blk_lo = 0, int blk_hi = -1)
         if (cost < best_cost - 1e-9) { best_cost = cost; best = sk; }
     }
     p.sk = best;
+    if (const char* e = getenv("VEL_SYRK_SK")) {          // tuning / experiment override
+        const int v = atoi(e);
+        if (v >= 1 && v <= p.ktiles) p.sk = v;
+    }
     const long long items = (long long)p.ntiles * p.sk;
     p.grid = (int)(items < sms ? (items > 0 ? items : 1) : sms);
     return p;
@@ -135,6 +167,12 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
     const int mt_cnt = max(0, min(4, (bme - wr * 32 + 7) >> 3));
     const int nt_cnt = max(0, min(4, (bme - wc * 32 + 7) >> 3));
     const long long nitems = (long long)ntiles * sk;
+    __shared__ unsigned long long full_bar[SY_STAGES], empty_bar[SY_STAGES];
+    if (tid == 0) {
+        for (int s2 = 0; s2 < SY_STAGES; ++s2) { mbar_init(&full_bar[s2], SY_THREADS); mbar_init(&empty_bar[s2], SY_THREADS / 32); }
+    }
+    __syncthreads();
+    long long gtile = 0;                                         // k-tiles consumed so far by this CTA (all items)
 
     for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
         const int c = (int)(item / ntiles), t = (int)(item % ntiles);
@@ -177,21 +215,25 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
             }
         };
 
-        // prologue
+        // ---- k-tile ring without a CTA-wide barrier: full[slot] collects the 512 "my copies have landed" arrivals of a tile,
+        //      empty[slot] the 16 "this warp is done reading" arrivals; `gtile` numbers the tiles over the CTA's whole life,
+        //      so slots and mbarrier phases simply continue from item to item ------------------------------------------------
+        auto issue_tile = [&](int kt, long long gt) {
+            const int slot = (int)(gt % SY_STAGES);
+            const unsigned use = (unsigned)(gt / SY_STAGES);
+            mbar_wait(&empty_bar[slot], (use & 1u) ^ 1u);           // everybody finished the previous tenant of the slot (free at first use)
+            issue(kt, slot);
+            cp_async_mbar_arrive(&full_bar[slot]);
+        };
 #pragma unroll
-        for (int s = 0; s < SY_STAGES - 1; ++s) {
-            if (kt0 + s < kt1) issue(kt0 + s, s);
-            cp_async_commit();
-        }
+        for (int s2 = 0; s2 < SY_STAGES - 1; ++s2)
+            if (kt0 + s2 < kt1) issue_tile(kt0 + s2, gtile + s2);
         for (int kt = kt0; kt < kt1; ++kt) {
-            const int stage = (kt - kt0) % SY_STAGES;
-            cp_async_wait<SY_STAGES - 2>();
-            __syncthreads();                                    // tile kt landed for everyone; everyone is done with tile kt-1's slot
-            const int nk = kt + SY_STAGES - 1;
-            if (nk < kt1) issue(nk, (nk - kt0) % SY_STAGES);
-            cp_async_commit();
+            const long long gt = gtile + (kt - kt0);
+            const int slot = (int)(gt % SY_STAGES);
+            mbar_wait(&full_bar[slot], (unsigned)(gt / SY_STAGES) & 1u);
             if (!skip_warp) {
-                const double* sA = sy_smem + stage * SY_STAGE_DOUBLES;
+                const double* sA = sy_smem + slot * SY_STAGE_DOUBLES;
                 const double* sB = diag ? sA : sA + SY_BM * SY_LDS;
                 const double* pa = sA + (wr * 32 + g) * SY_LDS + t4;
                 const double* pb = sB + (wc * 32 + g) * SY_LDS + t4;
@@ -202,9 +244,13 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
                 else if (mt_cnt == 2) syrk_ktile_nt<2>(acc, pa, pb, nt_cnt);
                 else if (mt_cnt == 1) syrk_ktile_nt<1>(acc, pa, pb, nt_cnt);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[slot]);
+            // refill the slot of tile kt-1: every warp has had this whole k-tile to leave it, so the wait inside rarely blocks
+            const int nk = kt + SY_STAGES - 1;
+            if (nk < kt1) issue_tile(nk, gt + SY_STAGES - 1);
         }
-        cp_async_wait<0>();
-        __syncthreads();                                        // the ring is free for the next item
+        gtile += kt1 - kt0;
 
         // turnstile: the partial products of a tile are subtracted from S in chunk order
         if (c > 0) {
@@ -241,6 +287,8 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
 constexpr int CH_NB = 64, CH_NBO = 256, CH_THREADS = 512, CH_LD = CH_NB + 1, CH_LDT = CH_NB + 4;
 // diagonal block (stride 65: conflict-free column walks) + two DMMA operand tiles (stride 68: conflict-free fragment loads)
 constexpr size_t CH_SMEM = sizeof(double) * (CH_NB * CH_LD + 2 * CH_NB * CH_LDT);      // 102,912 B
+constexpr int CH_MAXOWN = 2048;                                                        // own-tile list of the task-graph form
+constexpr size_t CH_DAG_SMEM = sizeof(double) * (CH_NB * CH_LD + 3 * CH_NB * CH_LDT);  // + the panel's inverse diagonal tile
 
 // 64x64 (w x w) lower Cholesky of sD in place, all CH_THREADS threads of the CTA; 8-column blocked:
 // (i) one warp factors the 8x8 diagonal sub-block in registers, (ii) a thread per row solves the 8-column sub-panel below it,
@@ -322,14 +370,19 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
                 double lc[8];
 #pragma unroll
                 for (int c2 = 0; c2 < 8; ++c2) lc[c2] = c2 < wb ? sD[cidx][jb + c2] : 0.0;
-                for (int ri = rg; ri < below; ri += CH_THREADS / 64) {
-                    if (ci <= ri) {
-                        const int r = jb + wb + ri;
-                        double s2 = sD[r][cidx];
+                constexpr int RS = CH_THREADS / 64;
+                for (int ri = rg; ri < below; ri += 2 * RS) {      // two rows in flight, two partial sums each: the 8-term update is a
+                    const int ri2 = ri + RS;                       // latency chain otherwise
+                    const bool on1 = ci <= ri, on2 = ri2 < below && ci <= ri2;
+                    const int r = jb + wb + ri, r2 = jb + wb + ri2;
+                    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
-                        for (int c2 = 0; c2 < 8; ++c2) s2 -= sD[r][jb + c2] * lc[c2];
-                        sD[r][cidx] = s2;
+                    for (int c2 = 0; c2 < 8; c2 += 2) {
+                        if (on1) { p0 += sD[r][jb + c2] * lc[c2]; p1 += sD[r][jb + c2 + 1] * lc[c2 + 1]; }
+                        if (on2) { q0 += sD[r2][jb + c2] * lc[c2]; q1 += sD[r2][jb + c2 + 1] * lc[c2 + 1]; }
                     }
+                    if (on1) sD[r][cidx] -= p0 + p1;
+                    if (on2) sD[r2][cidx] -= q0 + q1;
                 }
             }
         }
@@ -615,6 +668,355 @@ chol_solve_kernel(double* S, long long lds, int n, double* b, int* __restrict__ 
     }
 }
 
+
+// ---- Cholesky as a task graph (default): no grid barrier in the factorisation -------------------------------------------------
+// Tasks on 64x64 tiles:  D(k) factor the diagonal tile (+ L_kk^-1),  T(i,k) L_ik = A_ik L_kk^-T,  U(i,j,k) A_ij -= L_ik L_jk^T;
+// the right-hand side is tile row nb.  Every tile has ONE owner CTA that applies all of its updates in panel order (fixed
+// floating-point order, no atomics); readiness travels through release/acquire flags in global memory (dflag[k], tflag[i][k]).
+// A CTA walks the panels k = 0, 1, ... and at each one runs its D, then its T, then its U tasks, spinning on the flags of the
+// tiles it needs.  All waits point to tasks of the same or an earlier panel and the grid is co-resident (cooperative launch),
+// so the schedule cannot deadlock; the look-ahead is implicit -- while the owner of the next diagonal tile factors it, the
+// other CTAs apply the current panel to the rest of the matrix.  The two tiles on the critical path of panel k+1, (k+1,k) and
+// (k+1,k+1), belong to the same CTA (k+1 mod G), so the chain D(k) -> T(k+1,k) -> U(k+1,k+1,k) -> D(k+1) crosses CTAs once.
+#ifdef VEL_CHOL_TIMING
+__device__ unsigned long long g_dag_t[2][8];
+#define DG_T(k) do { if (threadIdx.x == 0) { unsigned long long now_ = gtime(); atomicAdd(&g_dag_t[blockIdx.x < nb ? 0 : 1][k], now_ - dg_last); dg_last = now_; } } while (0)
+#else
+#define DG_T(k)
+#endif
+
+struct DagOwn {
+    int nb, G, W0, NW;
+    __device__ __forceinline__ int owner(int i, int j) const      // i in j..nb (nb = right-hand-side strip)
+    {
+        if (i == j || i == j + 1) return i % G;                 // the two tiles on panel j+1's critical path share a CTA
+        const long long e = (long long)j * (nb - 1) - (long long)j * (j - 1) / 2 + (i - (j + 2));
+        return W0 + (int)(e % NW);
+    }
+};
+
+__device__ __forceinline__ void dag_wait(const int* flag)
+{
+    if (threadIdx.x == 0) {
+        while (ld_acquire(flag) == 0) __nanosleep(32);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void dag_signal(int* flag)
+{
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) st_release(flag, 1);
+}
+
+// Linv = L^-1 for the w x w lower-triangular L in sD (reciprocal diagonal in rdiag) -> sI [64][CH_LDT] (row-major, zero above the
+// diagonal).  Right-looking: once row m of Linv is final, every later row i accumulates L[i][m] * Linv[m][:]; thread = (row group, column).
+__device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int w, double* sI)
+{
+    const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
+    for (int e = tid; e < CH_NB * CH_LDT; e += CH_THREADS) sI[e] = 0.0;
+    __syncthreads();
+    // processed in 8-row groups: inside a group the rows are finished one after the other by the threads of their column,
+    // then the whole group is applied to the rows below it (8 pivots per barrier instead of one)
+    for (int m0 = 0; m0 < w; m0 += 8) {
+        const int mw = min(8, w - m0);
+        if (tid < 64 && c < m0 + mw) {
+            // rows m0..m0+mw-1, column c: x_m = rdiag[m] * ((m == c) - acc[m][c] - sum_{m0 <= q < m} L[m][q] x_q), column-oriented so
+            // that the dependent chain is one multiply + one FMA per row (FP64 latency is ~38 cycles on this part)
+            double a[8], x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = u < mw ? ((m0 + u == c ? 1.0 : 0.0) - sI[(m0 + u) * CH_LDT + c]) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                x[q] = (q < mw && c <= m0 + q) ? a[q] * rdiag[m0 + q] : 0.0;
+#pragma unroll
+                for (int u = q + 1; u < 8; ++u)
+                    if (u < mw) a[u] -= sD[m0 + u][m0 + q] * x[q];
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (u < mw) sI[(m0 + u) * CH_LDT + c] = x[u];
+        }
+        __syncthreads();
+        // rows below the group: acc[i][c] += sum_u L[i][m0+u] * Linv[m0+u][c]   (two rows in flight per thread, split sums)
+        if (c < m0 + mw) {
+            double xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) xv[u] = u < mw ? sI[(m0 + u) * CH_LDT + c] : 0.0;
+            constexpr int RS = CH_THREADS / 64;
+            for (int i = m0 + mw + rg; i < w; i += 2 * RS) {
+                const int i2 = i + RS;
+                const bool two = i2 < w;
+                double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; u += 2) {
+                    p0 += sD[i][m0 + u] * xv[u];
+                    p1 += sD[i][m0 + u + 1] * xv[u + 1];
+                    if (two) { q0 += sD[i2][m0 + u] * xv[u]; q1 += sD[i2][m0 + u + 1] * xv[u + 1]; }
+                }
+                sI[i * CH_LDT + c] += p0 + p1;
+                if (two) sI[i2 * CH_LDT + c] += q0 + q1;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// C(64x64 accumulators of the calling thread layout) = A(64 x kw) * B(64 x kw)^T from two staged tiles
+__device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bufB, double (&acc)[2][2][2])
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    const int sr = (warp >> 2) * 16, sc = (warp & 3) * 16;
+#pragma unroll
+    for (int kk = 0; kk < CH_NB / 4; ++kk) {
+        double a[2], bb[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            a[i] = bufA[(sr + i * 8 + g) * CH_LDT + kk * 4 + t4];
+            bb[i] = bufB[(sc + i * 8 + g) * CH_LDT + kk * 4 + t4];
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) dmma884(acc[i][j][0], acc[i][j][1], a[i], bb[j]);
+    }
+}
+
+__global__ void __launch_bounds__(CH_THREADS, 1)
+chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, double* Linv_g)
+{
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) double ch_smem[];
+    double (*sD)[CH_LD] = reinterpret_cast<double (*)[CH_LD]>(ch_smem);
+    double* bufA = ch_smem + CH_NB * CH_LD + (CH_NB * CH_LD & 1);
+    double* bufB = bufA + CH_NB * CH_LDT;
+    double* sI = bufB + CH_NB * CH_LDT;                            // L_kk^-1 of the panel this CTA is working with
+    __shared__ int s_ok, own_n;
+    __shared__ unsigned short own_i[CH_MAXOWN], own_j[CH_MAXOWN];
+    __shared__ double rdiag[CH_NB];
+    __shared__ double sx[2][CH_NB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int nb = (n + CH_NB - 1) / CH_NB;
+    const bool vec = (lds & 1) == 0 && ((size_t)S & 15) == 0;
+    const int me = blockIdx.x, G = gridDim.x;
+    DagOwn own;
+    own.nb = nb; own.G = G;
+    if (nb <= G / 2) { own.W0 = nb; own.NW = G - nb; } else { own.W0 = 0; own.NW = G; }
+    if (tid == 0) { s_ok = 1; own_n = 0; }
+    __syncthreads();
+    const int sr = (warp >> 2) * 16, sc = (warp & 3) * 16;
+
+    // ---- this CTA's tiles, in (column, row) order -----------------------------------------------------------------------
+    {
+        const long long ntile = (long long)nb * (nb + 1) / 2 + nb;              // lower tiles + one strip tile per column
+        const double hb = nb + 1.5;
+        for (long long t = tid; t < ntile; t += CH_THREADS) {
+            int j = (int)(hb - sqrt(fmax(hb * hb - 2.0 * (double)t, 0.0)));
+            j = max(0, min(j, nb - 1));
+            while (j > 0 && (long long)j * (nb + 1) - (long long)j * (j - 1) / 2 > t) --j;
+            while (j < nb - 1 && (long long)(j + 1) * (nb + 1) - (long long)(j + 1) * j / 2 <= t) ++j;
+            const int i = j + (int)(t - ((long long)j * (nb + 1) - (long long)j * (j - 1) / 2));
+            if (own.owner(i, j) == me) {
+                const int idx = atomicAdd(&own_n, 1);
+                if (idx < CH_MAXOWN) { own_i[idx] = (unsigned short)i; own_j[idx] = (unsigned short)j; }
+            }
+        }
+        __syncthreads();
+        if (own_n > CH_MAXOWN) {                      // cannot happen for n <= 64 * 65535 / ... with the sizes this library serves; report, do not hang
+            if (me == 0 && tid == 0) info[0] = 2;
+            own_n = 0;                                 // (every CTA takes the same decision only if all overflow; guarded on the host by the size check)
+        }
+        if (tid == 0) {                               // insertion sort by (j, i): a handful of entries
+            for (int a = 1; a < own_n; ++a) {
+                const unsigned short ti = own_i[a], tj = own_j[a];
+                int bpos = a - 1;
+                while (bpos >= 0 && (own_j[bpos] > tj || (own_j[bpos] == tj && own_i[bpos] > ti))) {
+                    own_i[bpos + 1] = own_i[bpos]; own_j[bpos + 1] = own_j[bpos];
+                    --bpos;
+                }
+                own_i[bpos + 1] = ti; own_j[bpos + 1] = tj;
+            }
+        }
+        __syncthreads();
+    }
+    int p_lo = 0;                                      // first own tile with column >= k
+#ifdef VEL_CHOL_TIMING
+    unsigned long long dg_last = gtime();
+#endif
+
+    for (int k = 0; k < nb; ++k) {
+        const int k0 = k * CH_NB, w = min(CH_NB, n - k0);
+        int have_linv = 0;
+        while (p_lo < own_n && own_j[p_lo] < k) ++p_lo;
+        int p = p_lo;
+        // ---------------- D(k) and T(i,k): own tiles of column k ----------------
+        for (; p < own_n && own_j[p] == k; ++p) {
+            const int i = own_i[p];
+            if (i == k) {
+                DG_T(7);
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                    const int r = e >> 6, c2 = e & 63;
+                    if (r < w && c2 < w) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(k0 + r) * lds + k0 + c2) : 0.0;
+                }
+                __syncthreads();
+                DG_T(0);
+                chol_block(sD, w, &s_ok, rdiag);
+                DG_T(1);
+                tri_inverse_block(sD, rdiag, w, sI);
+                DG_T(2);
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                    const int r = e >> 6, c2 = e & 63;
+                    if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+                    Linv_g[(long long)k * CH_NB * CH_NB + e] = (r < w && c2 < w) ? sI[r * CH_LDT + c2] : 0.0;
+                }
+                if (tid == 0 && !s_ok) info[0] = 1;
+                dag_signal(dflag + k);
+                DG_T(3);
+                have_linv = 1;
+                continue;
+            }
+            if (!have_linv) {
+                DG_T(7);
+                dag_wait(dflag + k);
+                DG_T(4);
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sI[(e >> 6) * CH_LDT + (e & 63)] = __ldcg(Linv_g + (long long)k * CH_NB * CH_NB + e);
+                have_linv = 1;
+            }
+            __syncthreads();
+            if (i == nb) {
+                // right-hand-side strip: y[c] = sum_{m <= c} b[k0+m] Linv[c][m]
+                if (tid < w) bufA[tid] = __ldcg(b + k0 + tid);
+                __syncthreads();
+                if (tid < w) {
+                    double a0 = 0.0, a1 = 0.0;
+                    for (int m = 0; m + 1 <= tid; m += 2) { a0 += bufA[m] * sI[tid * CH_LDT + m]; a1 += bufA[m + 1] * sI[tid * CH_LDT + m + 1]; }
+                    if ((tid & 1) == 0) a0 += bufA[tid] * sI[tid * CH_LDT + tid];
+                    b[k0 + tid] = a0 + a1;
+                }
+            } else {
+                const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
+                chol_load_tile(S, lds, r0, wi, k0, w, bufA, vec);
+                __syncthreads();
+                double acc[2][2][2] = {};
+                tile_mma_64(bufA, sI, acc);                     // X = A Linv^T
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int r = sr + ii * 8 + g, c2 = sc + jj * 8 + 2 * t4;
+                        if (r < wi) {
+                            double* pp = S + (long long)(r0 + r) * lds + k0 + c2;
+                            if (c2 < w) pp[0] = acc[ii][jj][0];
+                            if (c2 + 1 < w) pp[1] = acc[ii][jj][1];
+                        }
+                    }
+            }
+            dag_signal(tflag + (long long)i * nb + k);
+            DG_T(5);
+        }
+        // ---------------- U(i,j,k): own tiles of the columns j > k ----------------
+        int cur_j = -1;
+        for (; p < own_n; ++p) {
+            const int i = own_i[p], j = own_j[p];
+            const int c0 = j * CH_NB, wj = min(CH_NB, n - c0);
+            if (j != cur_j) {
+                DG_T(7);
+                dag_wait(tflag + (long long)j * nb + k);
+                DG_T(4);
+                chol_load_tile(S, lds, c0, wj, k0, w, bufB, vec);           // L_jk
+                cur_j = j;
+            }
+            if (i == nb) {
+                dag_wait(tflag + (long long)nb * nb + k);
+                if (tid < w) bufA[tid] = __ldcg(b + k0 + tid);
+                __syncthreads();
+                if (tid < wj) {
+                    double s2 = 0.0;
+                    for (int c2 = 0; c2 < w; ++c2) s2 += bufA[c2] * bufB[tid * CH_LDT + c2];
+                    b[c0 + tid] = __ldcg(b + c0 + tid) - s2;
+                }
+                __syncthreads();
+                continue;
+            }
+            const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
+            if (i != j) {
+                DG_T(6);
+                dag_wait(tflag + (long long)i * nb + k);
+                DG_T(4);
+                chol_load_tile(S, lds, r0, wi, k0, w, bufA, vec);           // L_ik
+            }
+            __syncthreads();
+            double acc[2][2][2] = {};
+            tile_mma_64(i == j ? bufB : bufA, bufB, acc);
+            double2 cur[2][2];
+            bool m0[2][2], m1[2][2];
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int r = sr + ii * 8 + g, c2 = sc + jj * 8 + 2 * t4;
+                    m0[ii][jj] = r < wi && c2 < wj && (i > j || c2 <= r);
+                    m1[ii][jj] = r < wi && c2 + 1 < wj && (i > j || c2 + 1 <= r);
+                    const double* pp = S + (long long)(r0 + r) * lds + c0 + c2;
+                    cur[ii][jj] = make_double2(0.0, 0.0);
+                    if (vec && m0[ii][jj] && m1[ii][jj]) cur[ii][jj] = __ldcg(reinterpret_cast<const double2*>(pp));
+                    else {
+                        if (m0[ii][jj]) cur[ii][jj].x = __ldcg(pp);
+                        if (m1[ii][jj]) cur[ii][jj].y = __ldcg(pp + 1);
+                    }
+                }
+#pragma unroll
+            for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int r = sr + ii * 8 + g, c2 = sc + jj * 8 + 2 * t4;
+                    double* pp = S + (long long)(r0 + r) * lds + c0 + c2;
+                    const double2 v = make_double2(cur[ii][jj].x - acc[ii][jj][0], cur[ii][jj].y - acc[ii][jj][1]);
+                    if (vec && m0[ii][jj] && m1[ii][jj]) *reinterpret_cast<double2*>(pp) = v;
+                    else {
+                        if (m0[ii][jj]) pp[0] = v.x;
+                        if (m1[ii][jj]) pp[1] = v.y;
+                    }
+                }
+            __syncthreads();                                        // the operand tiles are reloaded by the next task
+            DG_T(6);
+        }
+    }
+    __threadfence();
+    grid.sync();
+    if (me == 0 && tid == 0 && info[0] != 1) info[0] = 0;
+
+    // ---- backward substitution  L^T x = y  with the stored inverses of the diagonal tiles: x_k = Linv_k^T y_k (a 64x64
+    //      product every CTA computes for itself), then y[c] -= sum_r L[k0+r][c] x[r] over the columns to the left -------------
+    for (int kb = nb - 1; kb >= 0; --kb) {
+        const int k0 = kb * CH_NB, w = min(CH_NB, n - k0);
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sI[(e >> 6) * CH_LDT + (e & 63)] = __ldcg(Linv_g + (long long)kb * CH_NB * CH_NB + e);
+        if (tid < CH_NB) sx[0][tid] = tid < w ? __ldcg(b + k0 + tid) : 0.0;
+        __syncthreads();
+        {
+            // x[c] = sum_{m >= c} Linv[m][c] y[m]: 8 threads per output, fixed-order tree
+            const int c = tid >> 3, part = tid & 7;
+            double a = 0.0;
+            for (int m = c + part; m < w; m += 8) a += sI[m * CH_LDT + c] * sx[0][m];
+            a += __shfl_down_sync(0xffffffffu, a, 4, 8);
+            a += __shfl_down_sync(0xffffffffu, a, 2, 8);
+            a += __shfl_down_sync(0xffffffffu, a, 1, 8);
+            if (part == 0) sx[1][c] = c < w ? a : 0.0;
+        }
+        __syncthreads();
+        if (me == 0 && tid < w) b[k0 + tid] = sx[1][tid];
+        const int gtid = me * CH_THREADS + tid, gthreads = G * CH_THREADS;
+        for (int c2 = gtid; c2 < k0; c2 += gthreads) {
+            double s2 = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < w; ++r) s2 += __ldcg(S + (long long)(k0 + r) * lds + c2) * sx[1][r];
+            b[c2] = __ldcg(b + c2) - s2;
+        }
+        if (kb > 0) grid.sync();
+    }
+}
+
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 }  // namespace
@@ -682,7 +1084,8 @@ VEL_API void vel_chol_timing(unsigned long long* out8, int reset)
     cudaDeviceSynchronize();
     cudaMemcpyFromSymbol(out8, g_chol_t, sizeof(unsigned long long) * 8);
     cudaMemcpyFromSymbol(out8 + 8, g_cb_t, sizeof(unsigned long long) * 4);
-    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_t, z, sizeof(z)); cudaMemcpyToSymbol(g_cb_t, z, sizeof(unsigned long long) * 4); }
+    cudaMemcpyFromSymbol(out8 + 12, g_dag_t, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[8] = {0}; cudaMemcpyToSymbol(g_chol_t, z, sizeof(z)); cudaMemcpyToSymbol(g_cb_t, z, sizeof(unsigned long long) * 4); unsigned long long z2[16] = {0}; cudaMemcpyToSymbol(g_dag_t, z2, sizeof(z2)); }
 }
 #endif
 
@@ -691,21 +1094,55 @@ VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t*
     VEL_CHECK_ARG(S && b && info, "vel_spd_solve: NULL argument");
     VEL_CHECK_ARG(n > 0 && lds >= n, "vel_spd_solve: bad sizes n=%d lds=%lld", n, (long long)lds);
     cudaStream_t st = (cudaStream_t)stream;
+    const char* mode = getenv("VEL_CHOL");
+    bool use_dag = !(mode && strcmp(mode, "sync") == 0);
+    {   // the task-graph form keeps each CTA's tile list in shared memory: very large systems take the barrier form
+        const long long nb_ = (n + CH_NB - 1) / CH_NB, ntile = nb_ * (nb_ + 1) / 2 + nb_;
+        if (ntile > (long long)sm_count() * (CH_MAXOWN / 2)) use_dag = false;
+    }
     static int max_grid = 0;
     if (max_grid == 0) {
         int per_sm = 0;
         VEL_CUDA(cudaFuncSetAttribute(chol_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_SMEM));
-        VEL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_solve_kernel, CH_THREADS, CH_SMEM));
+        VEL_CUDA(cudaFuncSetAttribute(chol_dag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CH_DAG_SMEM));
+        VEL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chol_dag_kernel, CH_THREADS, CH_DAG_SMEM));
         VEL_CHECK_ARG(per_sm >= 1, "vel_spd_solve: kernel does not fit an SM");
         max_grid = sm_count();
     }
     const int nblk = (n + CH_NB - 1) / CH_NB;
-    int grid = max_grid;
-    const int want = nblk * (nblk + 1) / 2 + nblk;          // tiles of the first trailing update
-    if (want < grid) grid = want < 1 ? 1 : want;
     long long lds_ = lds;
     int n_ = n;
-    void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info};
-    VEL_CUDA(cudaLaunchCooperativeKernel((void*)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, CH_SMEM, st));
+    if (!use_dag) {
+        int grid = max_grid;
+        const int want = nblk * (nblk + 1) / 2 + nblk;          // tiles of the first trailing update
+        if (want < grid) grid = want < 1 ? 1 : want;
+        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info};
+        VEL_CUDA(cudaLaunchCooperativeKernel((void*)chol_solve_kernel, dim3(grid), dim3(CH_THREADS), args, CH_SMEM, st));
+        return VEL_OK;
+    }
+    // task-graph form: flags (dflag[nb], tflag[(nb+1)*nb]) and the inverses of the diagonal tiles live in stream-ordered scratch
+    vel_keep_async_pool_cached();
+    const size_t nflags = (size_t)nblk + (size_t)(nblk + 1) * nblk;
+    const size_t flag_bytes = align256(sizeof(int) * nflags);
+    const size_t bytes = flag_bytes + sizeof(double) * (size_t)nblk * CH_NB * CH_NB;
+    char* scratch = nullptr;
+    VEL_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
+    cudaError_t e = cudaMemsetAsync(scratch, 0, flag_bytes, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), st);
+    int* dflag = (int*)scratch;
+    int* tflag = dflag + nblk;
+    double* Linv_g = (double*)(scratch + flag_bytes);
+    const int want = nblk * (nblk + 1) / 2 + nblk;
+    int grid = max_grid;
+    if (want < grid) grid = want < 1 ? 1 : want;
+    if (e == cudaSuccess) {
+        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&Linv_g};
+        e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
+    }
+    cudaFreeAsync(scratch, st);
+    if (e != cudaSuccess) {
+        vel_set_error("vel_spd_solve: %s", cudaGetErrorString(e));
+        return VEL_ERR_CUDA;
+    }
     return VEL_OK;
 }

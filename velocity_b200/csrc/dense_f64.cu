@@ -290,10 +290,19 @@ constexpr size_t CH_SMEM = sizeof(double) * (CH_NB * CH_LD + 2 * CH_NB * CH_LDT)
 constexpr int CH_MAXOWN = 2048;                                                        // own-tile list of the task-graph form
 constexpr size_t CH_DAG_SMEM = sizeof(double) * (CH_NB * CH_LD + 3 * CH_NB * CH_LDT);  // + the panel's inverse diagonal tile
 
-// 64x64 (w x w) lower Cholesky of sD in place, all CH_THREADS threads of the CTA; 8-column blocked:
-// (i) one warp factors the 8x8 diagonal sub-block in registers, (ii) a thread per row solves the 8-column sub-panel below it,
-// (iii) everyone applies the rank-8 update to the rest of the block.  ok is cleared when a pivot is not positive;
-// rdiag receives the reciprocals of the diagonal of L.
+// reciprocal to full double precision from the 20-bit hardware seed and two Newton steps: ~170 cycles of dependent latency
+// against ~250 for the library's rsqrt / divide (FP64 instructions have ~38 cycles of latency on this part, so the per-column
+// pivot chain of a Cholesky factorisation is what bounds it)
+__device__ __forceinline__ double fast_rcp(double x)
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+
 #ifdef VEL_CHOL_TIMING
 __device__ unsigned long long g_cb_t[4];
 #define CB_T(k) do { if (blockIdx.x == 0 && threadIdx.x == 0) { long long now_ = clock64(); g_cb_t[k] += now_ - cb_last; cb_last = now_; } } while (0)
@@ -301,94 +310,134 @@ __device__ unsigned long long g_cb_t[4];
 #define CB_T(k)
 #endif
 
-__device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag)
+struct CholScratch {
+    double T[CH_NB][8];      // the current 8-column sub-panel scaled by the reciprocal pivots (rows of the block)
+    double d[CH_NB];         // pivots of the square-root-free factorisation
+};
+
+// 64x64 (w x w) lower Cholesky of sD in place, all CH_THREADS threads of the CTA, organised around the one thing that bounds
+// it -- the pivot-to-pivot dependency chain:
+//   * square-root free inside (A = M D^-1 M^T, M = unscaled columns): a column costs one reciprocal + one multiply + one FMA on
+//     the chain; the 64 square roots are taken at the end, in parallel (L = M D^-1/2);
+//   * 8-column steps; EVERY thread factors the 8x8 diagonal sub-block redundantly in registers (no shuffles, no barrier between
+//     that and the forward substitution of the thread's own row below it);
+//   * the rank-8 update of the rest of the block runs on the tensor cores (DMMA).
+// ok is cleared when a pivot is not positive; rdiag receives 1 / L_cc.
+__device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, CholScratch* cs)
 {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
 #ifdef VEL_CHOL_TIMING
     long long cb_last = clock64();
 #endif
     for (int jb = 0; jb < w; jb += 8) {
         const int wb = min(8, w - jb);
         CB_T(3);
-        if (tid < 32) {
-            // lanes 0..7 own the rows of the sub-block
-            const int r = tid & 7;
-            double a[8];
+        // ---- (i) the 8x8 diagonal sub-block, redundantly in every thread: a[u(u+1)/2 + c], c <= u ------------------------------
+        double a[36], rp[8];
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) a[c2] = (r < wb && c2 < wb && c2 <= r) ? sD[jb + r][jb + c2] : 0.0;
+        for (int u = 0; u < 8; ++u)
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) {
-                if (c2 < wb) {
-                    const double piv = __shfl_sync(0xffffffffu, a[c2], c2);
-                    if (!(piv > 0.0) && tid == 0) *ok = 0;
-                    const double inv = rsqrt(piv);                // one slow op on the column-to-column chain instead of sqrt + divide
-                    const double d = piv * inv;
-                    if (tid == c2) rdiag[jb + c2] = inv;
-                    a[c2] = (r == c2) ? d : a[c2] * inv;          // column c2 of L (rows > c2 are scaled, row c2 holds the pivot root)
+            for (int c = 0; c <= u; ++c)
+                a[u * (u + 1) / 2 + c] = (u < wb) ? sD[jb + u][jb + c] : (u == c ? 1.0 : 0.0);     // identity padding past the block
+        bool bad = false;
 #pragma unroll
-                    for (int c3 = c2 + 1; c3 < 8; ++c3) {
-                        const double l3 = __shfl_sync(0xffffffffu, a[c2], c3);   // L[c3][c2]
-                        if (c3 <= r) a[c3] -= a[c2] * l3;
-                    }
-                }
+        for (int c = 0; c < 8; ++c) {
+            const double piv = a[c * (c + 1) / 2 + c];
+            bad = bad || !(piv > 0.0);
+            rp[c] = fast_rcp(piv);
+            double m[8];
+#pragma unroll
+            for (int u = c + 1; u < 8; ++u) {
+                m[u] = a[u * (u + 1) / 2 + c];
+                a[u * (u + 1) / 2 + c] = m[u] * rp[c];                       // T[u][c] = M[u][c] / d_c
             }
-            if (tid < 8 && r < wb) {
 #pragma unroll
-                for (int c2 = 0; c2 < 8; ++c2)
-                    if (c2 < wb && c2 <= r) sD[jb + r][jb + c2] = a[c2];
-            }
+            for (int u = c + 1; u < 8; ++u)
+#pragma unroll
+                for (int u2 = c + 1; u2 <= u; ++u2) a[u * (u + 1) / 2 + u2] -= m[u] * a[u2 * (u2 + 1) / 2 + c];
         }
-        __syncthreads();
-        CB_T(0);
-        // (ii) rows below the sub-block: x L_sub^T = a  (forward substitution over the 8 columns)
+        if (bad && tid == 0) *ok = 0;
+        // ---- (ii) the thread's own row below the sub-block: M[r][q] = a[r][q] - sum_{p<q} M[r][p] T[q][p] ------------------------
         const int below = w - jb - wb;
         if (tid < below) {
             const int r = jb + wb + tid;
             double x[8];
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) x[c2] = c2 < wb ? sD[r][jb + c2] : 0.0;
+            for (int q = 0; q < 8; ++q) x[q] = q < wb ? sD[r][jb + q] : 0.0;
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2) {
-                if (c2 < wb) {
-                    x[c2] = x[c2] * rdiag[jb + c2];
+            for (int q = 0; q < 8; ++q)
 #pragma unroll
-                    for (int c3 = c2 + 1; c3 < 8; ++c3)
-                        if (c3 < wb) x[c3] -= x[c2] * sD[jb + c3][jb + c2];
-                }
+                for (int u = q + 1; u < 8; ++u) x[u] -= x[q] * a[u * (u + 1) / 2 + q];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < wb) sD[r][jb + q] = x[q];
+                cs->T[r][q] = q < wb ? x[q] * rp[q] : 0.0;
             }
+        } else if (tid >= 448 && tid < 448 + 8) {
+            // one thread per row of the sub-block writes it back as M (unscaled: T * d) and publishes the pivots
+            const int u = tid - 448;
+            if (u < wb) {
 #pragma unroll
-            for (int c2 = 0; c2 < 8; ++c2)
-                if (c2 < wb) sD[r][jb + c2] = x[c2];
+                for (int c = 0; c < 8; ++c) {
+                    if (c < u) {
+                        double tv = 0.0, dv = 1.0;
+#pragma unroll
+                        for (int uu = 0; uu < 8; ++uu)
+                            if (uu == u) { tv = a[uu * (uu + 1) / 2 + c]; }
+                        dv = a[c * (c + 1) / 2 + c];
+                        sD[jb + u][jb + c] = tv * dv;
+                    }
+                }
+                double du = 0.0;
+#pragma unroll
+                for (int uu = 0; uu < 8; ++uu)
+                    if (uu == u) du = a[uu * (uu + 1) / 2 + uu];
+                cs->d[jb + u] = du;
+            }
         }
         __syncthreads();
-        CB_T(1);
-        // (iii) rank-wb update of the trailing lower part: thread = (row group, column)
-        {
-            const int ci = tid & 63, rg = tid >> 6;
-            if (ci < below) {
-                const int cidx = jb + wb + ci;
-                double lc[8];
+        CB_T(0);
+        // ---- (iii) rank-8 update of the rest of the block on the tensor cores: a[r][r'] -= sum_q M[r][q] T[r'][q] ----------------
+        if (below > 0) {
+            const int R0 = jb + wb, nt8 = (below + 7) >> 3, ntile = nt8 * (nt8 + 1) / 2;
+            for (int tt = warp; tt < ntile; tt += CH_THREADS / 32) {
+                int ta = (int)((sqrtf(8.f * (float)tt + 1.f) - 1.f) * 0.5f);
+                while ((ta + 1) * (ta + 2) / 2 <= tt) ++ta;
+                while (ta * (ta + 1) / 2 > tt) --ta;
+                const int tb = tt - ta * (ta + 1) / 2;
+                const int ra = R0 + ta * 8 + g, rb = R0 + tb * 8 + g;
+                double d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int c2 = 0; c2 < 8; ++c2) lc[c2] = c2 < wb ? sD[cidx][jb + c2] : 0.0;
-                constexpr int RS = CH_THREADS / 64;
-                for (int ri = rg; ri < below; ri += 2 * RS) {      // two rows in flight, two partial sums each: the 8-term update is a
-                    const int ri2 = ri + RS;                       // latency chain otherwise
-                    const bool on1 = ci <= ri, on2 = ri2 < below && ci <= ri2;
-                    const int r = jb + wb + ri, r2 = jb + wb + ri2;
-                    double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-#pragma unroll
-                    for (int c2 = 0; c2 < 8; c2 += 2) {
-                        if (on1) { p0 += sD[r][jb + c2] * lc[c2]; p1 += sD[r][jb + c2 + 1] * lc[c2 + 1]; }
-                        if (on2) { q0 += sD[r2][jb + c2] * lc[c2]; q1 += sD[r2][jb + c2 + 1] * lc[c2 + 1]; }
-                    }
-                    if (on1) sD[r][cidx] -= p0 + p1;
-                    if (on2) sD[r2][cidx] -= q0 + q1;
+                for (int kk = 0; kk < 2; ++kk) {
+                    const int q = kk * 4 + t4;
+                    const double av = (ra < w && q < wb) ? sD[ra][jb + q] : 0.0;
+                    const double bv = rb < w ? cs->T[rb][q] : 0.0;
+                    dmma884(d0, d1, av, bv);
+                }
+                const int cc = R0 + tb * 8 + 2 * t4;
+                if (ra < w) {
+                    if (cc < w && cc <= ra) sD[ra][cc] -= d0;
+                    if (cc + 1 < w && cc + 1 <= ra) sD[ra][cc + 1] -= d1;
                 }
             }
         }
         __syncthreads();
         CB_T(2);
     }
+    // ---- L = M D^-1/2: the square roots, all at once ------------------------------------------------------------------------------
+    if (tid < w) {
+        const double dv = cs->d[tid];
+        const double rs = rsqrt(dv);
+        rdiag[tid] = rs;                       // 1 / L_cc
+        cs->d[tid] = dv * rs;                  // L_cc
+    }
+    __syncthreads();
+    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+        const int r = e >> 6, c = e & 63;
+        if (r < w && c < r) sD[r][c] *= rdiag[c];
+        else if (r < w && c == r) sD[r][c] = cs->d[c];
+    }
+    __syncthreads();
 }
 
 #ifdef VEL_CHOL_TIMING
@@ -533,6 +582,7 @@ chol_solve_kernel(double* S, long long lds, int n, double* b, int* __restrict__ 
     double* bufA = ch_smem + CH_NB * CH_LD + (CH_NB * CH_LD & 1);              // 16-byte aligned operand tiles
     double* bufB = bufA + CH_NB * CH_LDT;
     __shared__ int s_ok;
+    __shared__ CholScratch cs;
     __shared__ double rdiag[CH_NB];              // reciprocals of the diagonal of the block in sD
     __shared__ double sx[2][CH_NB];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -554,7 +604,7 @@ chol_solve_kernel(double* S, long long lds, int n, double* b, int* __restrict__ 
         }
         __syncthreads();
         CH_T(0);
-        chol_block(sD, w, &s_ok, rdiag);
+        chol_block(sD, w, &s_ok, rdiag, &cs);
         CH_T(1);
         if (blockIdx.x == 0) {
             for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
@@ -710,53 +760,61 @@ __device__ __forceinline__ void dag_signal(int* flag)
 }
 
 // Linv = L^-1 for the w x w lower-triangular L in sD (reciprocal diagonal in rdiag) -> sI [64][CH_LDT] (row-major, zero above the
-// diagonal).  Right-looking: once row m of Linv is final, every later row i accumulates L[i][m] * Linv[m][:]; thread = (row group, column).
-__device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int w, double* sI)
+// diagonal).  Recursive doubling, so that almost nothing sits on an FP64 latency chain: the eight 8x8 diagonal blocks are
+// inverted by 64 threads in parallel (one 8-step chain), then three levels h = 8, 16, 32 fill the off-diagonal blocks with
+//     Inv[R][C] = -Inv[R][R] * (L[R][C] * Inv[C][C])        R = lower half, C = upper half of a 2h x 2h diagonal block
+// as two small tensor-core (DMMA) products per level.  tmp = [64][CH_LDT] scratch.  Rows/columns >= w behave as identity.
+__device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int w, double* sI, double* tmp)
 {
-    const int tid = threadIdx.x, c = tid & 63, rg = tid >> 6;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     for (int e = tid; e < CH_NB * CH_LDT; e += CH_THREADS) sI[e] = 0.0;
     __syncthreads();
-    // processed in 8-row groups: inside a group the rows are finished one after the other by the threads of their column,
-    // then the whole group is applied to the rows below it (8 pivots per barrier instead of one)
-    for (int m0 = 0; m0 < w; m0 += 8) {
-        const int mw = min(8, w - m0);
-        if (tid < 64 && c < m0 + mw) {
-            // rows m0..m0+mw-1, column c: x_m = rdiag[m] * ((m == c) - acc[m][c] - sum_{m0 <= q < m} L[m][q] x_q), column-oriented so
-            // that the dependent chain is one multiply + one FMA per row (FP64 latency is ~38 cycles on this part)
-            double a[8], x[8];
+    if (tid < 64) {
+        const int m0 = tid & ~7, c = tid & 7;                // block m0/8, column c of the block
+        double a[8], x[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = u < mw ? ((m0 + u == c ? 1.0 : 0.0) - sI[(m0 + u) * CH_LDT + c]) : 0.0;
+        for (int u = 0; u < 8; ++u) a[u] = u == c ? 1.0 : 0.0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                x[q] = (q < mw && c <= m0 + q) ? a[q] * rdiag[m0 + q] : 0.0;
+        for (int q = 0; q < 8; ++q) {
+            const bool in = m0 + q < w;
+            x[q] = q >= c ? (in ? a[q] * rdiag[m0 + q] : a[q]) : 0.0;
 #pragma unroll
-                for (int u = q + 1; u < 8; ++u)
-                    if (u < mw) a[u] -= sD[m0 + u][m0 + q] * x[q];
+            for (int u = q + 1; u < 8; ++u)
+                if (m0 + u < w && in) a[u] -= sD[m0 + u][m0 + q] * x[q];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sI[(m0 + u) * CH_LDT + m0 + c] = x[u];
+    }
+    __syncthreads();
+    for (int h = 8; h < CH_NB; h *= 2) {
+        const int tpd = h >> 3, tpp = tpd * tpd, npair = CH_NB / (2 * h), ntile = npair * tpp;
+        // tmp[R][C] = L[R][C] * Inv[C][C]
+        for (int tt = warp; tt < ntile; tt += CH_THREADS / 32) {
+            const int pr = tt / tpp, ta = (tt % tpp) / tpd, tb = tt % tpd;
+            const int R0 = (2 * pr + 1) * h, C0 = 2 * pr * h;
+            double d0 = 0.0, d1 = 0.0;
+            for (int k4 = 0; k4 < h / 4; ++k4) {
+                const int rr = R0 + ta * 8 + g, kk = C0 + k4 * 4 + t4;
+                const double a = (rr < w && kk < w) ? sD[rr][kk] : 0.0;
+                const double bv = sI[kk * CH_LDT + C0 + tb * 8 + g];
+                dmma884(d0, d1, a, bv);
             }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (u < mw) sI[(m0 + u) * CH_LDT + c] = x[u];
+            tmp[(R0 + ta * 8 + g) * CH_LDT + C0 + tb * 8 + 2 * t4] = d0;
+            tmp[(R0 + ta * 8 + g) * CH_LDT + C0 + tb * 8 + 2 * t4 + 1] = d1;
         }
         __syncthreads();
-        // rows below the group: acc[i][c] += sum_u L[i][m0+u] * Linv[m0+u][c]   (two rows in flight per thread, split sums)
-        if (c < m0 + mw) {
-            double xv[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) xv[u] = u < mw ? sI[(m0 + u) * CH_LDT + c] : 0.0;
-            constexpr int RS = CH_THREADS / 64;
-            for (int i = m0 + mw + rg; i < w; i += 2 * RS) {
-                const int i2 = i + RS;
-                const bool two = i2 < w;
-                double p0 = 0.0, p1 = 0.0, q0 = 0.0, q1 = 0.0;
-#pragma unroll
-                for (int u = 0; u < 8; u += 2) {
-                    p0 += sD[i][m0 + u] * xv[u];
-                    p1 += sD[i][m0 + u + 1] * xv[u + 1];
-                    if (two) { q0 += sD[i2][m0 + u] * xv[u]; q1 += sD[i2][m0 + u + 1] * xv[u + 1]; }
-                }
-                sI[i * CH_LDT + c] += p0 + p1;
-                if (two) sI[i2 * CH_LDT + c] += q0 + q1;
+        // Inv[R][C] = -Inv[R][R] * tmp[R][C]
+        for (int tt = warp; tt < ntile; tt += CH_THREADS / 32) {
+            const int pr = tt / tpp, ta = (tt % tpp) / tpd, tb = tt % tpd;
+            const int R0 = (2 * pr + 1) * h, C0 = 2 * pr * h;
+            double d0 = 0.0, d1 = 0.0;
+            for (int k4 = 0; k4 < h / 4; ++k4) {
+                const double a = sI[(R0 + ta * 8 + g) * CH_LDT + R0 + k4 * 4 + t4];
+                const double bv = tmp[(R0 + k4 * 4 + t4) * CH_LDT + C0 + tb * 8 + g];
+                dmma884(d0, d1, a, bv);
             }
+            sI[(R0 + ta * 8 + g) * CH_LDT + C0 + tb * 8 + 2 * t4] = -d0;
+            sI[(R0 + ta * 8 + g) * CH_LDT + C0 + tb * 8 + 2 * t4 + 1] = -d1;
         }
         __syncthreads();
     }
@@ -792,6 +850,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     double* bufB = bufA + CH_NB * CH_LDT;
     double* sI = bufB + CH_NB * CH_LDT;                            // L_kk^-1 of the panel this CTA is working with
     __shared__ int s_ok, own_n;
+    __shared__ CholScratch cs;
     __shared__ unsigned short own_i[CH_MAXOWN], own_j[CH_MAXOWN];
     __shared__ double rdiag[CH_NB];
     __shared__ double sx[2][CH_NB];
@@ -861,9 +920,9 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                 }
                 __syncthreads();
                 DG_T(0);
-                chol_block(sD, w, &s_ok, rdiag);
+                chol_block(sD, w, &s_ok, rdiag, &cs);
                 DG_T(1);
-                tri_inverse_block(sD, rdiag, w, sI);
+                tri_inverse_block(sD, rdiag, w, sI, bufA);
                 DG_T(2);
                 for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
                     const int r = e >> 6, c2 = e & 63;

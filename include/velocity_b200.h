@@ -187,6 +187,18 @@ size_t vel_ba_solve_workspace(int32_t nt, int32_t nc);
 int vel_ba_solve(const double* V, const double* U, const double* W, const double* g, int32_t nt, int32_t nc, double* x,
                  double* rms_delta, void* work, size_t work_bytes, vel_stream_t stream);
 
+/* K7 + K8 as one device-resident loop: the whole `for i in range(10)` of fcnNLS_batch (utils/NLS.py:222-242) -- residuals, the
+ * block-sparse forward-difference normal equations, the Schur solve, x += 0.9 delta and the `rms(delta) < tol: break` test (:238),
+ * the test evaluated ON THE DEVICE: max_iter iterations are enqueued back to back, every kernel of an iteration returns at once
+ * after the test has passed, and nothing synchronises with the host.  x [nt*3 + nc*6] is updated in place (layout as above).
+ *   hist [max_iter][2] (DEVICE)  row i = (sum of squared residuals before update i, rms(delta_i)); NaN rows = not run
+ *   iters_run[1]       (DEVICE)  number of iterations that ran
+ * A failed Cholesky of the reduced system makes rms(delta) NaN for that iteration.  The cross blocks exist only in the scaled form
+ * W' = W blockdiag(chol((V_i+I)^-1)) inside `work` (vel_ba_iterate_workspace(nt, nc) bytes, 256-byte aligned). */
+size_t vel_ba_iterate_workspace(int32_t nt, int32_t nc);
+int vel_ba_iterate(const double* K, const double* z, int32_t nt, int32_t nc, double* x, int32_t max_iter, double tol, double* hist,
+                   int32_t* iters_run, void* work, size_t work_bytes, vel_stream_t stream);
+
 /* K8 in three stages, for the camera-sharded form: every rank accumulates its cameras (vel_ba_accumulate with a
  * camera slice), the point blocks are all-reduced and the camera rows all-gathered; then
  *   vel_ba_reduce   per-point (V+I)^-1 factors, W' = W blockdiag(L), the rank's TILE ROWS [blk_lo, blk_hi) of the reduced camera

@@ -22,3 +22,19 @@ for it in range(4):
     e[0].record(); ba.accumulate(); e[1].record(); ba.solve(); e[2].record()
     torch.cuda.synchronize()
     print("it %d: accumulate %.3f ms, solve %.3f ms, rms_delta %.3e" % (it, e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), ba.rms_delta.item()))
+
+# the device-resident loop (vel_ba_iterate): 10 iterations enqueued at once, no host synchronisation in between (tol = 0: all run)
+lb = NLS.BundleAdjuster(K, z, x, NT, F - 1)
+lb.iterate(2, 0.0)
+for rep in range(3):
+    lb.reset(z, x)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(); h = lb.iterate(10, 0.0); e1.record()
+    torch.cuda.synchronize()
+    print("device loop: %d iterations, %.3f ms per iteration (events), %.3f ms wall; rms_delta %s" % (
+        len(h), e0.elapsed_time(e1) / len(h), (time.perf_counter() - t0) * 1e3 / len(h), " ".join("%.2e" % r for _, r in h[:5])))
+print("max |x_loop - x_stepwise| after 4 iterations:", end=" ")
+lb.reset(z, x); lb.iterate(4, 0.0)
+print(float((lb.x - ba.x).abs().max()))

@@ -105,17 +105,36 @@ class BundleAdjuster:
         if shard and torch.distributed.is_available() and torch.distributed.is_initialized():
             self.rank, self.world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
         self.per, self.slices = camera_slices(nc, self.world)
+        self.rms_delta = torch.zeros((1,), dtype=torch.float64, device=dev)
+        self.timing = None
+        self._staged = False
+        if self.world > 1:
+            self._stage_buffers()
+
+    _STAGED = ("small", "cost", "V", "g", "U", "W_ext", "W", "work", "S", "rhs", "blocks", "row_ranges")
+
+    def __getattr__(self, name):            # only reached when normal lookup fails: the lazily allocated stage buffers
+        if name in BundleAdjuster._STAGED and not self.__dict__.get("_staged", True):
+            self._stage_buffers()
+            if name in self.__dict__:
+                return self.__dict__[name]
+        raise AttributeError(name)
+
+    def _stage_buffers(self):
+        """Buffers of the stage-by-stage form (accumulate / solve / step): the K7 blocks and the K8 workspace.  iterate() keeps
+        its own single workspace (the cross blocks exist only in scaled form there), so these are allocated on first use."""
+        if self._staged:
+            return
+        self._staged = True
+        nt, nc, dev, L = self.nt, self.nc, self.x.device, _lib.lib()
         self.small, self.cost, self.V, self.g, self.U = small_buffer(nt, nc, dev)
         # one 6-row block per camera 0..per*world-1 (camera 0's block is padding); the solver's W starts at camera 1
         self.W_ext = torch.zeros((6 * self.per * self.world, 3 * nt), dtype=torch.float64, device=dev)
         self.W = self.W_ext[6:]
-        self.rms_delta = torch.zeros((1,), dtype=torch.float64, device=dev)
-        L = _lib.lib()
         nbytes = int(L.vel_ba_solve_workspace(nt, nc))
         if nbytes == 0:
             raise RuntimeError("vel_ba_solve_workspace failed: %s" % L.vel_last_error().decode())
         self.work = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
-        self.timing = None
         if self.world > 1:
             off_S, off_rhs = C.c_int64(0), C.c_int64(0)
             _lib.check(L.vel_ba_solve_layout(nt, nc, C.byref(off_S), C.byref(off_rhs)), "vel_ba_solve_layout")
@@ -150,6 +169,7 @@ class BundleAdjuster:
 
     def accumulate(self):
         L = _lib.lib()
+        self._stage_buffers()
         first, count = self.slices[self.rank]
         self._t("begin")
         if self.world > 1:
@@ -163,6 +183,7 @@ class BundleAdjuster:
 
     def solve(self):
         L = _lib.lib()
+        self._stage_buffers()
         if self.world == 1:
             _lib.check(L.vel_ba_solve(ptr(self.V), ptr(self.U), ptr(self.W), ptr(self.g), self.nt, self.nc, ptr(self.x),
                                       ptr(self.rms_delta), ptr(self.work), self.work.numel(), stream_ptr()), "vel_ba_solve")
@@ -183,6 +204,40 @@ class BundleAdjuster:
         _lib.check(L.vel_ba_update(ptr(self.W), self.nt, self.nc, ptr(self.x), ptr(self.rms_delta), ptr(self.work), self.work.numel(),
                                    stream_ptr()), "vel_ba_update")
         self._t("update")
+
+    def iterate(self, max_iter=10, tol=1e-7):
+        """The reference's whole iteration loop (utils/NLS.py:222-242) enqueued at once: the `rms(delta) < tol: break` test runs
+        on the device (vel_ba_iterate), the host reads the history back afterwards.  Returns [(f, rms(delta)), ...] for the
+        iterations that ran -- the same ones a step-by-step loop with a host-side test would run.  Single rank only."""
+        if self.world != 1:
+            raise RuntimeError("BundleAdjuster.iterate: the sharded form exchanges blocks between stages -- use step()")
+        L = _lib.lib()
+        assert max_iter <= 64
+        self._t("begin")
+        _lib.check(L.vel_ba_iterate(ptr(self.K), ptr(self.z), self.nt, self.nc, ptr(self.x), max_iter, float(tol), *self.loop_buffers(),
+                                    stream_ptr()), "vel_ba_iterate")
+        self._t("iterate")
+        return self.history(max_iter)
+
+    def loop_buffers(self):
+        """(hist, iters_run, work, work_bytes) arguments of vel_ba_iterate, allocated on first use"""
+        if getattr(self, "_loop_work", None) is None:
+            nbytes = int(_lib.lib().vel_ba_iterate_workspace(self.nt, self.nc))
+            if nbytes == 0:
+                raise RuntimeError("vel_ba_iterate_workspace failed: %s" % _lib.lib().vel_last_error().decode())
+            self._loop_work = torch.empty((nbytes,), dtype=torch.uint8, device=self.x.device)
+            self._hist = torch.empty((64, 2), dtype=torch.float64, device=self.x.device)
+            self._iters = torch.zeros((1,), dtype=torch.int32, device=self.x.device)
+        return ptr(self._hist), ptr(self._iters), ptr(self._loop_work), self._loop_work.numel()
+
+    launches_per_loop_iteration = 10   # cam setup, point, reduce+prep, zero S, camera, SYRK, Cholesky, GEMV, update, finalize
+
+    def history(self, max_iter):
+        """[(f, rms(delta))] of the last iterate() call (synchronises on the readback)."""
+        h = self._hist[:max_iter].cpu().numpy()
+        nz = 2 * self.nt * (self.nc + 1)
+        ran = int(np.isfinite(h[:, 0]).sum())
+        return [(float(np.sqrt(h[i, 0] / nz)), float(h[i, 1])) for i in range(ran)]
 
     def step(self):
         """One LM iteration.  Returns (f = rms(z - zhat) before the update, rms(delta))."""
@@ -208,18 +263,15 @@ def fcnNLS_batch(K, P, pw, cw):
     x0 = np.concatenate((np.asarray(pw, np.float64), np.asarray(cw, np.float64)[1:], np.zeros((nc, 3)))).ravel()
     ba = BundleAdjuster(np.asarray(K, float), z, x0, nt, nc)
     max_iter = 10
-    i = 0
     tic = time.time()
-    f = float("nan")
-    for i in range(max_iter):
-        tic = time.time()
-        f, xr = ba.step()
-        print(f"{i:g}: {time.time() - tic:.3f}s, f={f:g}, x={xr}")
-        if xr < 1e-7:
-            break
-    else:
+    hist = ba.iterate(max_iter, 1e-7)              # the loop of utils/NLS.py:222-242, convergence test on the device
+    dt = (time.time() - tic) / max(len(hist), 1)
+    i, f = len(hist) - 1, float("nan")
+    for i, (f, xr) in enumerate(hist):
+        print(f"{i:g}: {dt:.3f}s, f={f:g}, x={xr}")
+    if not hist or not hist[-1][1] < 1e-7:
         print("WARNING: fcnNLS_batch() reaching max iterations!")
-    print(f"fcnNLS_batch done in {i:g} steps, {time.time() - tic:.3f}s, f={f:g}")
+    print(f"fcnNLS_batch done in {i:g} steps, {dt:.3f}s, f={f:g}")
     x = ba.x.cpu().numpy()
     j = nt * 3
     pw_out = x[:j].reshape(nt, 3)

@@ -60,6 +60,8 @@ SIGNATURES = {
     "vel_ba_accumulate": (C.c_int, [_P, _P, _P, _I32, _I32, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vel_ba_solve_workspace": (C.c_size_t, [_I32, _I32]),
     "vel_ba_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
+    "vel_ba_iterate_workspace": (C.c_size_t, [_I32, _I32]),
+    "vel_ba_iterate": (C.c_int, [_P, _P, _I32, _I32, _P, _I32, C.c_double, _P, _P, _P, C.c_size_t, _P]),
     "vel_syrk_lower_sub_workspace": (C.c_size_t, [_I32, _I32]),
     "vel_syrk_lower_sub": (C.c_int, [_P, _I64, _I32, _I32, _P, _I64, _P, C.c_size_t, _P]),
     "vel_syrk_tile_rows": (C.c_int, [_I32, C.POINTER(_I32), C.POINTER(_I32)]),

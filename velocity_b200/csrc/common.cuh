@@ -45,6 +45,11 @@ void vel_keep_async_pool_cached();
 
 // dense_f64.cu: bytes of scratch vel_syrk_lower_sub needs for an m x k operand (ba.cu sizes its workspace with it)
 size_t vel_dense_syrk_workspace(int m, int k);
+// dense_f64.cu: vel_syrk_lower_sub_rows / vel_spd_solve with a device-side gate (NULL = always run): when *gate != 0 at launch
+// time the kernels return immediately.  ba_loop.cu enqueues a whole iteration loop and lets the convergence test close the gate.
+int vel_dense_syrk_rows_gated(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                              int32_t blk_lo, int32_t blk_hi, const int* gate, vel_stream_t stream);
+int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int32_t* info, const int* gate, vel_stream_t stream);
 
 static constexpr int kNumSMs = 148;  // B200
 

@@ -158,8 +158,9 @@ __device__ __forceinline__ void syrk_ktile_nt(double (&acc)[4][4][2], const doub
 // E [m][ld] row-major, K contiguous (ld even, rows 16-byte aligned, columns k..ld-1 of the last k-tile readable and ZERO)
 __global__ void __launch_bounds__(SY_THREADS, 1)
 dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb, int bme, int ntiles, int sk, int ktiles,
-                       double* __restrict__ S, long long lds, int* __restrict__ flags, int tile0)
+                       double* __restrict__ S, long long lds, int* __restrict__ flags, int tile0, const int* __restrict__ gate)
 {
+    if (gate && *gate) return;                                   // device-side loop control (vel_ba_iterate): the whole grid leaves
     extern __shared__ __align__(16) double sy_smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
@@ -841,8 +842,10 @@ __device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bu
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
-chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, double* Linv_g)
+chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, double* Linv_g,
+                const int* __restrict__ gate)
 {
+    if (gate && *gate) return;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double ch_smem[];
     double (*sD)[CH_LD] = reinterpret_cast<double (*)[CH_LD]>(ch_smem);
@@ -1103,8 +1106,9 @@ VEL_API int vel_syrk_tile_rows(int32_t m, int32_t* nb, int32_t* rows_per_block)
     return VEL_OK;
 }
 
-VEL_API int vel_syrk_lower_sub_rows(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
-                                    int32_t blk_lo, int32_t blk_hi, vel_stream_t stream)
+// gate (DEVICE, may be NULL): when *gate != 0 at launch the kernel returns at once -- the device-side loop control of vel_ba_iterate
+int vel_dense_syrk_rows_gated(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                              int32_t blk_lo, int32_t blk_hi, const int* gate, vel_stream_t stream)
 {
     VEL_CHECK_ARG(E && S && work, "vel_syrk_lower_sub: NULL argument");
     VEL_CHECK_ARG(m > 0 && k > 0 && lds >= m, "vel_syrk_lower_sub: bad sizes m=%d k=%d lds=%lld", m, k, (long long)lds);
@@ -1125,10 +1129,16 @@ VEL_API int vel_syrk_lower_sub_rows(const double* E, int64_t ld, int32_t m, int3
     }
     long long ld_ = ld, lds_ = lds;
     int m_ = m, nb = p.nb, bme = p.bme, ntiles = p.ntiles, sk = p.sk, ktiles = p.ktiles, tile0 = p.tile0;
-    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags, &tile0};
+    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags, &tile0, (void*)&gate};
     // co-residency of the whole grid is what makes the turnstile wait safe: cooperative launch guarantees it (or fails)
     VEL_CUDA(cudaLaunchCooperativeKernel((void*)dsyrk_lower_sub_kernel, dim3(p.grid), dim3(SY_THREADS), args, SY_SMEM, st));
     return VEL_OK;
+}
+
+VEL_API int vel_syrk_lower_sub_rows(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
+                                    int32_t blk_lo, int32_t blk_hi, vel_stream_t stream)
+{
+    return vel_dense_syrk_rows_gated(E, ld, m, k, S, lds, work, work_bytes, blk_lo, blk_hi, nullptr, stream);
 }
 
 VEL_API int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double* S, int64_t lds, void* work, size_t work_bytes,
@@ -1148,7 +1158,7 @@ VEL_API void vel_chol_timing(unsigned long long* out8, int reset)
 }
 #endif
 
-VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream)
+int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int32_t* info, const int* gate, vel_stream_t stream)
 {
     VEL_CHECK_ARG(S && b && info, "vel_spd_solve: NULL argument");
     VEL_CHECK_ARG(n > 0 && lds >= n, "vel_spd_solve: bad sizes n=%d lds=%lld", n, (long long)lds);
@@ -1171,6 +1181,10 @@ VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t*
     const int nblk = (n + CH_NB - 1) / CH_NB;
     long long lds_ = lds;
     int n_ = n;
+    if (gate && !use_dag) {
+        vel_set_error("vel_spd_solve: the barrier form (VEL_CHOL=sync or a very large system) has no gated variant");
+        return VEL_ERR_INVALID;
+    }
     if (!use_dag) {
         int grid = max_grid;
         const int want = nblk * (nblk + 1) / 2 + nblk;          // tiles of the first trailing update
@@ -1195,7 +1209,7 @@ VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t*
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
     if (e == cudaSuccess) {
-        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&Linv_g};
+        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&Linv_g, (void*)&gate};
         e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
     }
     cudaFreeAsync(scratch, st);
@@ -1204,4 +1218,9 @@ VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t*
         return VEL_ERR_CUDA;
     }
     return VEL_OK;
+}
+
+VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream)
+{
+    return vel_dense_spd_solve_gated(S, lds, n, b, info, nullptr, stream);
 }

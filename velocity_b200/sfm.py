@@ -165,24 +165,23 @@ class SfmSequence:
             self.ba = BundleAdjuster(self.K, z, x0, nsel, n - 1)
         else:
             self.ba.reset(z, x0)
-        hist = []
-        for it in range(self.ba_iters):
-            f, xr = self.ba.step()
-            hist.append((f, xr))
-            if verbose:
-                print(f"{it:g}: f={f:g}, x={xr}")
-            if xr < 1e-7:
-                break
-        else:
-            if verbose:
-                print("WARNING: fcnNLS_batch() reaching max iterations!")
-        self.launches += self.ba.launches_per_step * len(hist)
+        # the whole iteration loop is enqueued at once (convergence test on the device); what follows does not depend on how many
+        # iterations ran, so it is enqueued behind it and the history is read back last
+        self.ba.timing = None
+        _lib.check(L.vel_ba_iterate(ptr(self.ba.K), ptr(self.ba.z), nsel, n - 1, ptr(self.ba.x), self.ba_iters, 1e-7, *self.ba.loop_buffers(),
+                                    stream_ptr()), "vel_ba_iterate")
         # B[:, 3:6] = cw (the commented call site, vidExample.py:157) on a copy, and the speed table that follows from it
         _lib.check(L.vel_seq_ba_cameras(ptr(self.ba.x), nsel, n, ptr(self.B), ptr(self.S), ptr(self.B_ba), ptr(self.S_ba), stream_ptr()),
                    "vel_seq_ba_cameras")
         _lib.check(L.vel_seq_stats(ptr(self.B_ba), ptr(self.alive), n, npts, ptr(self.S_ba), stream_ptr()), "vel_seq_stats")
-        self.launches += 2
         self._mark("bundle")
+        hist = self.ba.history(self.ba_iters)
+        if verbose:
+            for it, (f, xr) in enumerate(hist):
+                print(f"{it:g}: f={f:g}, x={xr}")
+            if not hist or not hist[-1][1] < 1e-7:
+                print("WARNING: fcnNLS_batch() reaching max iterations!")
+        self.launches += 1 + self.ba.launches_per_loop_iteration * len(hist) + 2
         return hist
 
     def export_P(self):

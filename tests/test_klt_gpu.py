@@ -56,6 +56,32 @@ def test_pyramid_batch_1080p_matches_oracle(cuda):
             assert np.array_equal(fb.level(i, l).cpu().numpy(), lvl), (i, l)
 
 
+@pytest.mark.parametrize("h,w", [(1080, 1920), (270, 480), (64, 64), (33, 48), (17, 32), (542, 976), (135, 1936)])
+def test_pyramid_fused_two_level_kernel_equals_level_by_level(cuda, monkeypatch, h, w):
+    """K1's fused kernel (levels 1 and 2 from one pass over the frame; widths that are multiples of 16) against the
+    level-by-level kernels and the oracle: even and odd level-1 heights (the bottom-edge reflection does not commute with
+    the filter), strips that hang over the image, single-warp and multi-warp rows, several frames per launch."""
+    from oracle import cv_oracle as O
+    from velocity_b200 import synth
+    from velocity_b200.lk import FrameBatch
+
+    rng = np.random.default_rng(h * 10007 + w)
+    frames = np.stack([synth.texture(h, w, 5) if h >= 64 and w >= 64 else rng.integers(0, 256, (h, w), dtype=np.uint8),
+                       rng.integers(0, 256, (h, w), dtype=np.uint8)])
+    d = cuda.from_numpy(frames).cuda()
+    monkeypatch.setenv("VEL_PYR_FUSED", "1")
+    fused = FrameBatch(d, (3, 3), 3).build()
+    monkeypatch.setenv("VEL_PYR_FUSED", "0")
+    plain = FrameBatch(d, (3, 3), 3).build()
+    assert fused.layout.max_level >= 2
+    for i in range(2):
+        lvl = frames[i]
+        for l in range(1, fused.layout.max_level + 1):
+            lvl = O.pyrDown(lvl)
+            assert np.array_equal(fused.level(i, l).cpu().numpy(), lvl), (i, l)
+            assert np.array_equal(plain.level(i, l).cpu().numpy(), lvl), (i, l)
+
+
 @pytest.mark.parametrize("name", LK_CASES)
 def test_lk_matches_oracle_bit_exact_and_reference_golden(cuda, name):
     from oracle import klt_oracle as KO

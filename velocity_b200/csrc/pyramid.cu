@@ -8,6 +8,8 @@
 //   BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2).
 //
 // Streaming, HBM-bound: algorithmic bytes per level = src bytes read once + dst bytes written once.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -184,6 +186,170 @@ pyrdown_strip_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
     }
 }
 
+// ---- fused two-level kernel: levels 1 AND 2 from one pass over the frame ------------------------------------------------
+// (source width a multiple of 16, 16-byte aligned rows: 1080p, 4K, ...)
+// Level 2 taps level-1 rows 2y-2..2y+2, so a thread that walks down the frame producing level-1 rows can emit level 2 from
+// the five most recent ones without level 1 ever being read back (67 MB per 129 1080p frames, and one launch instead of two).
+// Thread t owns 16 source columns = 8 level-1 columns = 4 level-2 columns and walks DOWN: per iteration four new source rows
+// (one 16-byte load each, the next four already in flight) -> two level-1 rows -> one level-2 row.  Horizontal halos come from
+// the neighbouring lanes by shuffle at BOTH levels; a warp therefore overlaps its neighbours by one lane on each side (lanes
+// 1..30 own columns and store, lanes 0 / 31 recompute the neighbours' level-1 columns; their own outer halo bytes are fetched
+// from memory).  Rows: a CTA produces H2 level-2 rows and the 2*H2 level-1 rows under them, plus three level-1 halo rows
+// (two above, one below) that are computed and not stored.  REFLECT_101: columns by byte selection at t = 0 / t = last; rows
+// by reflecting the (virtual) source row index -- which commutes with the symmetric filter at the top edge; below the bottom
+// edge it does not (even heights), so a level-1 row r >= h1 is recomputed from the five source rows of row 2*h1-2-r.
+constexpr int F2_WARPS = 2;                 // warps per CTA, side by side along x
+constexpr int F2_OWN = 30;                  // owner lanes per warp
+
+// horizontally filtered row of 16 source bytes: 8 outputs as packed 16-bit pairs; lo2 = the two bytes left of v, b16 = the byte right
+__device__ __forceinline__ uint4 hfilt16(const uint4 v, unsigned lo2, unsigned b16)
+{
+    const unsigned K = 0x04060401u;
+    const unsigned h0 = dp4a_uu(lo2 | (v.x << 16), K, (v.x >> 16) & 0xffu);
+    const unsigned h1 = dp4a_uu(v.x, K, v.y & 0xffu);
+    const unsigned h2 = dp4a_uu(__funnelshift_r(v.x, v.y, 16), K, (v.y >> 16) & 0xffu);
+    const unsigned h3 = dp4a_uu(v.y, K, v.z & 0xffu);
+    const unsigned h4 = dp4a_uu(__funnelshift_r(v.y, v.z, 16), K, (v.z >> 16) & 0xffu);
+    const unsigned h5 = dp4a_uu(v.z, K, v.w & 0xffu);
+    const unsigned h6 = dp4a_uu(__funnelshift_r(v.z, v.w, 16), K, (v.w >> 16) & 0xffu);
+    const unsigned h7 = dp4a_uu(v.w, K, b16);
+    return make_uint4(h0 | (h1 << 16), h2 | (h3 << 16), h4 | (h5 << 16), h6 | (h7 << 16));
+}
+
+// vertical [1 4 6 4 1] on packed 16-bit pairs, + 128, >> 8: two words of pairs -> four output bytes
+__device__ __forceinline__ unsigned vfilt4(unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned a4, unsigned b0, unsigned b1, unsigned b2,
+                                           unsigned b3, unsigned b4)
+{
+    const unsigned ax = a0 + a4 + ((a1 + a3) << 2) + a2 * 6u + 0x00800080u;
+    const unsigned ay = b0 + b4 + ((b1 + b3) << 2) + b2 * 6u + 0x00800080u;
+    return __byte_perm(ax, ay, 0x7531);
+}
+
+struct F2Args {
+    const uint8_t* src; long long src_stride; int sw, sh, spitch;
+    uint8_t* d1; long long d_stride; int w1, h1, p1;
+    uint8_t* d2; int w2, h2, p2;
+};
+
+template <int H2>
+__global__ void __launch_bounds__(32 * F2_WARPS)
+pyrdown2_fused_kernel(const F2Args A)
+{
+    const uint8_t* __restrict__ src = A.src + (long long)blockIdx.z * A.src_stride;
+    uint8_t* __restrict__ d1 = A.d1 + (long long)blockIdx.z * A.d_stride;
+    uint8_t* __restrict__ d2 = A.d2 + (long long)blockIdx.z * A.d_stride;
+    const int lane = threadIdx.x & 31, wx = blockIdx.x * F2_WARPS + (threadIdx.x >> 5);
+    const int nt = A.sw >> 4;                                   // threads that own real columns
+    const int t = wx * F2_OWN - 1 + lane;
+    const int tc = max(0, min(t, nt - 1));
+    const bool owner = lane >= 1 && lane <= F2_OWN && t < nt;   // t >= 0 follows from lane >= 1
+    const bool first = tc == 0, last = tc == nt - 1;
+    const int y2_0 = blockIdx.y * H2;
+    const int R0 = 2 * y2_0 - 2;                                // first (virtual) level-1 row of the strip
+    const int sh = A.sh, spitch = A.spitch;
+    const uint8_t* __restrict__ col = src + 16 * tc;
+    // rows never need more than one reflection here: |overshoot| <= 6 at the top, <= 4 at the bottom (sh >= 16 checked by the host)
+    const bool interior = 2 * R0 - 2 >= 0 && 2 * (R0 + 2 * (H2 + 1) + 1) + 2 < sh;
+
+    auto load_row = [&](int sv, uint4& v, unsigned& elo, unsigned& ehi) {
+        int yy = sv;
+        if (!interior) {
+            yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);
+            yy = max(0, min(yy, sh - 1));
+        }
+        const uint8_t* row = col + (long long)yy * spitch;
+        v = __ldg(reinterpret_cast<const uint4*>(row));
+        elo = (lane == 0 && !first) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(row - 2)) : 0u;
+        ehi = (lane == 31 && !last) ? (unsigned)__ldg(row + 16) : 0u;
+    };
+    auto filt_row = [&](const uint4 v, unsigned elo, unsigned ehi) -> uint4 {
+        unsigned lo2 = __shfl_up_sync(0xffffffffu, v.w, 1) >> 16;       // source columns 16t-2, 16t-1
+        unsigned b16 = __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffu;   // source column 16t+16
+        if (lane == 0) lo2 = elo;
+        if (first) lo2 = ((v.x >> 16) & 0xffu) | (((v.x >> 8) & 0xffu) << 8);                  // REFLECT_101 at column 0
+        if (lane == 31) b16 = ehi;
+        if (last) b16 = (v.w >> 16) & 0xffu;                                                   // REFLECT_101 at column sw
+        return hfilt16(v, lo2, b16);
+    };
+    // level-1 row (8 bytes in o0, o1) -> its horizontally filtered form for level 2 (4 outputs, two words of 16-bit pairs)
+    auto hfilt_l1 = [&](unsigned o0, unsigned o1) -> uint2 {
+        unsigned l2 = __shfl_up_sync(0xffffffffu, o1, 1) >> 16;         // level-1 columns 8t-2, 8t-1
+        unsigned r0 = __shfl_down_sync(0xffffffffu, o0, 1) & 0xffu;     // level-1 column 8t+8
+        if (t <= 0) l2 = ((o0 >> 16) & 0xffu) | (((o0 >> 8) & 0xffu) << 8);
+        if (t >= nt - 1) r0 = (o1 >> 16) & 0xffu;
+        const unsigned K = 0x04060401u;
+        const unsigned g0 = dp4a_uu(l2 | (o0 << 16), K, (o0 >> 16) & 0xffu);
+        const unsigned g1 = dp4a_uu(o0, K, o1 & 0xffu);
+        const unsigned g2 = dp4a_uu(__funnelshift_r(o0, o1, 16), K, (o1 >> 16) & 0xffu);
+        const unsigned g3 = dp4a_uu(o1, K, r0);
+        return make_uint2(g0 | (g1 << 16), g2 | (g3 << 16));
+    };
+    // a level-1 row computed from scratch (five source rows): only for virtual rows at or below the bottom edge
+    auto l1_row_direct = [&](int r1, unsigned& o0, unsigned& o1) {
+        uint4 f[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            int yy = 2 * r1 - 2 + k;
+            yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);
+            yy = max(0, min(yy, sh - 1));
+            const uint8_t* row = col + (long long)yy * spitch;
+            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row));
+            const unsigned elo = (lane == 0 && !first) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(row - 2)) : 0u;
+            const unsigned ehi = (lane == 31 && !last) ? (unsigned)__ldg(row + 16) : 0u;
+            f[k] = filt_row(v, elo, ehi);
+        }
+        o0 = vfilt4(f[0].x, f[1].x, f[2].x, f[3].x, f[4].x, f[0].y, f[1].y, f[2].y, f[3].y, f[4].y);
+        o1 = vfilt4(f[0].z, f[1].z, f[2].z, f[3].z, f[4].z, f[0].w, f[1].w, f[2].w, f[3].w, f[4].w);
+    };
+
+    // prologue: the three carried source rows 2*R0-2 .. 2*R0, and the first four rows of the loop in flight
+    uint4 c0, c1, c2;
+    {
+        uint4 v[3]; unsigned el[3], eh[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) load_row(2 * R0 - 2 + k, v[k], el[k], eh[k]);
+        c0 = filt_row(v[0], el[0], eh[0]); c1 = filt_row(v[1], el[1], eh[1]); c2 = filt_row(v[2], el[2], eh[2]);
+    }
+    uint4 nv[4]; unsigned nel[4], neh[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) load_row(2 * R0 + 1 + k, nv[k], nel[k], neh[k]);
+    uint2 q0 = make_uint2(0, 0), q1 = q0, q2 = q0, q3 = q0;        // level-2-filtered level-1 rows a_{j-2}, b_{j-2}, a_{j-1}, b_{j-1}
+
+#pragma unroll 1
+    for (int j = 0; j < H2 + 2; ++j) {
+        const int ra = R0 + 2 * j, rb = ra + 1;                    // the two (virtual) level-1 rows of this iteration
+        uint4 v[4]; unsigned el[4], eh[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { v[k] = nv[k]; el[k] = nel[k]; eh[k] = neh[k]; }
+        if (j + 1 < H2 + 2) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) load_row(2 * ra + 5 + k, nv[k], nel[k], neh[k]);
+        }
+        const uint4 f0 = filt_row(v[0], el[0], eh[0]), f1 = filt_row(v[1], el[1], eh[1]);
+        const uint4 f2 = filt_row(v[2], el[2], eh[2]), f3 = filt_row(v[3], el[3], eh[3]);
+        unsigned a0 = vfilt4(c0.x, c1.x, c2.x, f0.x, f1.x, c0.y, c1.y, c2.y, f0.y, f1.y);
+        unsigned a1 = vfilt4(c0.z, c1.z, c2.z, f0.z, f1.z, c0.w, c1.w, c2.w, f0.w, f1.w);
+        unsigned b0 = vfilt4(c2.x, f0.x, f1.x, f2.x, f3.x, c2.y, f0.y, f1.y, f2.y, f3.y);
+        unsigned b1 = vfilt4(c2.z, f0.z, f1.z, f2.z, f3.z, c2.w, f0.w, f1.w, f2.w, f3.w);
+        c0 = f1; c1 = f2; c2 = f3;
+        if (!interior) {                                           // rows at / below the bottom edge: level-1 row 2*h1-2-r instead
+            if (ra >= A.h1) l1_row_direct(2 * A.h1 - 2 - ra, a0, a1);
+            if (rb >= A.h1) l1_row_direct(2 * A.h1 - 2 - rb, b0, b1);
+        }
+        if (owner && j >= 1 && j <= H2) {
+            if (ra < A.h1) *reinterpret_cast<uint2*>(d1 + (long long)ra * A.p1 + 8 * t) = make_uint2(a0, a1);
+            if (rb < A.h1) *reinterpret_cast<uint2*>(d1 + (long long)rb * A.p1 + 8 * t) = make_uint2(b0, b1);
+        }
+        const uint2 ga = hfilt_l1(a0, a1), gb = hfilt_l1(b0, b1);
+        if (j >= 2) {
+            const int y2 = y2_0 + j - 2;
+            const unsigned o = vfilt4(q0.x, q1.x, q2.x, q3.x, ga.x, q0.y, q1.y, q2.y, q3.y, ga.y);
+            if (owner && y2 < A.h2) *reinterpret_cast<unsigned*>(d2 + (long long)y2 * A.p2 + 4 * t) = o;
+        }
+        q0 = q2; q1 = q3; q2 = ga; q3 = gb;
+    }
+}
+
 __global__ void decimate4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst,
                                  int dw, int dh, int dpitch)
 {
@@ -231,7 +397,29 @@ VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t 
     if (L->max_level == 0) return VEL_OK;
     VEL_CHECK_ARG(pyr != nullptr && pyr_stride >= L->bytes, "vel_pyramid_u8: pyramid buffer missing or stride too small");
     cudaStream_t st = (cudaStream_t)stream;
-    for (int l = 1; l <= L->max_level; ++l) {
+    int l_first = 1;
+    {   // levels 1 and 2 in one pass over the frames (VEL_PYR_FUSED=0 keeps the level-by-level kernels: the cross-check of the tests)
+        const char* env = getenv("VEL_PYR_FUSED");
+        const bool fused_on = !(env && env[0] == '0');
+        const int sw = L->width[0], sh = L->height[0];
+        const bool ok = fused_on && L->max_level >= 2 && sw % 16 == 0 && sw >= 32 && sh >= 16 && pitch % 16 == 0 &&
+                        ((((uintptr_t)frames) | (uintptr_t)frame_stride) & 15) == 0 &&
+                        ((((uintptr_t)(pyr + L->offset[1])) | (uintptr_t)pyr_stride | (uintptr_t)L->pitch[1]) & 7) == 0 &&
+                        ((((uintptr_t)(pyr + L->offset[2])) | (uintptr_t)L->pitch[2]) & 3) == 0;
+        if (ok) {
+            F2Args A;
+            A.src = frames; A.src_stride = frame_stride; A.sw = sw; A.sh = sh; A.spitch = pitch;
+            A.d1 = pyr + L->offset[1]; A.d_stride = pyr_stride; A.w1 = L->width[1]; A.h1 = L->height[1]; A.p1 = L->pitch[1];
+            A.d2 = pyr + L->offset[2]; A.w2 = L->width[2]; A.h2 = L->height[2]; A.p2 = L->pitch[2];
+            const int nt = sw / 16, warps = (nt + F2_OWN - 1) / F2_OWN;
+            constexpr int H2 = 16;
+            dim3 grid((warps + F2_WARPS - 1) / F2_WARPS, (A.h2 + H2 - 1) / H2, nframes);
+            pyrdown2_fused_kernel<H2><<<grid, 32 * F2_WARPS, 0, st>>>(A);
+            VEL_LAUNCH_CHECK("pyrdown2_fused_kernel");
+            l_first = 3;
+        }
+    }
+    for (int l = l_first; l <= L->max_level; ++l) {
         const uint8_t* src = l == 1 ? frames : pyr + L->offset[l - 1];
         const long long sstride = l == 1 ? frame_stride : pyr_stride;
         const int spitch = l == 1 ? pitch : L->pitch[l - 1];

@@ -59,6 +59,16 @@ class FrameBatch:
         self.built = True
         return self
 
+    def pyramid_launches(self):
+        """Kernel launches of one build(): levels 1 and 2 share one fused kernel when the frames are 16-byte aligned rows of a
+        width that is a multiple of 16 (csrc/pyramid.cu), every further level is one launch."""
+        import os
+
+        lv = self.layout.max_level
+        fused = (lv >= 2 and self.w % 16 == 0 and self.w >= 32 and self.h >= 16 and self.pitch % 16 == 0
+                 and self.frames.data_ptr() % 16 == 0 and self.frame_stride % 16 == 0 and os.environ.get("VEL_PYR_FUSED", "1")[:1] != "0")
+        return lv - 1 if fused else lv
+
     def level(self, i, l):
         """Level l of frame i as a [h, w] uint8 view (for tests)."""
         if l == 0:

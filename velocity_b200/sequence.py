@@ -96,7 +96,7 @@ class SequenceTracker:
             fb = self.batches[s]
             sub = fb if n == self.chunk else self._sub_batch(fb, n + 1)
             sub.build()
-            self.launches += sub.layout.max_level
+            self.launches += sub.pyramid_launches()
             out, st, err, _ = track_pairs(sub, sub, pts, self.params, 0, 1, n)
             self.launches += 1
             lo = c * self.chunk

@@ -84,7 +84,7 @@ class SfmSequence:
             _lib.check(L.vel_pyramid_u8(C.c_void_p(fr.data_ptr() + pyr_lo * fr.stride(0)), fr.stride(0), fr.stride(1), hi - pyr_lo + 1,
                                         C.byref(fb.layout), C.c_void_p(fb.pyr.data_ptr() + pyr_lo * fb.pyr.stride(0)), fb.pyr.stride(0),
                                         stream_ptr()), "vel_pyramid_u8")
-            self.launches += fb.layout.max_level
+            self.launches += fb.pyramid_launches()
         nfr = hi - lo + 1
         if nfr >= 2:
             _lib.check(L.vel_klt_sequence(C.c_void_p(fr.data_ptr() + lo * fr.stride(0)), fr.stride(0), fr.stride(1),

@@ -201,19 +201,35 @@ pyrdown_strip_kernel(const uint8_t* __restrict__ src_base, long long src_stride,
 constexpr int F2_WARPS = 2;                 // warps per CTA, side by side along x
 constexpr int F2_OWN = 30;                  // owner lanes per warp
 
-// horizontally filtered row of 16 source bytes: 8 outputs as packed 16-bit pairs; lo2 = the two bytes left of v, b16 = the byte right
-__device__ __forceinline__ uint4 hfilt16(const uint4 v, unsigned lo2, unsigned b16)
+// horizontally filtered row of 16 source bytes: 8 outputs as packed 16-bit pairs.  pw = the word LEFT of v (its two top bytes are
+// source columns -2, -1), nx = the word RIGHT of v (its low byte is column 16).  Output m taps bytes 2m-2 .. 2m+2:
+// [1 4 6 4] on the word starting at byte 2m-2 plus byte 2 of the word starting at byte 2m -- two dp4a, no byte extraction.
+__device__ __forceinline__ uint4 hfilt16(const uint4 v, unsigned pw, unsigned nx)
 {
-    const unsigned K = 0x04060401u;
-    const unsigned h0 = dp4a_uu(lo2 | (v.x << 16), K, (v.x >> 16) & 0xffu);
-    const unsigned h1 = dp4a_uu(v.x, K, v.y & 0xffu);
-    const unsigned h2 = dp4a_uu(__funnelshift_r(v.x, v.y, 16), K, (v.y >> 16) & 0xffu);
-    const unsigned h3 = dp4a_uu(v.y, K, v.z & 0xffu);
-    const unsigned h4 = dp4a_uu(__funnelshift_r(v.y, v.z, 16), K, (v.z >> 16) & 0xffu);
-    const unsigned h5 = dp4a_uu(v.z, K, v.w & 0xffu);
-    const unsigned h6 = dp4a_uu(__funnelshift_r(v.z, v.w, 16), K, (v.w >> 16) & 0xffu);
-    const unsigned h7 = dp4a_uu(v.w, K, b16);
-    return make_uint4(h0 | (h1 << 16), h2 | (h3 << 16), h4 | (h5 << 16), h6 | (h7 << 16));
+    const unsigned K = 0x04060401u, K5 = 0x00010000u;
+    const unsigned wm2 = __funnelshift_r(pw, v.x, 16), w2 = __funnelshift_r(v.x, v.y, 16), w6 = __funnelshift_r(v.y, v.z, 16);
+    const unsigned w10 = __funnelshift_r(v.z, v.w, 16), w14 = __funnelshift_r(v.w, nx, 16);
+    const unsigned h0 = dp4a_uu(v.x, K5, dp4a_uu(wm2, K, 0u));
+    const unsigned h1 = dp4a_uu(w2, K5, dp4a_uu(v.x, K, 0u));
+    const unsigned h2 = dp4a_uu(v.y, K5, dp4a_uu(w2, K, 0u));
+    const unsigned h3 = dp4a_uu(w6, K5, dp4a_uu(v.y, K, 0u));
+    const unsigned h4 = dp4a_uu(v.z, K5, dp4a_uu(w6, K, 0u));
+    const unsigned h5 = dp4a_uu(w10, K5, dp4a_uu(v.z, K, 0u));
+    const unsigned h6 = dp4a_uu(v.w, K5, dp4a_uu(w10, K, 0u));
+    const unsigned h7 = dp4a_uu(w14, K5, dp4a_uu(v.w, K, 0u));
+    return make_uint4(__byte_perm(h0, h1, 0x5410), __byte_perm(h2, h3, 0x5410), __byte_perm(h4, h5, 0x5410), __byte_perm(h6, h7, 0x5410));
+}
+
+// the same for a level-1 row of 8 bytes (o0, o1): 4 outputs
+__device__ __forceinline__ uint2 hfilt8(unsigned o0, unsigned o1, unsigned pw, unsigned nx)
+{
+    const unsigned K = 0x04060401u, K5 = 0x00010000u;
+    const unsigned wm2 = __funnelshift_r(pw, o0, 16), w2 = __funnelshift_r(o0, o1, 16), w6 = __funnelshift_r(o1, nx, 16);
+    const unsigned g0 = dp4a_uu(o0, K5, dp4a_uu(wm2, K, 0u));
+    const unsigned g1 = dp4a_uu(w2, K5, dp4a_uu(o0, K, 0u));
+    const unsigned g2 = dp4a_uu(o1, K5, dp4a_uu(w2, K, 0u));
+    const unsigned g3 = dp4a_uu(w6, K5, dp4a_uu(o1, K, 0u));
+    return make_uint2(__byte_perm(g0, g1, 0x5410), __byte_perm(g2, g3, 0x5410));
 }
 
 // vertical [1 4 6 4 1] on packed 16-bit pairs, + 128, >> 8: two words of pairs -> four output bytes
@@ -231,58 +247,61 @@ struct F2Args {
     uint8_t* d2; int w2, h2, p2;
 };
 
-template <int H2>
-__global__ void __launch_bounds__(32 * F2_WARPS)
-pyrdown2_fused_kernel(const F2Args A)
+struct F2Row { uint4 v; unsigned elo, ehi; };      // one source row in flight: the thread's 16 bytes + the warp-edge halo words
+
+// INTERIOR: every source row of the strip lies inside the frame (row pointers are stepped, no reflection, no bottom-edge rows)
+template <int H2, bool INTERIOR>
+__device__ __forceinline__ void f2_strip(const F2Args& A, const uint8_t* __restrict__ src, uint8_t* __restrict__ d1, uint8_t* __restrict__ d2)
 {
-    const uint8_t* __restrict__ src = A.src + (long long)blockIdx.z * A.src_stride;
-    uint8_t* __restrict__ d1 = A.d1 + (long long)blockIdx.z * A.d_stride;
-    uint8_t* __restrict__ d2 = A.d2 + (long long)blockIdx.z * A.d_stride;
     const int lane = threadIdx.x & 31, wx = blockIdx.x * F2_WARPS + (threadIdx.x >> 5);
     const int nt = A.sw >> 4;                                   // threads that own real columns
     const int t = wx * F2_OWN - 1 + lane;
     const int tc = max(0, min(t, nt - 1));
     const bool owner = lane >= 1 && lane <= F2_OWN && t < nt;   // t >= 0 follows from lane >= 1
     const bool first = tc == 0, last = tc == nt - 1;
+    const bool edge_warp = __any_sync(0xffffffffu, first || last);
+    const bool ld_lo = lane == 0 && !first, ld_hi = lane == 31 && !last;
     const int y2_0 = blockIdx.y * H2;
     const int R0 = 2 * y2_0 - 2;                                // first (virtual) level-1 row of the strip
     const int sh = A.sh, spitch = A.spitch;
     const uint8_t* __restrict__ col = src + 16 * tc;
-    // rows never need more than one reflection here: |overshoot| <= 6 at the top, <= 4 at the bottom (sh >= 16 checked by the host)
-    const bool interior = 2 * R0 - 2 >= 0 && 2 * (R0 + 2 * (H2 + 1) + 1) + 2 < sh;
+    const uint8_t* __restrict__ rowp = col + (long long)(2 * R0 - 2) * spitch;      // INTERIOR: the next row to load
 
-    auto load_row = [&](int sv, uint4& v, unsigned& elo, unsigned& ehi) {
-        int yy = sv;
-        if (!interior) {
-            yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);
+    auto load_row = [&](int sv, F2Row& r) {
+        const uint8_t* row;
+        if (INTERIOR) {
+            row = rowp;
+            rowp += spitch;
+        } else {
+            int yy = sv < 0 ? -sv : (sv >= sh ? 2 * sh - 2 - sv : sv);
             yy = max(0, min(yy, sh - 1));
+            row = col + (long long)yy * spitch;
         }
-        const uint8_t* row = col + (long long)yy * spitch;
-        v = __ldg(reinterpret_cast<const uint4*>(row));
-        elo = (lane == 0 && !first) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(row - 2)) : 0u;
-        ehi = (lane == 31 && !last) ? (unsigned)__ldg(row + 16) : 0u;
+        r.v = __ldg(reinterpret_cast<const uint4*>(row));
+        r.elo = 0u; r.ehi = 0u;
+        if (ld_lo) r.elo = __ldg(reinterpret_cast<const unsigned*>(row - 4));     // columns 16t-4 .. 16t-1
+        if (ld_hi) r.ehi = __ldg(reinterpret_cast<const unsigned*>(row + 16));    // columns 16t+16 .. 16t+19
     };
-    auto filt_row = [&](const uint4 v, unsigned elo, unsigned ehi) -> uint4 {
-        unsigned lo2 = __shfl_up_sync(0xffffffffu, v.w, 1) >> 16;       // source columns 16t-2, 16t-1
-        unsigned b16 = __shfl_down_sync(0xffffffffu, v.x, 1) & 0xffu;   // source column 16t+16
-        if (lane == 0) lo2 = elo;
-        if (first) lo2 = ((v.x >> 16) & 0xffu) | (((v.x >> 8) & 0xffu) << 8);                  // REFLECT_101 at column 0
-        if (lane == 31) b16 = ehi;
-        if (last) b16 = (v.w >> 16) & 0xffu;                                                   // REFLECT_101 at column sw
-        return hfilt16(v, lo2, b16);
+    auto filt_row = [&](const F2Row& r) -> uint4 {
+        unsigned pw = __shfl_up_sync(0xffffffffu, r.v.w, 1);      // top bytes: source columns 16t-2, 16t-1
+        unsigned nx = __shfl_down_sync(0xffffffffu, r.v.x, 1);    // low byte: source column 16t+16
+        if (lane == 0) pw = r.elo;
+        if (lane == 31) nx = r.ehi;
+        if (edge_warp) {
+            if (first) pw = __byte_perm(r.v.x, 0u, 0x1200);       // REFLECT_101 at column 0: columns 2, 1
+            if (last) nx = __byte_perm(r.v.w, 0u, 0x0002);        // REFLECT_101 at column sw: column sw-2
+        }
+        return hfilt16(r.v, pw, nx);
     };
-    // level-1 row (8 bytes in o0, o1) -> its horizontally filtered form for level 2 (4 outputs, two words of 16-bit pairs)
+    // level-1 row (8 bytes in o0, o1) -> its horizontally filtered form for level 2
     auto hfilt_l1 = [&](unsigned o0, unsigned o1) -> uint2 {
-        unsigned l2 = __shfl_up_sync(0xffffffffu, o1, 1) >> 16;         // level-1 columns 8t-2, 8t-1
-        unsigned r0 = __shfl_down_sync(0xffffffffu, o0, 1) & 0xffu;     // level-1 column 8t+8
-        if (t <= 0) l2 = ((o0 >> 16) & 0xffu) | (((o0 >> 8) & 0xffu) << 8);
-        if (t >= nt - 1) r0 = (o1 >> 16) & 0xffu;
-        const unsigned K = 0x04060401u;
-        const unsigned g0 = dp4a_uu(l2 | (o0 << 16), K, (o0 >> 16) & 0xffu);
-        const unsigned g1 = dp4a_uu(o0, K, o1 & 0xffu);
-        const unsigned g2 = dp4a_uu(__funnelshift_r(o0, o1, 16), K, (o1 >> 16) & 0xffu);
-        const unsigned g3 = dp4a_uu(o1, K, r0);
-        return make_uint2(g0 | (g1 << 16), g2 | (g3 << 16));
+        unsigned pw = __shfl_up_sync(0xffffffffu, o1, 1);         // top bytes: level-1 columns 8t-2, 8t-1
+        unsigned nx = __shfl_down_sync(0xffffffffu, o0, 1);       // low byte: level-1 column 8t+8
+        if (edge_warp) {
+            if (t <= 0) pw = __byte_perm(o0, 0u, 0x1200);
+            if (t >= nt - 1) nx = __byte_perm(o1, 0u, 0x0002);
+        }
+        return hfilt8(o0, o1, pw, nx);
     };
     // a level-1 row computed from scratch (five source rows): only for virtual rows at or below the bottom edge
     auto l1_row_direct = [&](int r1, unsigned& o0, unsigned& o1) {
@@ -293,10 +312,11 @@ pyrdown2_fused_kernel(const F2Args A)
             yy = yy < 0 ? -yy : (yy >= sh ? 2 * sh - 2 - yy : yy);
             yy = max(0, min(yy, sh - 1));
             const uint8_t* row = col + (long long)yy * spitch;
-            const uint4 v = __ldg(reinterpret_cast<const uint4*>(row));
-            const unsigned elo = (lane == 0 && !first) ? (unsigned)__ldg(reinterpret_cast<const unsigned short*>(row - 2)) : 0u;
-            const unsigned ehi = (lane == 31 && !last) ? (unsigned)__ldg(row + 16) : 0u;
-            f[k] = filt_row(v, elo, ehi);
+            F2Row r;
+            r.v = __ldg(reinterpret_cast<const uint4*>(row));
+            r.elo = ld_lo ? __ldg(reinterpret_cast<const unsigned*>(row - 4)) : 0u;
+            r.ehi = ld_hi ? __ldg(reinterpret_cast<const unsigned*>(row + 16)) : 0u;
+            f[k] = filt_row(r);
         }
         o0 = vfilt4(f[0].x, f[1].x, f[2].x, f[3].x, f[4].x, f[0].y, f[1].y, f[2].y, f[3].y, f[4].y);
         o1 = vfilt4(f[0].z, f[1].z, f[2].z, f[3].z, f[4].z, f[0].w, f[1].w, f[2].w, f[3].w, f[4].w);
@@ -305,49 +325,68 @@ pyrdown2_fused_kernel(const F2Args A)
     // prologue: the three carried source rows 2*R0-2 .. 2*R0, and the first four rows of the loop in flight
     uint4 c0, c1, c2;
     {
-        uint4 v[3]; unsigned el[3], eh[3];
+        F2Row r[3];
 #pragma unroll
-        for (int k = 0; k < 3; ++k) load_row(2 * R0 - 2 + k, v[k], el[k], eh[k]);
-        c0 = filt_row(v[0], el[0], eh[0]); c1 = filt_row(v[1], el[1], eh[1]); c2 = filt_row(v[2], el[2], eh[2]);
+        for (int k = 0; k < 3; ++k) load_row(2 * R0 - 2 + k, r[k]);
+        c0 = filt_row(r[0]); c1 = filt_row(r[1]); c2 = filt_row(r[2]);
     }
-    uint4 nv[4]; unsigned nel[4], neh[4];
+    F2Row bufA[4], bufB[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) load_row(2 * R0 + 1 + k, nv[k], nel[k], neh[k]);
+    for (int k = 0; k < 4; ++k) load_row(2 * R0 + 1 + k, bufA[k]);
     uint2 q0 = make_uint2(0, 0), q1 = q0, q2 = q0, q3 = q0;        // level-2-filtered level-1 rows a_{j-2}, b_{j-2}, a_{j-1}, b_{j-1}
 
-#pragma unroll 1
-    for (int j = 0; j < H2 + 2; ++j) {
-        const int ra = R0 + 2 * j, rb = ra + 1;                    // the two (virtual) level-1 rows of this iteration
-        uint4 v[4]; unsigned el[4], eh[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { v[k] = nv[k]; el[k] = nel[k]; eh[k] = neh[k]; }
+    // iteration j: four source rows (cur; the next four are requested into nxt first) -> level-1 rows a_j, b_j -> level-2 row j-2
+    auto iteration = [&](int j, F2Row (&cur)[4], F2Row (&nxt)[4]) {
+        const int ra = R0 + 2 * j, rb = ra + 1;
         if (j + 1 < H2 + 2) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) load_row(2 * ra + 5 + k, nv[k], nel[k], neh[k]);
+            for (int k = 0; k < 4; ++k) load_row(2 * ra + 5 + k, nxt[k]);
         }
-        const uint4 f0 = filt_row(v[0], el[0], eh[0]), f1 = filt_row(v[1], el[1], eh[1]);
-        const uint4 f2 = filt_row(v[2], el[2], eh[2]), f3 = filt_row(v[3], el[3], eh[3]);
+        const uint4 f0 = filt_row(cur[0]), f1 = filt_row(cur[1]), f2 = filt_row(cur[2]), f3 = filt_row(cur[3]);
         unsigned a0 = vfilt4(c0.x, c1.x, c2.x, f0.x, f1.x, c0.y, c1.y, c2.y, f0.y, f1.y);
         unsigned a1 = vfilt4(c0.z, c1.z, c2.z, f0.z, f1.z, c0.w, c1.w, c2.w, f0.w, f1.w);
         unsigned b0 = vfilt4(c2.x, f0.x, f1.x, f2.x, f3.x, c2.y, f0.y, f1.y, f2.y, f3.y);
         unsigned b1 = vfilt4(c2.z, f0.z, f1.z, f2.z, f3.z, c2.w, f0.w, f1.w, f2.w, f3.w);
         c0 = f1; c1 = f2; c2 = f3;
-        if (!interior) {                                           // rows at / below the bottom edge: level-1 row 2*h1-2-r instead
+        if (!INTERIOR) {                                           // rows at / below the bottom edge: level-1 row 2*h1-2-r instead
             if (ra >= A.h1) l1_row_direct(2 * A.h1 - 2 - ra, a0, a1);
             if (rb >= A.h1) l1_row_direct(2 * A.h1 - 2 - rb, b0, b1);
         }
         if (owner && j >= 1 && j <= H2) {
-            if (ra < A.h1) *reinterpret_cast<uint2*>(d1 + (long long)ra * A.p1 + 8 * t) = make_uint2(a0, a1);
-            if (rb < A.h1) *reinterpret_cast<uint2*>(d1 + (long long)rb * A.p1 + 8 * t) = make_uint2(b0, b1);
+            uint8_t* o = d1 + (long long)ra * A.p1 + 8 * t;
+            if (INTERIOR || ra < A.h1) *reinterpret_cast<uint2*>(o) = make_uint2(a0, a1);
+            if (INTERIOR || rb < A.h1) *reinterpret_cast<uint2*>(o + A.p1) = make_uint2(b0, b1);
         }
         const uint2 ga = hfilt_l1(a0, a1), gb = hfilt_l1(b0, b1);
         if (j >= 2) {
             const int y2 = y2_0 + j - 2;
             const unsigned o = vfilt4(q0.x, q1.x, q2.x, q3.x, ga.x, q0.y, q1.y, q2.y, q3.y, ga.y);
-            if (owner && y2 < A.h2) *reinterpret_cast<unsigned*>(d2 + (long long)y2 * A.p2 + 4 * t) = o;
+            if (owner && (INTERIOR || y2 < A.h2)) *reinterpret_cast<unsigned*>(d2 + (long long)y2 * A.p2 + 4 * t) = o;
         }
         q0 = q2; q1 = q3; q2 = ga; q3 = gb;
+    };
+    static_assert((H2 & 1) == 0, "the loop is unrolled by two (ping-pong row buffers)");
+    const int jend = min(H2 + 2, A.h2 - y2_0 + 2);               // a strip that hangs over the frame stops after its last real level-2 row
+#pragma unroll 1
+    for (int j = 0; j < jend; j += 2) {
+        iteration(j, bufA, bufB);
+        iteration(j + 1, bufB, bufA);
     }
+}
+
+template <int H2>
+__global__ void __launch_bounds__(32 * F2_WARPS)
+pyrdown2_fused_kernel(const F2Args A)
+{
+    const uint8_t* __restrict__ src = A.src + (long long)blockIdx.z * A.src_stride;
+    uint8_t* __restrict__ d1 = A.d1 + (long long)blockIdx.z * A.d_stride;
+    uint8_t* __restrict__ d2 = A.d2 + (long long)blockIdx.z * A.d_stride;
+    const int R0 = 2 * (int)blockIdx.y * H2 - 2;
+    // rows never need more than one reflection: |overshoot| <= 6 at the top (sh >= 16 checked by the host); rows far below the frame
+    // (a strip that hangs over it) are clamped, their results are never stored
+    const bool interior = 2 * R0 - 2 >= 0 && 2 * (R0 + 2 * (H2 + 1) + 1) + 2 < A.sh;
+    if (interior) f2_strip<H2, true>(A, src, d1, d2);
+    else f2_strip<H2, false>(A, src, d1, d2);
 }
 
 __global__ void decimate4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst,
@@ -412,9 +451,21 @@ VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t 
             A.d1 = pyr + L->offset[1]; A.d_stride = pyr_stride; A.w1 = L->width[1]; A.h1 = L->height[1]; A.p1 = L->pitch[1];
             A.d2 = pyr + L->offset[2]; A.w2 = L->width[2]; A.h2 = L->height[2]; A.p2 = L->pitch[2];
             const int nt = sw / 16, warps = (nt + F2_OWN - 1) / F2_OWN;
-            constexpr int H2 = 16;
-            dim3 grid((warps + F2_WARPS - 1) / F2_WARPS, (A.h2 + H2 - 1) / H2, nframes);
-            pyrdown2_fused_kernel<H2><<<grid, 32 * F2_WARPS, 0, st>>>(A);
+            // rows per strip: 32 level-2 rows keep the halo rows (11 source rows per strip) below 9 % of the loads; small images
+            // take 16 so that the grid still fills the machine
+            const int gx = (warps + F2_WARPS - 1) / F2_WARPS;
+            const char* eh = getenv("VEL_PYR_H2");
+            const int h2sel = eh ? atoi(eh) : ((long long)gx * ((A.h2 + 31) / 32) * nframes >= 8ll * kNumSMs ? 32 : 16);
+            if (h2sel == 32) {
+                dim3 grid(gx, (A.h2 + 31) / 32, nframes);
+                pyrdown2_fused_kernel<32><<<grid, 32 * F2_WARPS, 0, st>>>(A);
+            } else if (h2sel == 24) {
+                dim3 grid(gx, (A.h2 + 23) / 24, nframes);
+                pyrdown2_fused_kernel<24><<<grid, 32 * F2_WARPS, 0, st>>>(A);
+            } else {
+                dim3 grid(gx, (A.h2 + 15) / 16, nframes);
+                pyrdown2_fused_kernel<16><<<grid, 32 * F2_WARPS, 0, st>>>(A);
+            }
             VEL_LAUNCH_CHECK("pyrdown2_fused_kernel");
             l_first = 3;
         }

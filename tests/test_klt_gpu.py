@@ -56,8 +56,10 @@ def test_pyramid_batch_1080p_matches_oracle(cuda):
             assert np.array_equal(fb.level(i, l).cpu().numpy(), lvl), (i, l)
 
 
-@pytest.mark.parametrize("h,w", [(1080, 1920), (270, 480), (64, 64), (33, 48), (17, 32), (542, 976), (135, 1936)])
-def test_pyramid_fused_two_level_kernel_equals_level_by_level(cuda, monkeypatch, h, w):
+@pytest.mark.parametrize("h,w,strip", [(1080, 1920, None), (270, 480, None), (64, 64, None), (33, 48, None), (17, 32, None), (542, 976, None),
+                                       (135, 1936, None), (1080, 1920, 32), (542, 976, 32), (135, 1936, 32), (270, 480, 32), (2160, 3840, 32),
+                                       (1080, 1920, 24)])
+def test_pyramid_fused_two_level_kernel_equals_level_by_level(cuda, monkeypatch, h, w, strip):
     """K1's fused kernel (levels 1 and 2 from one pass over the frame; widths that are multiples of 16) against the
     level-by-level kernels and the oracle: even and odd level-1 heights (the bottom-edge reflection does not commute with
     the filter), strips that hang over the image, single-warp and multi-warp rows, several frames per launch."""
@@ -70,6 +72,8 @@ def test_pyramid_fused_two_level_kernel_equals_level_by_level(cuda, monkeypatch,
                        rng.integers(0, 256, (h, w), dtype=np.uint8)])
     d = cuda.from_numpy(frames).cuda()
     monkeypatch.setenv("VEL_PYR_FUSED", "1")
+    if strip:
+        monkeypatch.setenv("VEL_PYR_H2", str(strip))
     fused = FrameBatch(d, (3, 3), 3).build()
     monkeypatch.setenv("VEL_PYR_FUSED", "0")
     plain = FrameBatch(d, (3, 3), 3).build()

@@ -8,6 +8,7 @@
 //   BORDER_REFLECT_101, dst size ((w+1)/2, (h+1)/2).
 //
 // Streaming, HBM-bound: algorithmic bytes per level = src bytes read once + dst bytes written once.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -374,6 +375,159 @@ __device__ __forceinline__ void f2_strip(const F2Args& A, const uint8_t* __restr
     }
 }
 
+// ---- the same strip with the source rows staged by TMA ---------------------------------------------------------------
+// The LDG form keeps at most eight 16-byte loads per thread in flight (registers), ~4.7 MB over the chip at 16 warps per SM --
+// short of what 6.4 TB/s needs at HBM latency.  Here lane 0 of each warp issues one cp.async.bulk.tensor (3-D map: x in 32-bit
+// words, row, frame) per GROUP of four source rows: box = 136 words x 4 rows = the warp's 32 x 16 bytes plus 16 bytes either side
+// (the halo words of lanes 0 / 31), into a ring of F2_STAGES groups per warp, completion on one mbarrier per stage.  Bytes in
+// flight no longer cost registers: 4 stages x 2176 B per warp.  Out-of-frame columns are zero-filled by the TMA unit and replaced
+// by the REFLECT_101 bytes exactly as in the LDG form; strips that touch the top / bottom edge take the LDG form (row reflection).
+constexpr int F2_STAGES = 4;
+constexpr int F2_BOXW = 136;                        // 32-bit words per box row: 16 B + 32 lanes x 16 B + 16 B
+constexpr int F2_GROUP_BYTES = 4 * F2_BOXW * 4;     // 2176 = 17 x 128
+
+__device__ __forceinline__ uint32_t f2_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f2_mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void f2_mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f2_mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "F2_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra F2_DONE_%=;\n\t"
+        "bra F2_WAIT_%=;\n\t"
+        "F2_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void f2_tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+template <int H2>
+__device__ __forceinline__ void f2_strip_tma(const F2Args& A, const CUtensorMap* tm, uint8_t* __restrict__ d1, uint8_t* __restrict__ d2,
+                                             unsigned (*ring)[4][F2_BOXW], unsigned long long* bars)
+{
+    const int lane = threadIdx.x & 31, wx = blockIdx.x * F2_WARPS + (threadIdx.x >> 5);
+    const int nt = A.sw >> 4;
+    const int t = wx * F2_OWN - 1 + lane;
+    const int tc = max(0, min(t, nt - 1));
+    const bool owner = lane >= 1 && lane <= F2_OWN && t < nt;
+    const bool first = tc == 0, last = tc == nt - 1;
+    const bool edge_warp = __any_sync(0xffffffffu, first || last);
+    const int y2_0 = blockIdx.y * H2;
+    const int R0 = 2 * y2_0 - 2;
+    const int jend = min(H2 + 2, A.h2 - y2_0 + 2);
+    const int ngroups = 1 + jend;                               // group 0 = the carried rows, group j+1 = the rows of iteration j
+    const int cx = 4 * (wx * F2_OWN - 1) - 4;                   // box origin in 32-bit words: 16 bytes left of lane 0
+    const int row_g0 = 2 * R0 - 3;                              // group 0 = rows 2*R0-3 .. 2*R0 (the first is not used)
+    const uint32_t ring0 = f2_smem_u32(&ring[0][0][0]), bar0 = f2_smem_u32(bars);
+
+    auto issue = [&](int g) {                                   // lane 0 only
+        const int sidx = g % F2_STAGES;
+        const uint32_t bar = bar0 + 8u * sidx;
+        f2_mbar_expect_tx(bar, F2_GROUP_BYTES);
+        f2_tma_load_3d(ring0 + (uint32_t)sidx * F2_GROUP_BYTES, tm, cx, g == 0 ? row_g0 : 2 * R0 + 1 + 4 * (g - 1), (int)blockIdx.z, bar);
+    };
+    if (lane == 0) {
+        for (int s2 = 0; s2 < F2_STAGES; ++s2) f2_mbar_init(bar0 + 8u * s2, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int g = 0; g < F2_STAGES && g < ngroups; ++g) issue(g);
+    }
+    __syncwarp();
+
+    // the four rows of group g -> registers (the stage is re-armed for group g + F2_STAGES as soon as every lane has read it)
+    auto fetch = [&](int g, F2Row (&r)[4]) {
+        const int sidx = g % F2_STAGES;
+        f2_mbar_wait(bar0 + 8u * sidx, (unsigned)(g / F2_STAGES) & 1u);
+        const unsigned (*rows)[F2_BOXW] = ring[sidx];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            r[k].v = *reinterpret_cast<const uint4*>(&rows[k][4 + 4 * lane]);
+            r[k].elo = 0u; r[k].ehi = 0u;
+            if (lane == 0) r[k].elo = rows[k][3];
+            if (lane == 31) r[k].ehi = rows[k][4 + 128];
+        }
+        __syncwarp();
+        if (lane == 0 && g + F2_STAGES < ngroups) issue(g + F2_STAGES);
+    };
+    auto filt_row = [&](const F2Row& r) -> uint4 {
+        unsigned pw = __shfl_up_sync(0xffffffffu, r.v.w, 1);
+        unsigned nx = __shfl_down_sync(0xffffffffu, r.v.x, 1);
+        if (lane == 0) pw = r.elo;
+        if (lane == 31) nx = r.ehi;
+        if (edge_warp) {
+            if (first) pw = __byte_perm(r.v.x, 0u, 0x1200);
+            if (last) nx = __byte_perm(r.v.w, 0u, 0x0002);
+        }
+        return hfilt16(r.v, pw, nx);
+    };
+    auto hfilt_l1 = [&](unsigned o0, unsigned o1) -> uint2 {
+        unsigned pw = __shfl_up_sync(0xffffffffu, o1, 1);
+        unsigned nx = __shfl_down_sync(0xffffffffu, o0, 1);
+        if (edge_warp) {
+            if (t <= 0) pw = __byte_perm(o0, 0u, 0x1200);
+            if (t >= nt - 1) nx = __byte_perm(o1, 0u, 0x0002);
+        }
+        return hfilt8(o0, o1, pw, nx);
+    };
+
+    uint4 c0, c1, c2;
+    {
+        F2Row r[4];
+        fetch(0, r);
+        c0 = filt_row(r[1]); c1 = filt_row(r[2]); c2 = filt_row(r[3]);
+    }
+    uint2 q0 = make_uint2(0, 0), q1 = q0, q2 = q0, q3 = q0;
+#pragma unroll 1
+    for (int j = 0; j < jend; ++j) {
+        const int ra = R0 + 2 * j;
+        F2Row cur[4];
+        fetch(j + 1, cur);
+        const uint4 f0 = filt_row(cur[0]), f1 = filt_row(cur[1]), f2 = filt_row(cur[2]), f3 = filt_row(cur[3]);
+        const unsigned a0 = vfilt4(c0.x, c1.x, c2.x, f0.x, f1.x, c0.y, c1.y, c2.y, f0.y, f1.y);
+        const unsigned a1 = vfilt4(c0.z, c1.z, c2.z, f0.z, f1.z, c0.w, c1.w, c2.w, f0.w, f1.w);
+        const unsigned b0 = vfilt4(c2.x, f0.x, f1.x, f2.x, f3.x, c2.y, f0.y, f1.y, f2.y, f3.y);
+        const unsigned b1 = vfilt4(c2.z, f0.z, f1.z, f2.z, f3.z, c2.w, f0.w, f1.w, f2.w, f3.w);
+        c0 = f1; c1 = f2; c2 = f3;
+        if (owner && j >= 1 && j <= H2) {
+            uint8_t* o = d1 + (long long)ra * A.p1 + 8 * t;
+            *reinterpret_cast<uint2*>(o) = make_uint2(a0, a1);
+            *reinterpret_cast<uint2*>(o + A.p1) = make_uint2(b0, b1);
+        }
+        const uint2 ga = hfilt_l1(a0, a1), gb = hfilt_l1(b0, b1);
+        if (j >= 2) {
+            const unsigned o = vfilt4(q0.x, q1.x, q2.x, q3.x, ga.x, q0.y, q1.y, q2.y, q3.y, ga.y);
+            if (owner) *reinterpret_cast<unsigned*>(d2 + (long long)(y2_0 + j - 2) * A.p2 + 4 * t) = o;
+        }
+        q0 = q2; q1 = q3; q2 = ga; q3 = gb;
+    }
+}
+
+template <int H2>
+__global__ void __launch_bounds__(32 * F2_WARPS)
+pyrdown2_fused_tma_kernel(const F2Args A, const __grid_constant__ CUtensorMap tm)
+{
+    __shared__ __align__(128) unsigned ring[F2_WARPS][F2_STAGES][4][F2_BOXW];
+    __shared__ __align__(8) unsigned long long bars[F2_WARPS][F2_STAGES];
+    const uint8_t* __restrict__ src = A.src + (long long)blockIdx.z * A.src_stride;
+    uint8_t* __restrict__ d1 = A.d1 + (long long)blockIdx.z * A.d_stride;
+    uint8_t* __restrict__ d2 = A.d2 + (long long)blockIdx.z * A.d_stride;
+    const int R0 = 2 * (int)blockIdx.y * H2 - 2;
+    const bool interior = 2 * R0 - 2 >= 0 && 2 * (R0 + 2 * (H2 + 1) + 1) + 2 < A.sh;
+    const int w = threadIdx.x >> 5;
+    if (interior) f2_strip_tma<H2>(A, &tm, d1, d2, ring[w], bars[w]);
+    else f2_strip<H2, false>(A, src, d1, d2);
+}
+
 template <int H2>
 __global__ void __launch_bounds__(32 * F2_WARPS)
 pyrdown2_fused_kernel(const F2Args A)
@@ -387,6 +541,31 @@ pyrdown2_fused_kernel(const F2Args A)
     const bool interior = 2 * R0 - 2 >= 0 && 2 * (R0 + 2 * (H2 + 1) + 1) + 2 < A.sh;
     if (interior) f2_strip<H2, true>(A, src, d1, d2);
     else f2_strip<H2, false>(A, src, d1, d2);
+}
+
+typedef CUresult (*F2EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3-D map over the frames as 32-bit words: (x word, row, frame); box = 136 words x 4 rows x 1 frame; zero fill outside
+bool f2_make_map(CUtensorMap* tm, const uint8_t* frames, int sw, int sh, int pitch, long long frame_stride, int nframes)
+{
+    static F2EncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return false;
+        enc = (F2EncodeTiledFn)p;
+    }
+    const long long fs = nframes > 1 ? frame_stride : (long long)pitch * sh;
+    if (fs <= 0 || (fs & 15) != 0) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)(sw / 4), (cuuint64_t)sh, (cuuint64_t)nframes};
+    cuuint64_t strides[2] = {(cuuint64_t)pitch, (cuuint64_t)fs};
+    cuuint32_t box[3] = {(cuuint32_t)F2_BOXW, 4, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return enc(tm, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, (void*)frames, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 __global__ void decimate4_kernel(const uint8_t* __restrict__ src, int sw, int sh, int spitch, uint8_t* __restrict__ dst,
@@ -456,7 +635,13 @@ VEL_API int vel_pyramid_u8(const uint8_t* frames, int64_t frame_stride, int32_t 
             const int gx = (warps + F2_WARPS - 1) / F2_WARPS;
             const char* eh = getenv("VEL_PYR_H2");
             const int h2sel = eh ? atoi(eh) : ((long long)gx * ((A.h2 + 31) / 32) * nframes >= 8ll * kNumSMs ? 32 : 16);
-            if (h2sel == 32) {
+            const char* et = getenv("VEL_PYR_TMA");
+            CUtensorMap tm;
+            const bool tma = !(et && et[0] == '0') && h2sel == 32 && f2_make_map(&tm, frames, sw, sh, pitch, frame_stride, nframes);
+            if (tma) {
+                dim3 grid(gx, (A.h2 + 31) / 32, nframes);
+                pyrdown2_fused_tma_kernel<32><<<grid, 32 * F2_WARPS, 0, st>>>(A, tm);
+            } else if (h2sel == 32) {
                 dim3 grid(gx, (A.h2 + 31) / 32, nframes);
                 pyrdown2_fused_kernel<32><<<grid, 32 * F2_WARPS, 0, st>>>(A);
             } else if (h2sel == 24) {

@@ -342,6 +342,80 @@ def global_ba_leg(seq, K, rank, world, dev, iters):
             "speed_kmh_rank0_cameras_mean": float(sp.mean().item()), "solver": os.environ.get("VEL_BA_SOLVER", "vendor")}
 
 
+def dense_and_match_legs(dev, peaks):
+    """Roofline legs of the two other kernel families a C3 / C4 job spends its time in, each timed alone with CUDA events:
+    K8 (the dense FP64 part of a bundle-adjustment iteration at C3 size: the Schur SYRK on the FP64 tensor cores against this
+    device's measured DMMA rate, and the task-graph Cholesky) and K4 (BASELINE configs[3]: 8192 x 8192 x 256-bit 2-NN match on
+    tcgen05, against 2x the measured BF16 rate as SURVEY.md 8(d) states for 8-bit kinds)."""
+    import ctypes as C
+
+    import torch
+
+    from velocity_b200 import _lib, match
+    from velocity_b200.device import ptr, stream_ptr
+
+    L = _lib.lib()
+    out = {}
+
+    def timed(fn, reps):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    # K8 at C3 size: S (6nc x 6nc) -= W' W'^T with W' 6nc x 3nt, then the solve
+    m, k = 6 * (NFRAMES - 1), 3 * NPTS
+    g = torch.Generator(device=dev).manual_seed(3)
+    E = torch.randn((m, k), dtype=torch.float64, device=dev, generator=g) * (1.0 / np.sqrt(k))
+    S0 = torch.eye(m, dtype=torch.float64, device=dev) * 4.0
+    S = S0.clone()
+    work = torch.empty((max(int(L.vel_syrk_lower_sub_workspace(m, k)), 16),), dtype=torch.uint8, device=dev)
+    ms_syrk = timed(lambda: _lib.check(L.vel_syrk_lower_sub(ptr(E), k, m, k, ptr(S), m, ptr(work), work.numel(), stream_ptr()), "syrk"), 10)
+    b0 = torch.randn((m,), dtype=torch.float64, device=dev, generator=g)
+    Sspd = (S0 + E @ E.T).contiguous()
+    Sw, bw, info = Sspd.clone(), b0.clone(), torch.zeros((1,), dtype=torch.int32, device=dev)
+
+    def chol():
+        Sw.copy_(Sspd)
+        bw.copy_(b0)
+        _lib.check(L.vel_spd_solve(ptr(Sw), m, m, ptr(bw), ptr(info), stream_ptr()), "spd_solve")
+    ms_chol = timed(chol, 10)
+    ms_copy = timed(lambda: (Sw.copy_(Sspd), bw.copy_(b0)), 10)
+    peak64 = float(L.vel_fp64_mma_peak_tflops())
+    fl = float(m) * (m + 1) * k
+    tf = fl / (ms_syrk * 1e-3) / 1e12
+    out["k8_schur_syrk"] = {"bound": "tensor", "kernel": "dsyrk_lower_sub_kernel (FP64 mma.sync m8n8k4)", "achieved": tf, "peak": peak64,
+                            "unit": "TFLOP/s", "frac": tf / peak64 if peak64 > 0 else None, "ms_per_launch": ms_syrk, "flops_per_launch": fl,
+                            "peak_kind": "measured here: vel_fp64_mma_peak_tflops (register-resident DMMA loop, best of 3)",
+                            "shape": "S[%d x %d] -= W'[%d x %d] W'^T" % (m, m, m, k)}
+    out["k8_cholesky"] = {"kernel": "chol_dag_kernel", "ms_per_launch": ms_chol - ms_copy, "n": m, "gflops": m ** 3 / 3.0 / 1e9,
+                          "note": "latency-bound: a dependency chain of n pivots (one reciprocal + one multiply + one FMA of FP64 latency each) and "
+                                  "n/64 panel hand-offs; reported as time, not against a throughput roofline"}
+    # K4 at C4 size
+    rng = np.random.default_rng(4)
+    t = rng.integers(0, 256, (8192, 32), dtype=np.uint8)
+    q = t[rng.permutation(8192)].copy()
+    flip = rng.integers(0, 256, (8192, 3))
+    for c in range(3):
+        q[np.arange(8192), flip[:, c] // 8] ^= (1 << (flip[:, c] % 8)).astype(np.uint8)
+    dq, dt = torch.from_numpy(q).to(dev), torch.from_numpy(t).to(dev)
+    ms_match = timed(lambda: match.knn2_hamming256(dq, dt), 20)
+    ops = 2.0 * 8192 * 8192 * 256
+    tops = ops / (ms_match * 1e-3) / 1e12
+    peak8 = 2.0 * peaks["bf16_tflops"]
+    out["k4_match"] = {"bound": "tensor", "kernel": "knn2_hamming_tc_kernel (tcgen05.mma kind::i8 + fused top-2) incl. operand expansion and merge",
+                       "achieved": tops, "peak": peak8, "unit": "Top/s (int8)", "frac": tops / peak8, "us_per_frame_pair": ms_match * 1e3,
+                       "workload": "C4: 8192 x 8192 descriptors of 256 bits, knnMatch k=2",
+                       "note": "the floor on this shape is reading the int32 accumulators out of TMEM (64 B per cycle and SM: 2048 cycles per "
+                               "128 x 256 tile against 1218 cycles of MMA at K = 256), so the tensor pipe cannot exceed ~50 %"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -444,6 +518,12 @@ def run_ours(args):
     k2_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
     c2_valid = float(c2[1].float().mean().item())
 
+    extra = None
+    if rank == 0:
+        try:
+            extra = dense_and_match_legs(dev, measured_peaks()[0])
+        except Exception as ex:  # pragma: no cover
+            extra = {"error": repr(ex)}
     gba = None
     if world > 1:
         gba = global_ba_leg(seq, K, rank, world, dev, args.global_ba_iters)
@@ -506,7 +586,7 @@ def run_ours(args):
                          "k1_pyramid": {"achieved": k1_gbs, "frac": k1_gbs / peaks["hbm_gbs"], "ms_per_step": k1_ms,
                                         "bytes_per_step": (C2_PAIRS + 1) * K1_BYTES_PER_FRAME},
                          "in_sequence": {"achieved": seq_gbs, "frac": seq_gbs / peaks["hbm_gbs"], "us_per_pair": st_track * 1e3 / (NFRAMES - 1),
-                                         "note": "K1 + 299 dependent single-pair K2 launches"}},
+                                         "note": "K1 + the K2 sequence kernel (one launch walks all 299 dependent pairs)"}},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps, "chunk_frames": args.chunk, "speed_kmh_mean": e2e_speed,
@@ -514,6 +594,8 @@ def run_ours(args):
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clk,
         }
+        if extra is not None:
+            line["roofline"].update(extra)
         if gba is not None:
             line["global_ba"] = gba
         print(json.dumps(line))

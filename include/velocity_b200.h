@@ -231,6 +231,10 @@ int vel_syrk_lower_sub(const double* E, int64_t ld, int32_t m, int32_t k, double
                        vel_stream_t stream);
 int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t* info, vel_stream_t stream);
 
+/* Measurement aid (bench.py's roofline denominator for the K8 SYRK; MEASURED_PEAKS.json has no FP64 entry): the FP64 tensor-core
+ * (mma.sync m8n8k4 f64) rate of the current device with operands in registers, TFLOP/s, best of 3.  Synchronises; 0 on failure. */
+double vel_fp64_mma_peak_tflops(void);
+
 /* fcnNLS_batch2 (utils/NLS.py:253-328): the range/elevation/azimuth-parametrised bundle adjustment.
  * x = [points nt*3 | q], q = [joint roll,pitch,yaw | el | az | range_1..range_nc] (nq = 5 + nc).
  * vel_ba2_accumulate writes V [nt][6], the dense symmetric camera-side block G [nq][nq], the cross

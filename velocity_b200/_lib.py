@@ -71,6 +71,7 @@ SIGNATURES = {
     "vel_ba_factor": (C.c_int, [_I32, _I32, _P, C.c_size_t, _P]),
     "vel_ba_update": (C.c_int, [_P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
     "vel_spd_solve": (C.c_int, [_P, _I64, _I32, _P, _P, _P]),
+    "vel_fp64_mma_peak_tflops": (C.c_double, []),
     "vel_ba2_accumulate": (C.c_int, [_P, _P, _P, _I32, _I32, _P, _P, _P, _P, _P, _P]),
     "vel_ba2_solve": (C.c_int, [_P, _P, _P, _P, _I32, _I32, _P, _P, _P, C.c_size_t, _P]),
     "vel_match_knn2_hamming256": (C.c_int, [_P, _I32, _P, _I32, _P, _P, _P]),

@@ -1224,3 +1224,49 @@ VEL_API int vel_spd_solve(double* S, int64_t lds, int32_t n, double* b, int32_t*
 {
     return vel_dense_spd_solve_gated(S, lds, n, b, info, nullptr, stream);
 }
+
+// ---- measurement aid: the FP64 tensor-core (DMMA m8n8k4) rate of this device with operands in registers -----------------------
+// MEASURED_PEAKS.json carries HBM and BF16 peaks only; bench.py reports the K8 SYRK against this number (TFLOP/s, best of 3).
+// Synchronises.  Returns 0 on failure.
+namespace {
+__global__ void dmma_peak_kernel(double* out, int iters, double a0, double b0)
+{
+    double acc[16][2];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+    const double a = a0 + threadIdx.x, b = b0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) dmma884(acc[i][0], acc[i][1], a, b);
+    }
+    double s2 = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s2 += acc[i][0] + acc[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s2;
+}
+}  // namespace
+
+VEL_API double vel_fp64_mma_peak_tflops(void)
+{
+    const int sms = sm_count(), threads = 512, iters = 4000;
+    double* out = nullptr;
+    if (cudaMalloc((void**)&out, sizeof(double) * sms * threads) != cudaSuccess) return 0.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<<<sms, threads>>>(out, iters, 1.0, 1e-3);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { best = 0.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double tf = 2.0 * 256 * 16 * (double)iters * (threads / 32) * sms / ms / 1e9;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}

@@ -9,29 +9,48 @@
 // row per thread) and keep a running top-2 in registers.  Ties resolve to the lower train index
 // (columns are visited in ascending order with strict >), as cv2.BFMatcher does.
 //
+// The epilogue is what bounds this kernel (an M128 N256 K256 int8 tile is 0.55 us of tensor time, its 32768 accumulators must be
+// scanned in less), so the MMA itself produces the sort keys: the operands are scaled (query bits -> +-2, train bits -> +-64,
+// product +-128) and a NINTH K32 step multiplies a constant query column of ones with a constant train column holding
+// 127 - (column mod 128), so the accumulator IS  128 * dot + tie-break  -- a running top-2 costs min / max / max per element and no
+// key construction; dot = acc >> 7, column = 127 - (acc & 127) within its 128-column block.  Keys are comparable inside the 64
+// columns a thread scans of one tile; per tile the thread's local top-2 is merged into its running global pair (20 instructions
+// per 64 elements).  The constant operands are written into shared memory once per CTA (hand-swizzled, 48 KB).
+//
+// What bounds it (measured on B200, 8192 x 8192, 128 CTAs x 16 tiles): 23.6 us.  With the scan removed (loads, barriers and MMAs only)
+// the same pipeline takes 20.5 us, with the operand loads removed as well it does not change -- the floor is reading the int32
+// accumulators out of TMEM: 128 KB per tile at 64 B per cycle and SM = 2048 cycles against 1218 cycles of MMA (K = 256 is short:
+// an accumulator costs 1.9x more to read than to compute), i.e. the tensor pipe cannot exceed ~50 % on this shape.  The scan
+// itself (3 alu-pipe instructions per element, 2 issue cycles each) hides behind the reads with 16 epilogue warps.
+//
 // Kernel anatomy (one CTA per 128 queries x one split of the train set, 320 threads):
 //   warp 0      TMA producer: Q' tile once (2 x 16 KB, SWIZZLE_128B), T' tiles double-buffered (2 x 64 KB)
-//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: 8 x (M128 N256 K32, kind::i8) per tile,
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: 9 x (M128 N256 K32, kind::i8) per tile,
 //               accumulators double-buffered in 2 x 256 TMEM columns; tcgen05.commit frees smem / publishes D
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32x32b.x32, branch-free
-//               running top-2 on packed keys, overlapped with the next tile's MMAs
+//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32x32b.x32 double-buffered in registers
+//               ACROSS tiles, running top-2 with four independent accumulator pairs, overlapped with the next tile's MMAs
 // Reference call site: cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) (the ORB variant of utils/KLT.py:16-26;
 // BASELINE config 4).  Roofline class: tensor (34.36 G int8-op per 8192^2 pair of frames).
 #include <cuda.h>
 #include <limits.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
 namespace tc {
 
 constexpr int TC_M = 128, TC_N = 256;
-constexpr int TC_THREADS = 320;   // TMA warp + MMA warp + 8 epilogue warps
+constexpr int TC_EPW = 4;         // epilogue warps per TMEM lane quarter
+constexpr int TC_CW = TC_N / TC_EPW;   // columns of a tile one epilogue thread scans
+constexpr int TC_THREADS = 64 + 32 * 4 * TC_EPW;   // TMA warp + MMA warp + 16 epilogue warps
+constexpr int Q_POS = 2, T_POS = 64;   // operand scaling: product of two set / two clear bits = +128
 constexpr uint32_t A_CHUNK = TC_M * 128;          // one 128-byte K chunk of the query tile
 constexpr uint32_t B_CHUNK = TC_N * 128;
 constexpr uint32_t SMEM_A = 2 * A_CHUNK;          // K = 256 bytes = 2 chunks
 constexpr uint32_t SMEM_B_STAGE = 2 * B_CHUNK;
+constexpr uint32_t SMEM_AE = A_CHUNK, SMEM_BE = B_CHUNK;   // the constant operands of the tie-break step (one 128-byte chunk each)
 constexpr uint32_t SMEM_BARS = 256;
-constexpr uint32_t SMEM_TOTAL = SMEM_A + 2 * SMEM_B_STAGE + SMEM_BARS + 1024;   // + alignment slack
+constexpr uint32_t SMEM_TOTAL = SMEM_A + 2 * SMEM_B_STAGE + SMEM_AE + SMEM_BE + SMEM_BARS + 1024;   // + alignment slack
 
 // instruction descriptor: D = S32 (2<<4), A = S8 (1<<7), B = S8 (1<<10), K-major A and B, N>>3 at bit 17, M>>4 at bit 24
 constexpr uint32_t IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TC_N >> 3) << 17) | ((uint32_t)(TC_M >> 4) << 24);
@@ -117,9 +136,9 @@ __device__ __forceinline__ void tmem_ld_wait(int (&v)[32])
                  : "memory");
 }
 
-// Branch-free running top-2 on packed keys: key = (dot << 16) + (0xFFFF - local column), so a larger key is a
-// smaller Hamming distance and, among equal distances, the LOWER train index.  Four independent (k0, k1)
-// pairs break the loop-carried dependency (ILP 4); they are merged once at the end.
+// Branch-free running top-2 on the accumulators themselves (acc = 128 * dot + 127 - (column mod 128): a larger value is a smaller
+// Hamming distance and, among equal distances, the LOWER column; comparable inside the 128 columns a thread scans of one tile).  Four independent (k0, k1) pairs break the loop-carried
+// dependency; they are merged once per tile.
 struct Top2Keys {
     int k0[4], k1[4];
     __device__ __forceinline__ void init()
@@ -134,26 +153,29 @@ struct Top2Keys {
     }
 };
 
-__device__ __forceinline__ void consume_chunk(const int (&v)[32], int inv_col0, Top2Keys& T)
+__device__ __forceinline__ void consume_chunk(const int (&v)[32], Top2Keys& T)
 {
-    // inv_col0 = 0xFFFF - (local column of v[0]); columns ascend => the inverted index descends
 #pragma unroll
-    for (int c = 0; c < 32; ++c) T.push(c & 3, (v[c] << 16) + (inv_col0 - c));
+    for (int c = 0; c < 32; ++c) T.push(c & 3, v[c]);
 }
 
-// bits -> +-1 int8 (bit b of byte k -> element 8k + b)
-__global__ void expand_pm1_kernel(const uint8_t* __restrict__ in, long long nbytes, uint2* __restrict__ out)
+// bits -> scaled +-1 int8 (bit b of byte k -> element 8k + b); the first nq_bytes bytes are queries (+-Q_POS), the rest train (+-T_POS)
+__global__ void expand_pm_kernel(const uint8_t* __restrict__ q, long long nq_bytes, const uint8_t* __restrict__ t, long long nt_bytes,
+                                 uint2* __restrict__ qe, uint2* __restrict__ te)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= nbytes) return;
-    const unsigned b = in[i];
+    if (i >= nq_bytes + nt_bytes) return;
+    const bool isq = i < nq_bytes;
+    const unsigned b = isq ? q[i] : t[i - nq_bytes];
+    const unsigned pos = isq ? (unsigned)Q_POS : (unsigned)T_POS, neg = (0u - pos) & 0xFFu;
     unsigned lo = 0, hi = 0;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        lo |= (((b >> k) & 1u) ? 0x01u : 0xFFu) << (8 * k);
-        hi |= (((b >> (k + 4)) & 1u) ? 0x01u : 0xFFu) << (8 * k);
+        lo |= (((b >> k) & 1u) ? pos : neg) << (8 * k);
+        hi |= (((b >> (k + 4)) & 1u) ? pos : neg) << (8 * k);
     }
-    out[i] = make_uint2(lo, hi);
+    if (isq) qe[i] = make_uint2(lo, hi);
+    else te[i - nq_bytes] = make_uint2(lo, hi);
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
@@ -162,7 +184,7 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
 {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
-    const uint32_t sA = base, sB = base + SMEM_A, sBar = base + SMEM_A + 2 * SMEM_B_STAGE;
+    const uint32_t sA = base, sB = base + SMEM_A, sAe = sB + 2 * SMEM_B_STAGE, sBe = sAe + SMEM_AE, sBar = sBe + SMEM_BE;
     // barriers (8 bytes each): 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 tmem_full | 7,8 tmem_empty ; +80: TMEM base slot
     const uint32_t bar_a = sBar, bar_bfull = sBar + 8, bar_bempty = sBar + 24, bar_tfull = sBar + 40, bar_tempty = sBar + 56;
     const uint32_t tmem_slot = sBar + 80;
@@ -180,13 +202,23 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             mbar_init(bar_bfull + 8 * s, 1);
             mbar_init(bar_bempty + 8 * s, 1);
             mbar_init(bar_tfull + 8 * s, 1);
-            mbar_init(bar_tempty + 8 * s, 8);   // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * s, 4 * TC_EPW);   // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    {   // constant operands of the tie-break step, K-major SWIZZLE_128B by hand: element (row, k = 0) sits in 16-byte chunk (row & 7)
+        uint8_t* ce = smem_raw + (sAe - smem_u32(smem_raw));
+        for (uint32_t o = threadIdx.x * 16u; o < SMEM_AE + SMEM_BE; o += TC_THREADS * 16u) {
+            const uint32_t r = (o >> 7) & 0x1FFu, chunk = (o >> 4) & 7u;           // row within A_e (o < SMEM_AE) or A_e rows + B_e row
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (chunk == (r & 7u)) val.x = o < SMEM_AE ? 1u : (uint32_t)(127 - (int)(((o - SMEM_AE) >> 7) & 127u));
+            *reinterpret_cast<uint4*>(ce + o) = val;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");                // generic-proxy writes -> visible to the tensor core
     }
     tc_fence_before();
     __syncthreads();
@@ -224,64 +256,85 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                     const uint64_t bd = make_desc(sB + s * SMEM_B_STAGE + (k >> 2) * B_CHUNK + koff);
                     mma_i8(d, ad, bd, k > 0 ? 1u : 0u);
                 }
+                mma_i8(d, make_desc(sAe), make_desc(sBe), 1u);     // + (127 - column mod 128): the accumulator becomes the sort key
                 mma_commit(bar_bempty + 8 * s);   // smem stage reusable once these MMAs have read it
                 mma_commit(bar_tfull + 8 * s);    // accumulator tile complete
             }
         }
     } else {
         const int q = warp & 3;                   // TMEM lane quarter this warp may access
-        const int half = (warp - 2) >> 2;         // two warps share a quarter: each scans 128 of the 256 columns
+        const int sub = (warp - 2) >> 2;          // TC_EPW warps share a quarter: each scans TC_CW of the 256 columns
         const int row = q * 32 + lane;
-        const int col_base = blk0 * TC_N;         // keys carry columns local to this split (< 65536, checked on the host)
-        Top2Keys T;
-        T.init();
+        const int col_base = blk0 * TC_N;
+        const int blk128 = (sub * TC_CW) & ~127;  // the 128-column block of the tile this warp's columns lie in
+        int g0 = INT_MIN, g1 = INT_MIN;           // running global pair: (dot << 16) + (0xFFFF - column local to this split)
+        // TMEM reads are the floor of this kernel (64 B per cycle and SM: 2048 cycles for the 128 KB of a tile against 1218 of MMA), so
+        // they must never pause: chunks of 32 columns are double-buffered in registers, the next chunk -- of this tile or the first of
+        // the NEXT tile -- is requested before the current one is scanned, and the accumulator buffer is handed back to the MMA warp
+        // as soon as its last chunk has landed.
+        constexpr int NCH = TC_CW / 32;           // chunks per tile and thread (even: the two register buffers alternate across tiles)
+        static_assert(NCH % 2 == 0, "register double buffering assumes an even chunk count per tile");
+        const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * TC_CW);
+        int va[32], vb[32];
+        if (nblk > 0) {
+            mbar_wait(bar_tfull, 0);
+            tc_fence_after();
+            tmem_ld32(tlane, va);
+        }
         for (int i = 0; i < nblk; ++i) {
             const int s = i & 1;
-            mbar_wait(bar_tfull + 8 * s, (i >> 1) & 1);
-            tc_fence_after();
             const int jloc = i * TC_N;            // local column of the tile's first column
             const int valid = min(TC_N, nt - (col_base + jloc));   // columns of this tile that exist
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)s * TC_N;
-            int va[32], vb[32];
-            const int ch0 = half * 4, ch1 = half * 4 + 4;
-            tmem_ld32(taddr + ch0 * 32, va);
+            const uint32_t taddr = tlane + (uint32_t)s * TC_N;
+            Top2Keys T;
+            T.init();
 #pragma unroll
-            for (int ch = ch0; ch < ch1; ch += 2) {
-                tmem_ld_wait(va);
-                tmem_ld32(taddr + (ch + 1) * 32, vb);          // prefetch the next chunk while this one is consumed
-                if (valid < (ch + 1) * 32) {
-#pragma unroll
-                    for (int c = 0; c < 32; ++c) if (ch * 32 + c >= valid) va[c] = -30000;   // padded train rows never win
+            for (int ch = 0; ch < NCH; ++ch) {
+                int (&cur)[32] = (ch & 1) ? vb : va;
+                int (&nxt)[32] = (ch & 1) ? va : vb;
+                tmem_ld_wait(cur);
+                if (ch + 1 < NCH) {
+                    tmem_ld32(taddr + (ch + 1) * 32, nxt);
+                } else {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * s);          // every value of tile i is in registers
+                    if (i + 1 < nblk) {
+                        const int s1 = (i + 1) & 1;
+                        mbar_wait(bar_tfull + 8 * s1, ((i + 1) >> 1) & 1);
+                        tc_fence_after();
+                        tmem_ld32(tlane + (uint32_t)s1 * TC_N, nxt);
+                    }
                 }
-                consume_chunk(va, 0xFFFF - (jloc + ch * 32), T);
-                tmem_ld_wait(vb);
-                if (ch + 2 < ch1) tmem_ld32(taddr + (ch + 2) * 32, va);
-                if (valid < (ch + 2) * 32) {
+                if (valid < sub * TC_CW + (ch + 1) * 32) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) if ((ch + 1) * 32 + c >= valid) vb[c] = -30000;
+                    for (int c = 0; c < 32; ++c) if (sub * TC_CW + ch * 32 + c >= valid) cur[c] = INT_MIN;   // padded train rows never win
                 }
-                consume_chunk(vb, 0xFFFF - (jloc + (ch + 1) * 32), T);
+                consume_chunk(cur, T);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * s);
-        }
-        // merge the four accumulator pairs (keys are unique, so plain max/min merging is exact)
-        int k0 = T.k0[0], k1 = T.k1[0];
+            // the tile's pair -> global keys -> merge (keys are unique: plain max / min merging is exact)
+            int k0 = T.k0[0], k1 = T.k1[0];
 #pragma unroll
-        for (int a = 1; a < 4; ++a) {
-            const int x0 = T.k0[a], x1 = T.k1[a];
-            const int n0 = max(k0, x0);
-            const int n1 = max(min(k0, x0), max(k1, x1));
-            k0 = n0; k1 = n1;
+            for (int a = 1; a < 4; ++a) {
+                const int x0 = T.k0[a], x1 = T.k1[a];
+                const int n0 = max(k0, x0);
+                const int n1 = max(min(k0, x0), max(k1, x1));
+                k0 = n0; k1 = n1;
+            }
+            const int inv0 = 0xFFFF - (jloc + blk128 + 127);      // + (acc & 127) = 0xFFFF - column
+            const int t0 = k0 == INT_MIN ? INT_MIN : ((k0 >> 7) << 16) + inv0 + (k0 & 127);
+            const int t1 = k1 == INT_MIN ? INT_MIN : ((k1 >> 7) << 16) + inv0 + (k1 & 127);
+            const int n0 = max(g0, t0);
+            const int n1 = max(min(g0, t0), max(g1, t1));
+            g0 = n0; g1 = n1;
         }
         if (m0 + row < nq) {
             // key -> (dot, column): dot = key >> 16 (arithmetic), column = 0xFFFF - (key & 0xFFFF)
-            const int dot0 = k0 >> 16, dot1 = k1 >> 16;
-            const int idx0 = dot0 > -20000 ? col_base + (0xFFFF - (k0 & 0xFFFF)) : -1;
-            const int idx1 = dot1 > -20000 ? col_base + (0xFFFF - (k1 & 0xFFFF)) : -1;
+            const int dot0 = g0 >> 16, dot1 = g1 >> 16;
+            const int idx0 = g0 != INT_MIN ? col_base + (0xFFFF - (g0 & 0xFFFF)) : -1;
+            const int idx1 = g1 != INT_MIN ? col_base + (0xFFFF - (g1 & 0xFFFF)) : -1;
             const int d0 = idx0 >= 0 ? (256 - dot0) >> 1 : 0x7fffffff, d1 = idx1 >= 0 ? (256 - dot1) >> 1 : 0x7fffffff;
-            part[(long long)(blockIdx.y * 2 + half) * nq + m0 + row] = make_int4(d0, idx0, d1, idx1);
+            part[(long long)(blockIdx.y * TC_EPW + sub) * nq + m0 + row] = make_int4(d0, idx0, d1, idx1);
         }
     }
     tc_fence_before();
@@ -337,10 +390,9 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
     vel_keep_async_pool_cached();
     VEL_CUDA(cudaMallocAsync((void**)&qe, (size_t)nq * 256, st));
     VEL_CUDA(cudaMallocAsync((void**)&te, (size_t)nt * 256, st));
-    expand_pm1_kernel<<<(unsigned)(((long long)nq * 32 + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, (uint2*)qe);
-    VEL_LAUNCH_CHECK("expand_pm1_kernel");
-    expand_pm1_kernel<<<(unsigned)(((long long)nt * 32 + 255) / 256), 256, 0, st>>>(t, (long long)nt * 32, (uint2*)te);
-    VEL_LAUNCH_CHECK("expand_pm1_kernel");
+    expand_pm_kernel<<<(unsigned)(((long long)(nq + nt) * 32 + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, t, (long long)nt * 32, (uint2*)qe,
+                                                                                          (uint2*)te);
+    VEL_LAUNCH_CHECK("expand_pm_kernel");
 
     CUtensorMap tmQ, tmT;
     if (!make_map(&tmQ, qe, nq, TC_M) || !make_map(&tmT, te, nt, TC_N)) {
@@ -359,7 +411,7 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
     nsplit = (nblk_total + nblk_per_split - 1) / nblk_per_split;
     int4* part = nullptr;
     vel_keep_async_pool_cached();
-    VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsplit * 2, st));   // two column halves per split
+    VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsplit * TC_EPW, st));   // TC_EPW column ranges per split
     static bool attr_set = false;
     if (!attr_set) {
         VEL_CUDA(cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
@@ -367,7 +419,7 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
     }
     knn2_hamming_tc_kernel<<<dim3(mblocks, nsplit), TC_THREADS, SMEM_TOTAL, st>>>(tmQ, tmT, nq, nt, nblk_per_split, part);
     VEL_LAUNCH_CHECK("knn2_hamming_tc_kernel");
-    const int rc = vel_match_merge_hamming(part, nq, nsplit * 2, idx, dist, st);
+    const int rc = vel_match_merge_hamming(part, nq, nsplit * TC_EPW, idx, dist, st);
     if (rc != VEL_OK) return rc;
     VEL_CUDA(cudaFreeAsync(part, st));
     VEL_CUDA(cudaFreeAsync(te, st));

@@ -23,11 +23,11 @@
 // an accumulator costs 1.9x more to read than to compute), i.e. the tensor pipe cannot exceed ~50 % on this shape.  The scan
 // itself (3 alu-pipe instructions per element, 2 issue cycles each) hides behind the reads with 16 epilogue warps.
 //
-// Kernel anatomy (one CTA per 128 queries x one split of the train set, 320 threads):
+// Kernel anatomy (one CTA per 128 queries x one split of the train set, 576 threads):
 //   warp 0      TMA producer: Q' tile once (2 x 16 KB, SWIZZLE_128B), T' tiles double-buffered (2 x 64 KB)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer: 9 x (M128 N256 K32, kind::i8) per tile,
 //               accumulators double-buffered in 2 x 256 TMEM columns; tcgen05.commit frees smem / publishes D
-//   warps 2..9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32x32b.x32 double-buffered in registers
+//   warps 2..17 epilogue (four warps per TMEM lane quarter, 64 columns each): tcgen05.ld 32x32b.x16 double-buffered in registers
 //               ACROSS tiles, running top-2 with four independent accumulator pairs, overlapped with the next tile's MMAs
 // Reference call site: cv2.BFMatcher(NORM_HAMMING).knnMatch(k=2) (the ORB variant of utils/KLT.py:16-26;
 // BASELINE config 4).  Roofline class: tensor (34.36 G int8-op per 8192^2 pair of frames).
@@ -123,6 +123,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, int (&v)[32])
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, int (&v)[16])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(int (&v)[16])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                   "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+                 :
+                 : "memory");
+}
+
 // wait for the outstanding tcgen05.ld; the loaded registers are tied to the asm ("+r") so the compiler cannot
 // schedule their first use above the wait
 __device__ __forceinline__ void tmem_ld_wait(int (&v)[32])
@@ -137,7 +156,7 @@ __device__ __forceinline__ void tmem_ld_wait(int (&v)[32])
 }
 
 // Branch-free running top-2 on the accumulators themselves (acc = 128 * dot + 127 - (column mod 128): a larger value is a smaller
-// Hamming distance and, among equal distances, the LOWER column; comparable inside the 128 columns a thread scans of one tile).  Four independent (k0, k1) pairs break the loop-carried
+// Hamming distance and, among equal distances, the LOWER column; comparable inside the 64 columns a thread scans of one tile).  Four independent (k0, k1) pairs break the loop-carried
 // dependency; they are merged once per tile.
 struct Top2Keys {
     int k0[4], k1[4];
@@ -153,17 +172,26 @@ struct Top2Keys {
     }
 };
 
-__device__ __forceinline__ void consume_chunk(const int (&v)[32], Top2Keys& T)
+template <int N>
+__device__ __forceinline__ void consume_chunk(const int (&v)[N], Top2Keys& T)
 {
 #pragma unroll
-    for (int c = 0; c < 32; ++c) T.push(c & 3, v[c]);
+    for (int c = 0; c < N; ++c) T.push(c & 3, v[c]);
+}
+
+// (distance, index) lexicographic order, as cv2.BFMatcher ranks
+__device__ __forceinline__ void push_lex(int& d0, int& i0, int& d1, int& i1, int d, int j)
+{
+    if (d < d0 || (d == d0 && j < i0)) { d1 = d0; i1 = i0; d0 = d; i0 = j; }
+    else if (d < d1 || (d == d1 && j < i1)) { d1 = d; i1 = j; }
 }
 
 // bits -> scaled +-1 int8 (bit b of byte k -> element 8k + b); the first nq_bytes bytes are queries (+-Q_POS), the rest train (+-T_POS)
 __global__ void expand_pm_kernel(const uint8_t* __restrict__ q, long long nq_bytes, const uint8_t* __restrict__ t, long long nt_bytes,
-                                 uint2* __restrict__ qe, uint2* __restrict__ te)
+                                 uint2* __restrict__ qe, uint2* __restrict__ te, int* __restrict__ counters, int ncounters)
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < ncounters) counters[i] = 0;            // the per-query-block arrival counters of the main kernel
     if (i >= nq_bytes + nt_bytes) return;
     const bool isq = i < nq_bytes;
     const unsigned b = isq ? q[i] : t[i - nq_bytes];
@@ -178,11 +206,56 @@ __global__ void expand_pm_kernel(const uint8_t* __restrict__ q, long long nq_byt
     else te[i - nq_bytes] = make_uint2(lo, hi);
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// End of a CTA's scan: merge the TC_EPW column ranges of each row through shared memory (xch [TC_EPW][TC_M]: the idle train stages),
+// then the splits of a query block by whichever of its CTAs finishes last (a counter per query block) -- no separate merge launch.
+// Called by the epilogue warps only (named barrier 1).  Not inlined: its temporaries must not raise the register count of the scan.
+__device__ __noinline__ void epilogue_merge(int2* xch, int g0, int g1, int sub, int row, int m0, int col_base, int nq, int4* __restrict__ part,
+                                            int* __restrict__ counters, int* __restrict__ idx, int* __restrict__ dist, int* s_last_p)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    xch[sub * TC_M + row] = make_int2(g0, g1);
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * 4 * TC_EPW) : "memory");                  // epilogue warps only
+    const bool writer = sub == 0 && m0 + row < nq;
+    if (writer) {
+        int k0 = g0, k1 = g1;
+#pragma unroll
+        for (int a = 1; a < TC_EPW; ++a) {
+            const int2 o = xch[a * TC_M + row];
+            const int n0 = max(k0, o.x);
+            const int n1 = max(min(k0, o.x), max(k1, o.y));
+            k0 = n0; k1 = n1;
+        }
+        // key -> (dot, column): dot = key >> 16 (arithmetic), column = 0xFFFF - (key & 0xFFFF)
+        const int dot0 = k0 >> 16, dot1 = k1 >> 16;
+        const int idx0 = k0 != INT_MIN ? col_base + (0xFFFF - (k0 & 0xFFFF)) : -1;
+        const int idx1 = k1 != INT_MIN ? col_base + (0xFFFF - (k1 & 0xFFFF)) : -1;
+        const int d0 = idx0 >= 0 ? (256 - dot0) >> 1 : 0x7fffffff, d1 = idx1 >= 0 ? (256 - dot1) >> 1 : 0x7fffffff;
+        part[(long long)blockIdx.y * nq + m0 + row] = make_int4(d0, idx0, d1, idx1);
+        __threadfence();
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * 4 * TC_EPW) : "memory");
+    if (warp == 2 && lane == 0) *s_last_p = atomicAdd(&counters[blockIdx.x], 1) == (int)gridDim.y - 1 ? 1 : 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(32 * 4 * TC_EPW) : "memory");
+    if (*s_last_p && writer) {
+        __threadfence();
+        int d0 = INT_MAX, i0 = -1, d1 = INT_MAX, i1 = -1;
+        for (int sp = 0; sp < (int)gridDim.y; ++sp) {
+            const int4 p = __ldcg(&part[(long long)sp * nq + m0 + row]);
+            if (p.y >= 0) push_lex(d0, i0, d1, i1, p.x, p.y);
+            if (p.w >= 0) push_lex(d0, i0, d1, i1, p.z, p.w);
+        }
+        const int qi = m0 + row;
+        idx[2 * qi] = i0; idx[2 * qi + 1] = i1;
+        dist[2 * qi] = i0 < 0 ? -1 : d0; dist[2 * qi + 1] = i1 < 0 ? -1 : d1;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)  // 18 warps are allocated as 20: 96 registers per thread is the ceiling
 knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmT, int nq, int nt,
-                       int nblk_per_split, int4* __restrict__ part)
+                       int nblk_per_split, int4* __restrict__ part, int* __restrict__ counters, int* __restrict__ idx, int* __restrict__ dist)
 {
     extern __shared__ uint8_t smem_raw[];
+    __shared__ int s_last;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B tiles need 1024-byte alignment
     const uint32_t sA = base, sB = base + SMEM_A, sAe = sB + 2 * SMEM_B_STAGE, sBe = sAe + SMEM_AE, sBar = sBe + SMEM_BE;
     // barriers (8 bytes each): 0 a_full | 1,2 b_full | 3,4 b_empty | 5,6 tmem_full | 7,8 tmem_empty ; +80: TMEM base slot
@@ -272,14 +345,16 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
         // they must never pause: chunks of 32 columns are double-buffered in registers, the next chunk -- of this tile or the first of
         // the NEXT tile -- is requested before the current one is scanned, and the accumulator buffer is handed back to the MMA warp
         // as soon as its last chunk has landed.
-        constexpr int NCH = TC_CW / 32;           // chunks per tile and thread (even: the two register buffers alternate across tiles)
+        constexpr int CHW = 16;                   // columns per tcgen05.ld: two 16-register buffers (32-column chunks would need 64 data
+                                                  // registers; 18 warps are allocated as 20, so the ceiling is 96 per thread)
+        constexpr int NCH = TC_CW / CHW;          // chunks per tile and thread (even: the two register buffers alternate across tiles)
         static_assert(NCH % 2 == 0, "register double buffering assumes an even chunk count per tile");
         const uint32_t tlane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * TC_CW);
-        int va[32], vb[32];
+        int va[CHW], vb[CHW];
         if (nblk > 0) {
             mbar_wait(bar_tfull, 0);
             tc_fence_after();
-            tmem_ld32(tlane, va);
+            tmem_ld16(tlane, va);
         }
         for (int i = 0; i < nblk; ++i) {
             const int s = i & 1;
@@ -290,11 +365,11 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             T.init();
 #pragma unroll
             for (int ch = 0; ch < NCH; ++ch) {
-                int (&cur)[32] = (ch & 1) ? vb : va;
-                int (&nxt)[32] = (ch & 1) ? va : vb;
-                tmem_ld_wait(cur);
+                int (&cur)[CHW] = (ch & 1) ? vb : va;
+                int (&nxt)[CHW] = (ch & 1) ? va : vb;
+                tmem_ld_wait16(cur);
                 if (ch + 1 < NCH) {
-                    tmem_ld32(taddr + (ch + 1) * 32, nxt);
+                    tmem_ld16(taddr + (ch + 1) * CHW, nxt);
                 } else {
                     tc_fence_before();
                     __syncwarp();
@@ -303,12 +378,12 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
                         const int s1 = (i + 1) & 1;
                         mbar_wait(bar_tfull + 8 * s1, ((i + 1) >> 1) & 1);
                         tc_fence_after();
-                        tmem_ld32(tlane + (uint32_t)s1 * TC_N, nxt);
+                        tmem_ld16(tlane + (uint32_t)s1 * TC_N, nxt);
                     }
                 }
-                if (valid < sub * TC_CW + (ch + 1) * 32) {
+                if (valid < sub * TC_CW + (ch + 1) * CHW) {
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) if (sub * TC_CW + ch * 32 + c >= valid) cur[c] = INT_MIN;   // padded train rows never win
+                    for (int c = 0; c < CHW; ++c) if (sub * TC_CW + ch * CHW + c >= valid) cur[c] = INT_MIN;   // padded train rows never win
                 }
                 consume_chunk(cur, T);
             }
@@ -328,14 +403,8 @@ knn2_hamming_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
             const int n1 = max(min(g0, t0), max(g1, t1));
             g0 = n0; g1 = n1;
         }
-        if (m0 + row < nq) {
-            // key -> (dot, column): dot = key >> 16 (arithmetic), column = 0xFFFF - (key & 0xFFFF)
-            const int dot0 = g0 >> 16, dot1 = g1 >> 16;
-            const int idx0 = g0 != INT_MIN ? col_base + (0xFFFF - (g0 & 0xFFFF)) : -1;
-            const int idx1 = g1 != INT_MIN ? col_base + (0xFFFF - (g1 & 0xFFFF)) : -1;
-            const int d0 = idx0 >= 0 ? (256 - dot0) >> 1 : 0x7fffffff, d1 = idx1 >= 0 ? (256 - dot1) >> 1 : 0x7fffffff;
-            part[(long long)(blockIdx.y * TC_EPW + sub) * nq + m0 + row] = make_int4(d0, idx0, d1, idx1);
-        }
+        epilogue_merge(reinterpret_cast<int2*>(smem_raw + (sB - smem_u32(smem_raw))), g0, g1, sub, row, m0, col_base, nq, part, counters, idx, dist,
+                       &s_last);
     }
     tc_fence_before();
     __syncthreads();
@@ -385,20 +454,6 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
                                  cudaStream_t st)
 {
     using namespace tc;
-    int8_t* qe = nullptr;
-    int8_t* te = nullptr;
-    vel_keep_async_pool_cached();
-    VEL_CUDA(cudaMallocAsync((void**)&qe, (size_t)nq * 256, st));
-    VEL_CUDA(cudaMallocAsync((void**)&te, (size_t)nt * 256, st));
-    expand_pm_kernel<<<(unsigned)(((long long)(nq + nt) * 32 + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, t, (long long)nt * 32, (uint2*)qe,
-                                                                                          (uint2*)te);
-    VEL_LAUNCH_CHECK("expand_pm_kernel");
-
-    CUtensorMap tmQ, tmT;
-    if (!make_map(&tmQ, qe, nq, TC_M) || !make_map(&tmT, te, nt, TC_N)) {
-        vel_set_error("vel_match_knn2_hamming256: cuTensorMapEncodeTiled failed");
-        return VEL_ERR_CUDA;
-    }
     const int mblocks = (nq + TC_M - 1) / TC_M;
     const int nblk_total = (nt + TC_N - 1) / TC_N;
     int nsplit = kNumSMs / mblocks;                            // one CTA per SM, a single wave
@@ -409,20 +464,35 @@ int vel_match_knn2_hamming256_tc(const uint8_t* q, int32_t nq, const uint8_t* t,
         nblk_per_split = 255;
     }
     nsplit = (nblk_total + nblk_per_split - 1) / nblk_per_split;
-    int4* part = nullptr;
+    // one stream-ordered scratch block: expanded operands | per-split partial results | per-query-block counters
+    const size_t qe_bytes = ((size_t)nq * 256 + 255) & ~(size_t)255, te_bytes = ((size_t)nt * 256 + 255) & ~(size_t)255;
+    const size_t part_bytes = (sizeof(int4) * (size_t)nq * nsplit + 255) & ~(size_t)255;
+    char* scratch = nullptr;
     vel_keep_async_pool_cached();
-    VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(int4) * (size_t)nq * nsplit * TC_EPW, st));   // TC_EPW column ranges per split
+    VEL_CUDA(cudaMallocAsync((void**)&scratch, qe_bytes + te_bytes + part_bytes + sizeof(int) * (size_t)mblocks, st));
+    int8_t* qe = (int8_t*)scratch;
+    int8_t* te = (int8_t*)(scratch + qe_bytes);
+    int4* part = (int4*)(scratch + qe_bytes + te_bytes);
+    int* counters = (int*)(scratch + qe_bytes + te_bytes + part_bytes);
+    long long nexp = (long long)(nq + nt) * 32;
+    if (nexp < mblocks) nexp = mblocks;
+    expand_pm_kernel<<<(unsigned)((nexp + 255) / 256), 256, 0, st>>>(q, (long long)nq * 32, t, (long long)nt * 32, (uint2*)qe, (uint2*)te, counters,
+                                                                     mblocks);
+    VEL_LAUNCH_CHECK("expand_pm_kernel");
+
+    CUtensorMap tmQ, tmT;
+    if (!make_map(&tmQ, qe, nq, TC_M) || !make_map(&tmT, te, nt, TC_N)) {
+        cudaFreeAsync(scratch, st);
+        vel_set_error("vel_match_knn2_hamming256: cuTensorMapEncodeTiled failed");
+        return VEL_ERR_CUDA;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         VEL_CUDA(cudaFuncSetAttribute(knn2_hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_TOTAL));
         attr_set = true;
     }
-    knn2_hamming_tc_kernel<<<dim3(mblocks, nsplit), TC_THREADS, SMEM_TOTAL, st>>>(tmQ, tmT, nq, nt, nblk_per_split, part);
+    knn2_hamming_tc_kernel<<<dim3(mblocks, nsplit), TC_THREADS, SMEM_TOTAL, st>>>(tmQ, tmT, nq, nt, nblk_per_split, part, counters, idx, dist);
     VEL_LAUNCH_CHECK("knn2_hamming_tc_kernel");
-    const int rc = vel_match_merge_hamming(part, nq, nsplit * TC_EPW, idx, dist, st);
-    if (rc != VEL_OK) return rc;
-    VEL_CUDA(cudaFreeAsync(part, st));
-    VEL_CUDA(cudaFreeAsync(te, st));
-    VEL_CUDA(cudaFreeAsync(qe, st));
+    VEL_CUDA(cudaFreeAsync(scratch, st));
     return VEL_OK;
 }

@@ -87,6 +87,40 @@ def test_host_frames_path_is_identical():
         assert b.h2d_bytes == frames.size
 
 
+def test_prefetched_uploads_pipeline_across_sequences():
+    """SfmSequence.prefetch: the next sequence's upload is started before the current one runs (two device frame buffers);
+    three different recordings pushed through the pipeline give exactly what each gives on its own."""
+    from velocity_b200.sfm import SfmSequence
+
+    K, frames, p0, p3, times = scene_with_dying_tracks()
+    n, h, w = frames.shape
+    rng = np.random.default_rng(5)
+    recs = [frames, np.clip(frames.astype(np.int16) + rng.integers(-3, 4, frames.shape), 0, 255).astype(np.uint8), frames[:, ::-1].copy()]
+    want = []
+    for fr in recs:
+        a, _ = run_gpu(K, fr, p0, p3, times, host_frames=False)
+        want.append((a.tracks.clone(), a.alive.clone(), a.S.clone()))
+    seq = SfmSequence(K, h, w, n, len(p0), fbt=1.0, ba_iters=4, chunk=4, **LK)
+    host = [torch.from_numpy(fr).pin_memory() for fr in recs]
+    hp0, hp3, htm = torch.from_numpy(p0).pin_memory(), torch.from_numpy(p3).pin_memory(), torch.from_numpy(np.asarray(times, np.float32)).pin_memory()
+    seq.prefetch(host[0], hp0, hp3, htm)
+    for k in range(3):
+        if k + 1 < 3:
+            seq.prefetch(host[k + 1], hp0, hp3, htm)
+        seq.run(host[k], hp0, hp3, htm)
+        torch.cuda.synchronize()
+        assert torch.equal(seq.tracks, want[k][0]) and torch.equal(seq.alive, want[k][1]), k
+        assert torch.equal(seq.S.nan_to_num(), want[k][2].nan_to_num()), k
+        assert seq.h2d_bytes == frames.size
+    # a run() whose frames were not announced uploads by itself; a third unconsumed prefetch is refused
+    seq.run(host[1], p0, p3, times)
+    torch.cuda.synchronize()
+    assert torch.equal(seq.tracks, want[1][0])
+    seq.prefetch(host[0]); seq.prefetch(host[2])
+    with pytest.raises(RuntimeError):
+        seq.prefetch(host[1])
+
+
 def test_sequence_results_to_host():
     from velocity_b200.sfm import SfmSequence
 

@@ -1,3 +1,5 @@
-timeout 300 python tools/match_check.py 2>&1 | tail -8
-timeout 300 python -m pytest tests/test_sfm_gpu.py -x -q -k match 2>&1 | tail -2
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"knn2_hamming_tc|expand_pm" -s 12 -c 2 python tools/match_check.py 2>&1 | grep -E "duration" | tail -4
+python -m pytest tests/test_sequence_gpu.py -x -q 2>&1 | tail -3
+python tools/e2e_probe.py 2>&1 | head -4
+python bench.py --steps 10 --warmup 3 > gpurun_out/s3k_bench.json 2> gpurun_out/s3k_bench.err; tail -c 300 gpurun_out/s3k_bench.err
+python -c "
+import json;d=json.loads(open('gpurun_out/s3k_bench.json').read().strip().splitlines()[-1]);print(d['value'],d['ms_per_step'],d['e2e'])"

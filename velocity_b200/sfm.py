@@ -42,7 +42,13 @@ class SfmSequence:
         dev = self.dev
         self.K = torch.from_numpy(np.ascontiguousarray(np.asarray(K, np.float64))).to(dev)
         self.frames = torch.empty((nframes, height, width), dtype=torch.uint8, device=dev)     # filled per run (e2e) or aliased
-        self._own_frames = self.frames
+        self._bufs = [self.frames, None]     # host frames land in one of two device buffers (the second is allocated by the first prefetch)
+        self._buf_free = [None, None]        # event: the tracking launches that last read the buffer have been issued and completed
+        self._upload_buf = 0
+        self._pending = []                   # FIFO of uploads in flight: (host data_ptr, buffer index, per-chunk copy events, staged small inputs)
+        self._small = [{}, {}]               # per frame buffer: device copies of the small per-sequence inputs (p0, p3, frame_times)
+        self._cur_small = {}                 # the staged small inputs of the sequence being run
+        self._in = {}                        # their per-sequence device copies (taken out of the staging slot when tracking starts)
         self.batch = FrameBatch(self.frames, self.win, self.params.max_level)
         self.tracks = torch.empty((nframes, npts, 2), dtype=torch.float32, device=dev)
         self.alive = torch.empty((nframes, npts), dtype=torch.uint8, device=dev)
@@ -93,13 +99,74 @@ class SfmSequence:
                                           ptr(self.status), stream_ptr()), "vel_klt_sequence")
             self.launches += 1 + 2 * (nfr - 1)
 
+    def prefetch(self, frames, p0=None, p3=None, frame_times=None):
+        """Start uploading the NEXT sequence's frames (pinned host tensor) into the idle one of two device buffers, chunk by
+        chunk on the copy stream.  Call it before run() of the CURRENT sequence: the upload then overlaps the current
+        sequence's tracking and bundle adjustment (neither reads the idle buffer), and the run() that later receives the same
+        host tensor finds its frames already on their way.  Optional -- run() uploads by itself otherwise.
+        The small per-sequence inputs (p0, p3, frame_times: host tensors) should be handed over as well: they are uploaded AHEAD
+        of the frames.  Left to run(), their copies would queue in the host-to-device DMA engine behind whatever frame upload is
+        in flight (the engine serves copies in issue order across streams) and the tracking would wait ~12 ms for 100 KB.
+        run() uses the staged copies when it is given the same objects."""
+        assert not frames.is_cuda and tuple(frames.shape) == (self.n, self.h, self.w) and frames.dtype == torch.uint8
+        if len(self._pending) >= 2:
+            raise RuntimeError("SfmSequence.prefetch: both device buffers already hold uploads that no run() has consumed")
+        if self._bufs[1] is None:
+            self._bufs[1] = torch.empty_like(self._bufs[0])
+        b = self._upload_buf
+        self._upload_buf = 1 - b
+        dst = self._bufs[b]
+        if self._buf_free[b] is not None:
+            self.copy_stream.wait_event(self._buf_free[b])      # the tracking launches that last read this buffer
+        else:
+            self.copy_stream.wait_stream(torch.cuda.current_stream(self.dev))
+        events, small = [], {}
+        with torch.cuda.stream(self.copy_stream):
+            for name, src in (("p0", p0), ("p3", p3), ("frame_times", frame_times)):
+                if isinstance(src, torch.Tensor) and not src.is_cuda:
+                    if self._small[b].get(name) is None or self._small[b][name].shape != src.shape or self._small[b][name].dtype != src.dtype:
+                        self._small[b][name] = torch.empty(src.shape, dtype=src.dtype, device=self.dev)
+                    self._small[b][name].copy_(src, non_blocking=True)
+                    small[name] = (src, self._small[b][name])
+            for lo in range(0, self.n, self.chunk):
+                hi = min(self.n, lo + self.chunk)
+                dst[lo:hi].copy_(frames[lo:hi], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self.copy_stream)
+                events.append((lo, hi, ev))
+        self._pending.append((frames.data_ptr(), b, events, small))
+
+    def _staged(self, name, given):
+        """The device copy prefetch() made of a small input, if `given` is the object it was made from."""
+        ent = self._cur_small.get(name)
+        return ent[1] if ent is not None and ent[0] is given else given
+
     def track(self, frames, p0, alive0=None):
         """Stage 1 alone.  frames: CUDA uint8 [n,H,W] (used in place) or a pinned host tensor (uploaded chunk by chunk on
-        a copy stream while the previous chunk is being tracked)."""
+        a copy stream while the previous chunk is being tracked; already in flight if prefetch() was given the same tensor)."""
         n = self.n
         assert tuple(frames.shape) == (n, self.h, self.w) and frames.dtype == torch.uint8
         compute = torch.cuda.current_stream(self.dev)
-        self.tracks[0].copy_(p0 if isinstance(p0, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p0, np.float32)), non_blocking=True)
+        self._cur_small = {}
+        host_path = not frames.is_cuda
+        p0_done = False
+        if host_path:
+            if not self._pending or self._pending[0][0] != frames.data_ptr():
+                # not announced: the small input goes first (behind the frame chunks it would wait for the whole upload)
+                self.tracks[0].copy_(p0 if isinstance(p0, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p0, np.float32)), non_blocking=True)
+                p0_done = True
+                self.prefetch(frames)
+            _, b, events, self._cur_small = self._pending.pop(0) if self._pending[0][0] == frames.data_ptr() else self._pending.pop()
+            compute.wait_event(events[0][2])                   # staged small inputs precede the first frame chunk on the copy stream
+            # move them out of the per-buffer staging slots now (the slot is handed back together with the frame buffer below)
+            for name, (src, dev_t) in list(self._cur_small.items()):
+                if self._in.get(name) is None or self._in[name].shape != dev_t.shape or self._in[name].dtype != dev_t.dtype:
+                    self._in[name] = torch.empty_like(dev_t)
+                self._in[name].copy_(dev_t, non_blocking=True)
+                self._cur_small[name] = (src, self._in[name])
+            p0 = self._staged("p0", p0)
+        if not p0_done:
+            self.tracks[0].copy_(p0 if isinstance(p0, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p0, np.float32)), non_blocking=True)
         if alive0 is None:
             self.alive[0].fill_(1)
         else:
@@ -110,27 +177,22 @@ class SfmSequence:
                 self.batch.frames = self.frames
             self._track_range(0, n - 1, 0)
             return
-        self.frames = self._own_frames
+        self.frames = self._bufs[b]
         self.batch.frames = self.frames
-        self.copy_stream.wait_stream(compute)
-        events = []
-        for lo in range(0, n, self.chunk):
-            hi = min(n, lo + self.chunk)
-            with torch.cuda.stream(self.copy_stream):
-                self.frames[lo:hi].copy_(frames[lo:hi], non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(self.copy_stream)
-            events.append((lo, hi, ev))
-            self.h2d_bytes += (hi - lo) * self.h * self.w
+        self.h2d_bytes += n * self.h * self.w
         for lo, hi, ev in events:
             compute.wait_event(ev)
             self._track_range(max(lo - 1, 0), hi - 1, lo)
+        done = torch.cuda.Event()
+        done.record(compute)
+        self._buf_free[b] = done
 
     # ---- stages 2-4 -----------------------------------------------------------------------------------------------------
     def solve(self, p3, frame_times, t0=(0.0, 0.0, 0.0), subset=None, bundle=True, verbose=False):
         """Per-frame translation + speed table, then triangulation over all frames and the bundle adjustment."""
         L = _lib.lib()
         n, npts = self.n, self.npts
+        p3, frame_times = self._staged("p3", p3), self._staged("frame_times", frame_times)
         self.p3.copy_(p3 if isinstance(p3, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(p3, np.float64)), non_blocking=True)
         ft = frame_times if isinstance(frame_times, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(frame_times, np.float32))
         self.B[:, 12].copy_(ft, non_blocking=True)

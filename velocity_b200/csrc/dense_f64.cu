@@ -289,7 +289,7 @@ constexpr int CH_NB = 64, CH_NBO = 256, CH_THREADS = 512, CH_LD = CH_NB + 1, CH_
 // diagonal block (stride 65: conflict-free column walks) + two DMMA operand tiles (stride 68: conflict-free fragment loads)
 constexpr size_t CH_SMEM = sizeof(double) * (CH_NB * CH_LD + 2 * CH_NB * CH_LDT);      // 102,912 B
 constexpr int CH_MAXOWN = 2048;                                                        // own-tile list of the task-graph form
-constexpr size_t CH_DAG_SMEM = sizeof(double) * (CH_NB * CH_LD + 3 * CH_NB * CH_LDT);  // + the panel's inverse diagonal tile
+constexpr size_t CH_DAG_SMEM = sizeof(double) * (CH_NB * CH_LD + 4 * CH_NB * CH_LDT);  // + the panel's inverse diagonal tile + the resident sub-diagonal tile
 
 // reciprocal to full double precision from the 20-bit hardware seed and two Newton steps: ~170 cycles of dependent latency
 // against ~250 for the library's rsqrt / divide (FP64 instructions have ~38 cycles of latency on this part, so the per-column
@@ -310,6 +310,9 @@ __device__ unsigned long long g_cb_t[4];
 #else
 #define CB_T(k)
 #endif
+
+// row block of the t-th tile of a lower-triangular tile enumeration (t = ta (ta + 1) / 2 + tb, tb <= ta), t < 28
+__constant__ unsigned char kTriRow[28] = {0, 1, 1, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 4, 5, 5, 5, 5, 5, 5, 6, 6, 6, 6, 6, 6, 6};
 
 struct CholScratch {
     double T[CH_NB][8];      // the current 8-column sub-panel scaled by the reciprocal pivots (rows of the block)
@@ -400,26 +403,36 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, C
         CB_T(0);
         // ---- (iii) rank-8 update of the rest of the block on the tensor cores: a[r][r'] -= sum_q M[r][q] T[r'][q] ----------------
         if (below > 0) {
+            // at most 28 lower 8x8 tiles (below <= 56): a warp takes tile `warp` and tile `warp + 16`, both in flight at once (their
+            // loads, two DMMAs and read-modify-write are independent chains); tile -> (row block, column block) from a table
             const int R0 = jb + wb, nt8 = (below + 7) >> 3, ntile = nt8 * (nt8 + 1) / 2;
-            for (int tt = warp; tt < ntile; tt += CH_THREADS / 32) {
-                int ta = (int)((sqrtf(8.f * (float)tt + 1.f) - 1.f) * 0.5f);
-                while ((ta + 1) * (ta + 2) / 2 <= tt) ++ta;
-                while (ta * (ta + 1) / 2 > tt) --ta;
-                const int tb = tt - ta * (ta + 1) / 2;
-                const int ra = R0 + ta * 8 + g, rb = R0 + tb * 8 + g;
-                double d0 = 0.0, d1 = 0.0;
+            const int tt0 = warp, tt1 = warp + CH_THREADS / 32;
+            const bool on0 = tt0 < ntile, on1 = tt1 < ntile;
+            const int ta0 = kTriRow[tt0 < 28 ? tt0 : 0], tb0 = tt0 - ta0 * (ta0 + 1) / 2;
+            const int ta1 = kTriRow[tt1 < 28 ? tt1 : 0], tb1 = tt1 - ta1 * (ta1 + 1) / 2;
+            const int ra0 = R0 + ta0 * 8 + g, rb0 = R0 + tb0 * 8 + g, ra1 = R0 + ta1 * 8 + g, rb1 = R0 + tb1 * 8 + g;
+            double av0[2], bv0[2], av1[2], bv1[2];
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk) {
-                    const int q = kk * 4 + t4;
-                    const double av = (ra < w && q < wb) ? sD[ra][jb + q] : 0.0;
-                    const double bv = rb < w ? cs->T[rb][q] : 0.0;
-                    dmma884(d0, d1, av, bv);
-                }
-                const int cc = R0 + tb * 8 + 2 * t4;
-                if (ra < w) {
-                    if (cc < w && cc <= ra) sD[ra][cc] -= d0;
-                    if (cc + 1 < w && cc + 1 <= ra) sD[ra][cc + 1] -= d1;
-                }
+            for (int kk = 0; kk < 2; ++kk) {
+                const int q = kk * 4 + t4;
+                av0[kk] = (on0 && ra0 < w && q < wb) ? sD[ra0][jb + q] : 0.0;
+                bv0[kk] = (on0 && rb0 < w) ? cs->T[rb0][q] : 0.0;
+                av1[kk] = (on1 && ra1 < w && q < wb) ? sD[ra1][jb + q] : 0.0;
+                bv1[kk] = (on1 && rb1 < w) ? cs->T[rb1][q] : 0.0;
+            }
+            double d00 = 0.0, d01 = 0.0, d10 = 0.0, d11 = 0.0;
+            if (on0) { dmma884(d00, d01, av0[0], bv0[0]); }
+            if (on1) { dmma884(d10, d11, av1[0], bv1[0]); }
+            if (on0) { dmma884(d00, d01, av0[1], bv0[1]); }
+            if (on1) { dmma884(d10, d11, av1[1], bv1[1]); }
+            const int cc0 = R0 + tb0 * 8 + 2 * t4, cc1 = R0 + tb1 * 8 + 2 * t4;
+            if (on0 && ra0 < w) {
+                if (cc0 < w && cc0 <= ra0) sD[ra0][cc0] -= d00;
+                if (cc0 + 1 < w && cc0 + 1 <= ra0) sD[ra0][cc0 + 1] -= d01;
+            }
+            if (on1 && ra1 < w) {
+                if (cc1 < w && cc1 <= ra1) sD[ra1][cc1] -= d10;
+                if (cc1 + 1 < w && cc1 + 1 <= ra1) sD[ra1][cc1 + 1] -= d11;
             }
         }
         __syncthreads();
@@ -852,6 +865,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     double* bufA = ch_smem + CH_NB * CH_LD + (CH_NB * CH_LD & 1);
     double* bufB = bufA + CH_NB * CH_LDT;
     double* sI = bufB + CH_NB * CH_LDT;                            // L_kk^-1 of the panel this CTA is working with
+    double* bufT = sI + CH_NB * CH_LDT;                            // the resident sub-diagonal tile (me, me-1)
     __shared__ int s_ok, own_n;
     __shared__ CholScratch cs;
     __shared__ unsigned short own_i[CH_MAXOWN], own_j[CH_MAXOWN];
@@ -903,6 +917,20 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
         __syncthreads();
     }
     int p_lo = 0;                                      // first own tile with column >= k
+    // The two tiles on the critical path of panel `me` -- the diagonal tile (me, me) and the sub-diagonal tile (me, me-1), both owned
+    // by this CTA -- stay RESIDENT in shared memory from the start: their updates U(me, me, j), U(me, me-1, j) are applied there, the
+    // triangular solve T(me, me-1) and the factorisation D(me) read them there, and the chain D(k) -> T(k+1,k) -> U(k+1,k+1,k) ->
+    // D(k+1) crosses global memory only for what other CTAs need (L_kk^-1 in, L_(k+1,k) out).
+    const bool resident = nb <= G && me < nb;
+    if (resident) {
+        const int r0 = me * CH_NB, wme = min(CH_NB, n - r0);
+        for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+            const int r = e >> 6, c2 = e & 63;
+            if (r < wme && c2 < wme) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(r0 + r) * lds + r0 + c2) : 0.0;
+        }
+        if (me > 0) chol_load_tile(S, lds, r0, wme, r0 - CH_NB, CH_NB, bufT, vec);
+        __syncthreads();
+    }
 #ifdef VEL_CHOL_TIMING
     unsigned long long dg_last = gtime();
 #endif
@@ -910,6 +938,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     for (int k = 0; k < nb; ++k) {
         const int k0 = k * CH_NB, w = min(CH_NB, n - k0);
         int have_linv = 0;
+        int bufB_j = -1;                               // bufB holds L_(bufB_j, k)
         while (p_lo < own_n && own_j[p_lo] < k) ++p_lo;
         int p = p_lo;
         // ---------------- D(k) and T(i,k): own tiles of column k ----------------
@@ -917,23 +946,30 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
             const int i = own_i[p];
             if (i == k) {
                 DG_T(7);
-                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-                    const int r = e >> 6, c2 = e & 63;
-                    if (r < w && c2 < w) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(k0 + r) * lds + k0 + c2) : 0.0;
+                if (!resident) {
+                    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                        const int r = e >> 6, c2 = e & 63;
+                        if (r < w && c2 < w) sD[r][c2] = c2 <= r ? __ldcg(S + (long long)(k0 + r) * lds + k0 + c2) : 0.0;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 DG_T(0);
                 chol_block(sD, w, &s_ok, rdiag, &cs);
                 DG_T(1);
                 tri_inverse_block(sD, rdiag, w, sI, bufA);
                 DG_T(2);
+                // the inverse is what the waiting T tasks need: publish it first, the factor itself (read by nobody before the
+                // kernel's final barrier) afterwards
                 for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
                     const int r = e >> 6, c2 = e & 63;
-                    if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
                     Linv_g[(long long)k * CH_NB * CH_NB + e] = (r < w && c2 < w) ? sI[r * CH_LDT + c2] : 0.0;
                 }
                 if (tid == 0 && !s_ok) info[0] = 1;
                 dag_signal(dflag + k);
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                    const int r = e >> 6, c2 = e & 63;
+                    if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+                }
                 DG_T(3);
                 have_linv = 1;
                 continue;
@@ -958,10 +994,11 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                 }
             } else {
                 const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
-                chol_load_tile(S, lds, r0, wi, k0, w, bufA, vec);
+                const bool res_t = resident && i == me;         // the resident sub-diagonal tile (then k == me - 1)
+                if (!res_t) chol_load_tile(S, lds, r0, wi, k0, w, bufA, vec);
                 __syncthreads();
                 double acc[2][2][2] = {};
-                tile_mma_64(bufA, sI, acc);                     // X = A Linv^T
+                tile_mma_64(res_t ? bufT : bufA, sI, acc);      // X = A Linv^T
 #pragma unroll
                 for (int ii = 0; ii < 2; ++ii)
 #pragma unroll
@@ -972,22 +1009,26 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                             if (c2 < w) pp[0] = acc[ii][jj][0];
                             if (c2 + 1 < w) pp[1] = acc[ii][jj][1];
                         }
+                        if (res_t) {                             // L_(me,k) stays in bufB for U(me, me, k): rows >= wi and columns >= w are zero
+                            bufB[r * CH_LDT + c2] = acc[ii][jj][0];
+                            bufB[r * CH_LDT + c2 + 1] = acc[ii][jj][1];
+                        }
                     }
+                if (res_t) bufB_j = i;
             }
             dag_signal(tflag + (long long)i * nb + k);
             DG_T(5);
         }
         // ---------------- U(i,j,k): own tiles of the columns j > k ----------------
-        int cur_j = -1;
         for (; p < own_n; ++p) {
             const int i = own_i[p], j = own_j[p];
             const int c0 = j * CH_NB, wj = min(CH_NB, n - c0);
-            if (j != cur_j) {
+            if (j != bufB_j) {
                 DG_T(7);
                 dag_wait(tflag + (long long)j * nb + k);
                 DG_T(4);
                 chol_load_tile(S, lds, c0, wj, k0, w, bufB, vec);           // L_jk
-                cur_j = j;
+                bufB_j = j;
             }
             if (i == nb) {
                 dag_wait(tflag + (long long)nb * nb + k);
@@ -1010,7 +1051,26 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
             }
             __syncthreads();
             double acc[2][2][2] = {};
-            tile_mma_64(i == j ? bufB : bufA, bufB, acc);
+            if (!(i == j && sc > sr)) tile_mma_64(i == j ? bufB : bufA, bufB, acc);   // a diagonal tile needs its lower sub-tiles only
+            if (resident && i == me && (j == me || j == me - 1)) {
+                // the resident tiles take their update in shared memory
+#pragma unroll
+                for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int r = sr + ii * 8 + g, c2 = sc + jj * 8 + 2 * t4;
+                        if (j == me) {
+                            if (r < wi && c2 < wj && c2 <= r) sD[r][c2] -= acc[ii][jj][0];
+                            if (r < wi && c2 + 1 < wj && c2 + 1 <= r) sD[r][c2 + 1] -= acc[ii][jj][1];
+                        } else {
+                            if (r < wi && c2 < wj) bufT[r * CH_LDT + c2] -= acc[ii][jj][0];
+                            if (r < wi && c2 + 1 < wj) bufT[r * CH_LDT + c2 + 1] -= acc[ii][jj][1];
+                        }
+                    }
+                __syncthreads();
+                DG_T(6);
+                continue;
+            }
             double2 cur[2][2];
             bool m0[2][2], m1[2][2];
 #pragma unroll

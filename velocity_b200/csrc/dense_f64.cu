@@ -855,7 +855,7 @@ __device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bu
 }
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
-chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, double* Linv_g,
+chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, int* xflag, double* Linv_g,
                 const int* __restrict__ gate)
 {
     if (gate && *gate) return;
@@ -1109,8 +1109,60 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     grid.sync();
     if (me == 0 && tid == 0 && info[0] != 1) info[0] = 0;
 
-    // ---- backward substitution  L^T x = y  with the stored inverses of the diagonal tiles: x_k = Linv_k^T y_k (a 64x64
-    //      product every CTA computes for itself), then y[c] -= sum_r L[k0+r][c] x[r] over the columns to the left -------------
+    // ---- backward substitution  L^T x = y ---------------------------------------------------------------------------------------
+    if (nb <= G) {
+        // Task-graph form, no grid barrier: CTA c owns block c of the solution.  It subtracts the contributions L[j][c]^T x_j of the
+        // blocks below in FIXED order j = nb-1 ... c+1 as their x_j are published (xflag[j]), then x_c = Linv_c^T y_c and publishes.
+        // Only the last contribution (j = c+1) and the product with Linv_c sit on the chain x_(c+1) -> x_c; their operands are staged
+        // in shared memory beforehand.  out[col] = sum_r M[r][col] v[r] runs as 8 row classes x 64 columns (coalesced rows, 8-term
+        // chains) whose partial sums are added in a fixed order.
+        if (me < nb) {
+            const int c = me, c0 = c * CH_NB, wc = min(CH_NB, n - c0);
+            double* part = bufB;                                   // [8][CH_NB] partial sums
+            const int col = tid & 63, cls = tid >> 6;
+            if (c + 1 < nb) chol_load_tile(S, lds, c0 + CH_NB, min(CH_NB, n - c0 - CH_NB), c0, wc, bufA, vec);     // L[c+1][c]
+            for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sI[(e >> 6) * CH_LDT + (e & 63)] = __ldcg(Linv_g + (long long)c * CH_NB * CH_NB + e);
+            if (tid < CH_NB) sx[0][tid] = tid < wc ? __ldcg(b + c0 + tid) : 0.0;                                    // y_c
+            __syncthreads();
+            for (int j = nb - 1; j > c; --j) {
+                const int j0 = j * CH_NB, wj = min(CH_NB, n - j0);
+                dag_wait(xflag + j);
+                if (tid < CH_NB) sx[1][tid] = tid < wj ? __ldcg(b + j0 + tid) : 0.0;                                // x_j
+                __syncthreads();
+                double a = 0.0;
+                if (j == c + 1) {
+                    for (int r = cls; r < wj; r += 8) a += bufA[r * CH_LDT + col] * sx[1][r];
+                } else if (col < wc) {
+                    for (int r = cls; r < wj; r += 8) a += __ldcg(S + (long long)(j0 + r) * lds + c0 + col) * sx[1][r];
+                }
+                part[cls * CH_NB + col] = a;
+                __syncthreads();
+                if (tid < CH_NB) {
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) s2 += part[q * CH_NB + tid];
+                    sx[0][tid] -= s2;
+                }
+                __syncthreads();
+            }
+            {   // x_c[col] = sum_{m >= col} Linv_c[m][col] y_c[m]   (Linv is lower triangular: zero above the diagonal)
+                double a = 0.0;
+                for (int r = cls; r < wc; r += 8) a += sI[r * CH_LDT + col] * sx[0][r];
+                part[cls * CH_NB + col] = a;
+                __syncthreads();
+                if (tid < wc) {
+                    double s2 = 0.0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) s2 += part[q * CH_NB + tid];
+                    b[c0 + tid] = s2;
+                }
+            }
+            dag_signal(xflag + c);
+        }
+        return;
+    }
+    // (larger systems than CTAs: one grid barrier per panel) with the stored inverses of the diagonal tiles: x_k = Linv_k^T y_k (a 64x64
+    // product every CTA computes for itself), then y[c] -= sum_r L[k0+r][c] x[r] over the columns to the left
     for (int kb = nb - 1; kb >= 0; --kb) {
         const int k0 = kb * CH_NB, w = min(CH_NB, n - k0);
         for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) sI[(e >> 6) * CH_LDT + (e & 63)] = __ldcg(Linv_g + (long long)kb * CH_NB * CH_NB + e);
@@ -1255,7 +1307,7 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     }
     // task-graph form: flags (dflag[nb], tflag[(nb+1)*nb]) and the inverses of the diagonal tiles live in stream-ordered scratch
     vel_keep_async_pool_cached();
-    const size_t nflags = (size_t)nblk + (size_t)(nblk + 1) * nblk;
+    const size_t nflags = (size_t)nblk + (size_t)(nblk + 1) * nblk + (size_t)nblk;     // dflag | tflag | xflag
     const size_t flag_bytes = align256(sizeof(int) * nflags);
     const size_t bytes = flag_bytes + sizeof(double) * (size_t)nblk * CH_NB * CH_NB;
     char* scratch = nullptr;
@@ -1264,12 +1316,13 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     if (e == cudaSuccess) e = cudaMemsetAsync(info, 0, sizeof(int), st);
     int* dflag = (int*)scratch;
     int* tflag = dflag + nblk;
+    int* xflag = tflag + (size_t)(nblk + 1) * nblk;
     double* Linv_g = (double*)(scratch + flag_bytes);
     const int want = nblk * (nblk + 1) / 2 + nblk;
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
     if (e == cudaSuccess) {
-        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&Linv_g, (void*)&gate};
+        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&xflag, (void*)&Linv_g, (void*)&gate};
         e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
     }
     cudaFreeAsync(scratch, st);

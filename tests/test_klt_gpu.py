@@ -262,6 +262,33 @@ def test_full_size_against_cv2_itself(cuda):
     assert np.abs(err - qerr)[both].max() <= LK_ERR_TOL
 
 
+def test_4k_frames_and_the_10m_generator_where_most_tracks_fail(cuda):
+    """VERDICT r1 weak point 3: (a) a C5-size pair (3840 x 2160, 4 levels) and (b) SURVEY 8(d)'s literal generator (plane at 10 m:
+    up to 37 px of flow per frame, ~4 of 5 tracks fail the forward-backward gate, so the failure paths -- bounds exits at every
+    level, the minimum-eigenvalue test, 10-iteration non-convergence -- dominate) against the oracle, bit for bit."""
+    from oracle import klt_oracle as KO
+    from velocity_b200 import KLT, synth
+
+    lk = dict(winSize=(15, 15), maxLevel=3, criteria=(3, 10, 0.1))
+    frames, _ = synth.plane_sequence(2, h=2160, w=3840, seed=77, Z0=40.0)
+    pts = synth.harris_tracks(frames[0], 1536)
+    pts = np.concatenate([pts, np.float32([[3.0, 4.0], [3836.5, 2157.25], [1920.0, 6.5], [-20.0, 800.0], [3839.9, 1000.0]])])
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(frames[0], frames[1], pts, None, fbt=1.0, **lk)
+    o2, ov, oerr = KO.lk_forward_backward(frames[0], frames[1], pts, fbt=1.0, **lk)
+    ok = oerr.ravel() != 0
+    assert np.array_equal(v, ov) and np.array_equal(p2, o2) and np.array_equal(err[ok], oerr[ok])
+    assert v.mean() > 0.9
+
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    frames, _ = synth.plane_sequence(2, h=1080, w=1920, seed=1234, Z0=10.0)
+    pts = synth.harris_tracks(frames[0], 2048)
+    p2, v, err = KLT.cv2calcOpticalFlowPyrLK(frames[0], frames[1], pts, None, fbt=1.0, **lk)
+    o2, ov, oerr = KO.lk_forward_backward(frames[0], frames[1], pts, fbt=1.0, **lk)
+    ok = oerr.ravel() != 0
+    assert np.array_equal(v, ov) and np.array_equal(p2, o2) and np.array_equal(err[ok], oerr[ok])
+    assert 0.05 < v.mean() < 0.6          # the regime SURVEY describes: most tracks are lost
+
+
 def test_edge_cases_empty_single_and_errors(cuda):
     """Empty and single-point inputs, points far outside the frame (status 0, no crash), argument
     errors surfaced as RuntimeError with the C ABI's message; a point set on a pure-constant image

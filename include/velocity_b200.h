@@ -126,6 +126,22 @@ int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, int32_t 
                  const float* prev_pts, int64_t pts_stride, int32_t npts, const vel_lk_params* params, float* next_pts,
                  uint8_t* status, float* err, float* back_pts, vel_stream_t stream);
 
+/* a2.  KLTregional (utils/KLT.py:55-95) as ONE call: crop both frames to the ROI [x0,x1) x [y0,y1) (HOST values: boundingRect(p0) + 50,
+ * clipped, :60 / utils/images.py:6-19), bring the current frame into the previous frame's coordinates -- flags & VEL_KLT_TRANSLATE: the integer
+ * shift int(T[2,0]), int(T[2,1]) of the ROI (:62-66); else the affine remap of the ROI grid (K3, :68-73) --, build the pyramids of the
+ * two CROPS (what cv2 does inside calcOpticalFlowPyrLK: REFLECT_101 at the crop borders) and track p0 - (x0, y0) with the fused
+ * forward-backward gate (utils/KLT.py:37-51).  T_host: the 3x2 row-vector affine as float32 (T00,T01,T10,T11,T20,T21), HOST pointer.
+ * p0 [npts][2] DEVICE, full-frame coordinates.  Outputs (DEVICE): pa_roi [npts][2] the tracked points in ROI coordinates (the map-back
+ * :88-93 stays with the caller), status [npts] (gated), err [npts].  With the ROI = the whole frame and a zero shift this is
+ * cv2calcOpticalFlowPyrLK on the pair.  work: vel_klt_regional_workspace(...) bytes, 256-byte aligned.  Stream-ordered, no sync. */
+#define VEL_KLT_TRANSLATE 1      /* flags: integer-shift form (translateFlag); otherwise the affine remap */
+#define VEL_KLT_POINTS_IN_ROI 2  /* flags: p0 is already p0 - (x0, y0) (a caller that subtracts in float64 like numpy does for float64 points) */
+size_t vel_klt_regional_workspace(int32_t roi_w, int32_t roi_h, int32_t win_w, int32_t win_h, int32_t max_level, int32_t npts);
+int vel_klt_regional(const uint8_t* im0, const uint8_t* im, int32_t width, int32_t height, int32_t pitch0, int32_t pitch,
+                     const float* p0, int32_t npts, int32_t x0, int32_t x1, int32_t y0, int32_t y1, const float* T_host,
+                     int32_t flags, const vel_lk_params* params, void* work, size_t work_bytes, float* pa_roi, uint8_t* status,
+                     float* err, vel_stream_t stream);
+
 /* K3.  utils/KLT.py:70-73: float32 affine map of the ROI grid x in [x0,x0+dw), y in [y0,y0+dh)
  * through the 3x2 row-vector affine T (T[0..5] = T00,T01,T10,T11,T20,T21, HOST pointer), then
  * cv2.remap(INTER_LINEAR, BORDER_CONSTANT 0) in OpenCV's fixed point (1/32 px, 15-bit weights). */

@@ -262,6 +262,48 @@ def test_full_size_against_cv2_itself(cuda):
     assert np.abs(err - qerr)[both].max() <= LK_ERR_TOL
 
 
+def test_klt_regional_entry_point_equals_the_staged_calls(cuda):
+    """vel_klt_regional (one C call: crop, shift / remap, pyramids of the crops, LK + backward gate) against the same steps issued
+    one by one through vel_remap_affine_u8 / vel_pyramid_u8 / vel_lk_track on ROI views -- bit for bit, for the whole frame with a
+    zero shift, a shifted ROI at an odd offset and an affine ROI; and the argument checks of the entry point."""
+    import ctypes as C
+
+    from velocity_b200 import KLT, _lib, synth
+    from velocity_b200.device import ptr, stream_ptr
+    from velocity_b200.lk import FrameBatch, lk_params, track_pairs
+
+    im0 = synth.texture(300, 420, 9)
+    im1 = np.roll(im0, (2, -3), (0, 1))
+    d0, d1 = cuda.from_numpy(im0).cuda(), cuda.from_numpy(im1).cuda()
+    pts = synth.harris_tracks(im0[60:240, 80:340], 200, border=10) + np.float32([80, 60])
+    lk = dict(winSize=(15, 15), maxLevel=2, criteria=(3, 10, 0.1))
+    params = lk_params(fbt=1.0, **lk)
+    dp = cuda.from_numpy(pts).cuda()
+
+    def staged(prev_roi, next_roi, p_roi):
+        fa, fb = FrameBatch(prev_roi, (15, 15), 2).build(), FrameBatch(next_roi, (15, 15), 2).build()
+        out, st, err, _ = track_pairs(fa, fb, p_roi, params)
+        return out[0], st[0], err[0]
+
+    T_id = np.float32([[1, 0], [0, 1], [0, 0]])
+    a = KLT._regional_device(d0, d1, dp, 0, 420, 0, 300, T_id, True, 1.0, lk)
+    b = staged(d0, d1, dp)
+    assert all(cuda.equal(x, y) for x, y in zip(a, b)) and int(a[1].sum()) > 150
+    x0, x1, y0, y1 = 31, 391, 11, 289                       # odd offsets: unaligned ROI views
+    T_sh = np.float32([[1, 0], [0, 1], [-3.7, 2.2]])        # int() truncates toward zero: shift (-3, 2)
+    a = KLT._regional_device(d0, d1, dp, x0, x1, y0, y1, T_sh, True, 1.0, lk)
+    b = staged(d0[y0:y1, x0:x1], d1[y0 + 2:y1 + 2, x0 - 3:x1 - 3], dp - cuda.tensor([x0, y0], dtype=cuda.float32, device="cuda"))
+    assert all(cuda.equal(x, y) for x, y in zip(a, b)) and int(a[1].sum()) > 150
+    T_af = np.float32([[1.001, 0.002], [-0.002, 0.999], [-3.1, 2.3]])
+    a = KLT._regional_device(d0, d1, dp, x0, x1, y0, y1, T_af, False, 1.0, lk)
+    b = staged(d0[y0:y1, x0:x1], KLT._remap_affine_device(d1, T_af, x0, x1, y0, y1), dp - cuda.tensor([x0, y0], dtype=cuda.float32, device="cuda"))
+    assert all(cuda.equal(x, y) for x, y in zip(a, b)) and int(a[1].sum()) > 150
+    with pytest.raises(RuntimeError, match="leaves the frame"):
+        KLT._regional_device(d0, d1, dp, x0, x1, y0, y1, np.float32([[1, 0], [0, 1], [-40, 0]]), True, 1.0, lk)
+    with pytest.raises(RuntimeError, match="outside the"):
+        KLT._regional_device(d0, d1, dp, x0, 500, y0, y1, T_id, True, 1.0, lk)
+
+
 def test_4k_frames_and_the_10m_generator_where_most_tracks_fail(cuda):
     """VERDICT r1 weak point 3: (a) a C5-size pair (3840 x 2160, 4 levels) and (b) SURVEY 8(d)'s literal generator (plane at 10 m:
     up to 37 px of flow per frame, ~4 of 5 tracks fail the forward-backward gate, so the failure paths -- bounds exits at every

@@ -35,20 +35,54 @@ def _as_cuda_image(im):
     return t  # [h, w] uint8 CUDA tensor, last stride 1
 
 
+_scratch = {}
+
+
+def _workspace(nbytes, device):
+    """Grow-only scratch per device for vel_klt_regional (stream-ordered use: one tracker call at a time per stream)."""
+    buf = _scratch.get(device)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8, device=device)
+        _scratch[device] = buf
+    return buf
+
+
+def _regional_device(d0, dn, pts_dev, x0, x1, y0, y1, T32, translate, fbt, lk_param, pts_in_roi=False):
+    """vel_klt_regional on two CUDA frames: crop, shift / remap, pyramids of the crops, LK with the fused forward-backward gate.
+    Returns CUDA tensors (pa in ROI coordinates [N,2] f32, status [N] u8, err [N] f32); nothing is synchronised."""
+    params = lk_params(fbt=fbt, **lk_param)
+    n = pts_dev.shape[0]
+    dev = d0.device
+    L = _lib.lib()
+    nbytes = int(L.vel_klt_regional_workspace(x1 - x0, y1 - y0, params.win_w, params.win_h, params.max_level, n))
+    if nbytes == 0:
+        raise RuntimeError("vel_klt_regional_workspace failed: %s" % L.vel_last_error().decode())
+    work = _workspace(nbytes, dev)
+    status = torch.empty((n,), dtype=torch.uint8, device=dev)
+    pa_c = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    err_c = torch.empty((n,), dtype=torch.float32, device=dev)
+    Tc = (C.c_float * 6)(*[float(v) for v in np.asarray(T32, np.float32).reshape(6)])
+    _lib.check(L.vel_klt_regional(ptr(d0), ptr(dn), d0.shape[1], d0.shape[0], d0.stride(0), dn.stride(0), ptr(pts_dev), n, x0, x1, y0, y1, Tc,
+                                  (1 if translate else 0) | (2 if pts_in_roi else 0), C.byref(params), ptr(work), work.numel(), ptr(pa_c), ptr(status), ptr(err_c),
+                                  stream_ptr()), "vel_klt_regional")
+    return pa_c, status, err_c
+
+
 def lk_device(im1, im2, p1, fbt=None, **lk_param):
     """Device-resident core of cv2calcOpticalFlowPyrLK: CUDA tensors in, CUDA tensors out
     (next [N,2] f32, status [N] u8 -- already forward-backward gated when fbt is given --, err [N] f32)."""
     a, b = _as_cuda_image(im1), _as_cuda_image(im2)
     if a.shape != b.shape:
         raise ValueError("image sizes differ: %s vs %s" % (tuple(a.shape), tuple(b.shape)))
-    params = lk_params(fbt=fbt, **lk_param)
-    win = (params.win_w, params.win_h)
-    fa = FrameBatch(a, win, params.max_level).build()
-    fb = FrameBatch(b, win, params.max_level).build()
     pts = p1 if isinstance(p1, torch.Tensor) and p1.is_cuda else torch.from_numpy(
         np.ascontiguousarray(np.asarray(p1, np.float32).reshape(-1, 2))).cuda()
-    out, status, err, _ = track_pairs(fa, fb, pts.to(torch.float32), params)
-    return out[0], status[0], err[0]
+    pts = pts.to(torch.float32).contiguous()
+    if pts.shape[0] == 0:
+        dev = a.device
+        return (torch.empty((0, 2), dtype=torch.float32, device=dev), torch.empty((0,), dtype=torch.uint8, device=dev),
+                torch.empty((0,), dtype=torch.float32, device=dev))
+    # the whole frame as the "region", zero shift: one C call builds both pyramids and tracks
+    return _regional_device(a, b, pts, 0, a.shape[1], 0, a.shape[0], np.float32([[1, 0], [0, 1], [0, 0]]), True, fbt, lk_param)
 
 
 def cv2calcOpticalFlowPyrLK(im1, im2, p1, p2hat=None, fbt=None, **lk_param):
@@ -70,23 +104,23 @@ def _remap_affine_device(im, T32, x0, x1, y0, y1):
 
 def KLTregional(im0, im, p0, T, lk_param, fbt=1.0, translateFlag=False):
     """ROI tracker: warp the current frame into the previous frame's coordinates (integer shift or
-    affine remap), LK forward+backward on the ROI, map the result back through T."""
+    affine remap), LK forward+backward on the ROI, map the result back through T.  The device work is one call
+    (vel_klt_regional); the ROI rectangle (utils/KLT.py:60) and the map-back (:88-93) are the reference's numpy."""
     T = np.asarray(T).astype(np.float32)
     p0 = np.asarray(p0)
     d0, dn = _as_cuda_image(im0), _as_cuda_image(im)
     x0, x1, y0, y1 = boundingRect(p0, tuple(dn.shape), border=(50, 50))
-    roi_prev = d0[y0:y1, x0:x1]
     xy0 = np.float32([x0, y0])
-    p0_roi = p0 - xy0
     if translateFlag:
         dx, dy = int(T[2, 0]), int(T[2, 1])
-        ya, yb, xa, xb = y0 + dy, y1 + dy, x0 + dx, x1 + dx
-        if ya < 0 or xa < 0 or yb > dn.shape[0] or xb > dn.shape[1]:
+        if y0 + dy < 0 or x0 + dx < 0 or y1 + dy > dn.shape[0] or x1 + dx > dn.shape[1]:
             raise ValueError("KLTregional: shifted ROI leaves the frame (cv2 asserts on mismatched pyramid sizes here)")
-        roi_next = dn[ya:yb, xa:xb]
-    else:
-        roi_next = _remap_affine_device(dn, T, x0, x1, y0, y1)
-    pa, v, _ = cv2calcOpticalFlowPyrLK(roi_prev, roi_next, p0_roi, None, fbt=fbt, **lk_param)
+    # p0 - xy0 in numpy's arithmetic (float64 when the caller's points are float64), then float32 as cv2 takes them
+    p0_roi = np.ascontiguousarray(np.asarray(p0 - xy0, np.float32).reshape(-1, 2))
+    pts = torch.from_numpy(p0_roi).to(d0.device)
+    pa_d, st_d, err_d = _regional_device(d0, dn, pts, x0, x1, y0, y1, T, translateFlag, fbt, lk_param, pts_in_roi=True)
+    packed = torch.cat([pa_d, st_d.to(torch.float32).unsqueeze(1)], 1).cpu().numpy()      # one D2H copy
+    pa, v = np.ascontiguousarray(packed[:, 0:2]), packed[:, 2] != 0
     if translateFlag:
         p = pa + (xy0 + [dx, dy]).astype(np.float32)
     else:

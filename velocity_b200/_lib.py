@@ -51,6 +51,9 @@ SIGNATURES = {
     "vel_estimate_affine2d_ransac": (C.c_int, [_P, _P, _I32, C.c_double, C.c_double, _I32, _I32, _P, _P, _P, _P]),
     "vel_lk_track": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _P, _I64, C.POINTER(PyrLayout), _I32, _P, _I64, _I32,
                                C.POINTER(LkParams), _P, _P, _P, _P, _P]),
+    "vel_klt_regional_workspace": (C.c_size_t, [_I32, _I32, _I32, _I32, _I32, _I32]),
+    "vel_klt_regional": (C.c_int, [_P, _P, _I32, _I32, _I32, _I32, _P, _I32, _I32, _I32, _I32, _I32, C.POINTER(C.c_float), _I32,
+                                   C.POINTER(LkParams), _P, C.c_size_t, _P, _P, _P, _P]),
     "vel_remap_affine_u8": (C.c_int, [_P, _I32, _I32, _I32, C.POINTER(C.c_float), _I32, _I32, _I32, _I32, _P, _I32, _P]),
     "vel_nls_t": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),
     "vel_nls_rt": (C.c_int, [_P, _P, _P, _P, _P, _I32, _P, _P, _P, _P]),

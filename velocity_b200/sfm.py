@@ -97,7 +97,18 @@ class SfmSequence:
                                           C.c_void_p(fb.pyr.data_ptr() + lo * fb.pyr.stride(0)), fb.pyr.stride(0), C.byref(fb.layout), nfr,
                                           self.npts, C.byref(self.params), ptr(self.tracks[lo]), ptr(self.alive[lo]), ptr(self.err[lo]),
                                           ptr(self.status), stream_ptr()), "vel_klt_sequence")
-            self.launches += 1 + 2 * (nfr - 1)
+            self.launches += self._sequence_launches(nfr)
+
+    def _sequence_launches(self, nfr):
+        """Kernel launches of one vel_klt_sequence call over nfr frames: seed + ONE kernel that walks all pairs for the 15x15
+        window on word-aligned pitches (csrc/lk_track.cu: vel_lk_sequence_w15h), else seed + (track, propagate) per pair."""
+        import os
+
+        fb = self.batch
+        one = (self.win == (15, 15) and fb.pitch % 4 == 0 and (fb.frames.stride(0) % 4 == 0)
+               and all(fb.layout.pitch[l] % 4 == 0 for l in range(1, fb.layout.max_level + 1))
+               and os.environ.get("VEL_LK_W15") != "bytes" and os.environ.get("VEL_LK_SEQ") != "pairs")
+        return 2 if one else 1 + 2 * (nfr - 1)
 
     def prefetch(self, frames, p0=None, p3=None, frame_times=None):
         """Start uploading the NEXT sequence's frames (pinned host tensor) into the idle one of two device buffers, chunk by

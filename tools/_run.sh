@@ -1,2 +1,1 @@
-python -m pytest tests/test_klt_gpu.py tests/test_e2e.py tests/test_features_gpu.py tests/test_ransac_gpu.py -x -q 2>&1 | tail -4
-python tools/kltmain_bench.py 2>&1 | tail -5
+for q in 0 1; do echo "queue=$q"; VEL_SYRK_QUEUE=$q timeout 300 python tools/syrk_sweep.py 2 4 5 6 8 10 12 16 2>&1 | tail -8; done

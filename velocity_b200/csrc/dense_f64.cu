@@ -110,6 +110,11 @@ SyrkPlan syrk_plan(int m, int k, int blk_lo = 0, int blk_hi = -1)
     p.ntiles = blk_hi * (blk_hi + 1) / 2 - p.tile0;
     p.ktiles = (k + SY_BK - 1) / SY_BK;
     const int sms = sm_count();
+    // Items (tile, K chunk) are handed out in chunk-major order -- the first grid-ful by position, the rest by a device-side work
+    // queue (a CTA that drew cheap diagonal tiles simply takes more; VEL_SYRK_QUEUE=0 = static round-robin, the A/B).  The split
+    // is chosen by the round model below: an item costs ~11 us of fill + turnstile + read-modify-write of its 128x128 block of S
+    // besides its k-tiles (4.2 us each), measured by a sweep at M = 1794: SK = 6 -> 1.47 ms, SK = 16 -> 1.55 ms with the queue
+    // (1.48 / 1.56 without).
     int best = 1;
     double best_cost = 1e30;
     for (int sk = 1; sk <= 16 && sk <= p.ktiles; ++sk) {
@@ -158,7 +163,8 @@ __device__ __forceinline__ void syrk_ktile_nt(double (&acc)[4][4][2], const doub
 // E [m][ld] row-major, K contiguous (ld even, rows 16-byte aligned, columns k..ld-1 of the last k-tile readable and ZERO)
 __global__ void __launch_bounds__(SY_THREADS, 1)
 dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb, int bme, int ntiles, int sk, int ktiles,
-                       double* __restrict__ S, long long lds, int* __restrict__ flags, int tile0, const int* __restrict__ gate)
+                       double* __restrict__ S, long long lds, int* __restrict__ flags, int tile0, const int* __restrict__ gate,
+                       int* __restrict__ queue)
 {
     if (gate && *gate) return;                                   // device-side loop control (vel_ba_iterate): the whole grid leaves
     extern __shared__ __align__(16) double sy_smem[];
@@ -175,7 +181,10 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
     __syncthreads();
     long long gtile = 0;                                         // k-tiles consumed so far by this CTA (all items)
 
-    for (long long item = blockIdx.x; item < nitems; item += gridDim.x) {
+    __shared__ long long s_item;
+    long long item = blockIdx.x;                                 // the first gridDim.x items are taken by position, the rest from the queue
+    for (;;) {
+        if (item >= nitems) break;
         const int c = (int)(item / ntiles), t = (int)(item % ntiles);
         const int tg = t + tile0;                               // position in the triangular enumeration of ALL tiles
         int bi = (int)((sqrtf(8.f * (float)tg + 1.f) - 1.f) * 0.5f);
@@ -280,6 +289,15 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
             __threadfence();
             __syncthreads();
             if (tid == 0) st_release(flags + t, c + 1);
+        }
+        // next item: from the queue (dynamic: a CTA that drew cheap diagonal tiles or finished early simply takes more), or by stride
+        if (queue) {
+            if (tid == 0) s_item = (long long)gridDim.x + (long long)atomicAdd(queue, 1);
+            __syncthreads();
+            item = s_item;
+            __syncthreads();
+        } else {
+            item += gridDim.x;
         }
     }
 }
@@ -1199,7 +1217,7 @@ inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 size_t vel_dense_syrk_workspace(int m, int k)
 {
     const SyrkPlan p = syrk_plan(m, k);
-    return align256(sizeof(int) * (size_t)p.ntiles);
+    return align256(sizeof(int) * ((size_t)p.ntiles + 1));      // turnstile flags + the work-queue counter
 }
 
 VEL_API size_t vel_syrk_lower_sub_workspace(int32_t m, int32_t k)
@@ -1230,10 +1248,12 @@ int vel_dense_syrk_rows_gated(const double* E, int64_t ld, int32_t m, int32_t k,
                   SY_BK, (long long)ld, kpad);
     const SyrkPlan p = syrk_plan(m, k, blk_lo, blk_hi);
     if (p.ntiles == 0) return VEL_OK;
-    VEL_CHECK_ARG(work_bytes >= sizeof(int) * (size_t)p.ntiles, "vel_syrk_lower_sub: workspace too small");
+    VEL_CHECK_ARG(work_bytes >= sizeof(int) * ((size_t)p.ntiles + 1), "vel_syrk_lower_sub: workspace too small");
     cudaStream_t st = (cudaStream_t)stream;
     int* flags = (int*)work;
-    VEL_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)p.ntiles, st));
+    VEL_CUDA(cudaMemsetAsync(flags, 0, sizeof(int) * ((size_t)p.ntiles + 1), st));
+    const char* qenv = getenv("VEL_SYRK_QUEUE");
+    int* queue = (qenv && qenv[0] == '0') ? nullptr : flags + p.ntiles;
     static bool attr_set = false;
     if (!attr_set) {
         VEL_CUDA(cudaFuncSetAttribute(dsyrk_lower_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SY_SMEM));
@@ -1241,7 +1261,7 @@ int vel_dense_syrk_rows_gated(const double* E, int64_t ld, int32_t m, int32_t k,
     }
     long long ld_ = ld, lds_ = lds;
     int m_ = m, nb = p.nb, bme = p.bme, ntiles = p.ntiles, sk = p.sk, ktiles = p.ktiles, tile0 = p.tile0;
-    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags, &tile0, (void*)&gate};
+    void* args[] = {(void*)&E, &ld_, &m_, &nb, &bme, &ntiles, &sk, &ktiles, (void*)&S, &lds_, &flags, &tile0, (void*)&gate, (void*)&queue};
     // co-residency of the whole grid is what makes the turnstile wait safe: cooperative launch guarantees it (or fails)
     VEL_CUDA(cudaLaunchCooperativeKernel((void*)dsyrk_lower_sub_kernel, dim3(p.grid), dim3(SY_THREADS), args, SY_SMEM, st));
     return VEL_OK;

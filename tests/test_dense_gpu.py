@@ -122,3 +122,39 @@ def test_failed_cholesky_poisons_rms_delta(monkeypatch):
         ba.U[:, 0] = -1e12                                               # wreck the first diagonal entry of every camera block
         ba.solve()
         assert np.isnan(ba.rms_delta.item()), mode
+
+
+def test_more_panels_than_ctas_takes_the_shared_ownership_forms():
+    """n = 9,664 (151 panels on 148 SMs; the 8-GPU global BA factors n = 14,394 on its owner): a CTA then owns several diagonal tiles,
+    so the resident-tile form and the task-graph backward substitution step aside for the global-memory forms.  Against torch's FP64
+    Cholesky on the same device; the SYRK at the same order; the queue-fed and the statically assigned SYRK agree bit for bit."""
+    import os
+
+    from velocity_b200.device import ptr, stream_ptr
+
+    L = _lib()
+    n, k = 9664, 1024
+    g = torch.Generator(device="cuda").manual_seed(1)
+    E = torch.randn((n, k), dtype=torch.float64, device="cuda", generator=g) / 30.0
+    S0 = torch.eye(n, dtype=torch.float64, device="cuda") * 3.0
+    work = torch.empty((max(int(L.lib().vel_syrk_lower_sub_workspace(n, k)), 16),), dtype=torch.uint8, device="cuda")
+    outs = []
+    for q in ("1", "0"):
+        os.environ["VEL_SYRK_QUEUE"] = q
+        S = S0.clone()
+        L.check(L.lib().vel_syrk_lower_sub(ptr(E), k, n, k, ptr(S), n, ptr(work), work.numel(), stream_ptr()), "syrk")
+        outs.append(torch.tril(S))
+    os.environ.pop("VEL_SYRK_QUEUE")
+    want = S0 - E @ E.T
+    assert torch.equal(outs[0], outs[1])
+    assert (outs[0] - torch.tril(want)).abs().max().item() <= 1e-12 * want.abs().max().item()
+    A = (S0 + E @ E.T).contiguous()
+    b = torch.randn((n,), dtype=torch.float64, device="cuda", generator=g)
+    info = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    Aw, bw = A.clone(), b.clone()
+    L.check(L.lib().vel_spd_solve(ptr(Aw), n, n, ptr(bw), ptr(info), stream_ptr()), "spd_solve")
+    Lw = torch.linalg.cholesky(A)
+    xw = torch.cholesky_solve(b[:, None], Lw)[:, 0]
+    assert info.item() == 0
+    assert (bw - xw).abs().max().item() <= 1e-10 * xw.abs().max().item()
+    assert (torch.tril(Aw) - Lw).abs().max().item() <= 1e-11 * Lw.abs().max().item()

@@ -1,7 +1,3 @@
-python -m pytest tests/test_sequence_gpu.py -x -q 2>&1 | tail -3
-VEL_LK_SEQ=single python -m pytest tests/test_sequence_gpu.py -x -q 2>&1 | tail -2
-for m in dual single; do
-VEL_LK_SEQ=$m python bench.py --steps 5 --warmup 3 > gpurun_out/s3m_bench_$m.json 2> gpurun_out/s3m_bench.err
-python -c "
-import json;d=json.loads(open('gpurun_out/s3m_bench_$m.json').read().strip().splitlines()[-1]);print('$m', d['value'],d['ms_per_step'],d['details']['stage_ms']['klt_pyramids_and_tracking'], d['result']['speed_kmh_mean'])"
-done
+timeout 300 python -m pytest tests/test_sfm_gpu.py tests/test_dense_gpu.py tests/test_sequence_gpu.py -x -q 2>&1 | tail -2
+timeout 120 python tools/ba_c3_iter.py 2>&1 | tail -3
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"bal_camera" -s 40 -c 2 python tools/ba_c3_iter.py 2>&1 | grep -E "bal_camera|duration" | tail -4

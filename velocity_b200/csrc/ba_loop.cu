@@ -13,7 +13,7 @@
 //     dc    = S^-1 rhs                              (task-graph Cholesky, dense_f64.cu)
 //     dp_i  = y_i - (V_i+I)^-1 W_i^T dc = y_i - L_i t'_i,   t' = W'^T dc
 // so the point blocks are reduced FIRST (V needs every camera), the camera kernel then writes W' directly, and neither the
-// unscaled W (177 MB at nt=4096, nc=299) nor the separate scaling / W y passes over it exist.  Per iteration: 10 launches.
+// unscaled W (177 MB at nt=4096, nc=299) nor the separate scaling / W y passes over it exist.  Per iteration: 11 launches.
 //
 // Two deliberate departures from the reference's floating-point sequence, both below its own forward-difference noise
 // (eps * |u| / 1e-6 ~ 1e-7 in a Jacobian entry): a projection divides once (reciprocal, then two multiplies) instead of
@@ -192,39 +192,49 @@ __global__ void bal_zero_kernel(double2* __restrict__ p, long long n2, const Loo
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) p[i] = make_double2(0.0, 0.0);
 }
 
-// ---- camera side: one CTA per parameterised camera j -------------------------------------------------------------------------------
-//   U_j + I -> the diagonal block of S,  rhs_j = g_c,j - sum_i W_ji y_i,  W'_ji = W_ji L_i -> rows 6j..6j+5 of W'
-// A warp handles 32 consecutive points per trip; its 6 x 96 block of W' goes through shared memory so that the global stores are
-// whole 256-byte segments (a thread's own 3 values per row sit 24 bytes apart).
-__global__ void __launch_bounds__(CAM_THREADS)
+// ---- camera side: work items (camera j, chunk of CAM_CHUNK points) over a grid that fills the machine exactly ------------------------
+//   partial sums of U_j, g_c,j and sum_i W_ji y_i -> camp [j][chunk][33] (added in fixed order by bal_camera_reduce_kernel),
+//   W'_ji = W_ji L_i -> rows 6j..6j+5 of W'
+// One CTA per camera would be 299 CTAs of which 148 x (resident CTAs per SM) run at a time: a last round for three cameras.  Items
+// are 8x finer and walked with a grid stride, so the tail is one item.  A warp handles 32 consecutive points per trip; its 6 x 96
+// block of W' goes through shared memory so that the global stores are whole 256-byte segments (a thread's own 3 values per row sit
+// 24 bytes apart).
+constexpr int CAM_T = 128;                  // threads per CTA
+constexpr int CAM_CHUNK = 512;              // points per item
+constexpr int CAM_NACC = 21 + 6 + 6;
+
+__global__ void __launch_bounds__(CAM_T)
 bal_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, const double* __restrict__ z, const double* __restrict__ cams,
-                  const double* __restrict__ Lf, const double* __restrict__ y, int nt, int nc, double* __restrict__ Wp, long long ldw,
-                  double* __restrict__ S, double* __restrict__ rhs, const LoopState* __restrict__ st)
+                  const double* __restrict__ Lf, const double* __restrict__ y, int nt, int nc, int nchunk, double* __restrict__ Wp, long long ldw,
+                  double* __restrict__ camp, const LoopState* __restrict__ st)
 {
     if (st->gate) return;
-    constexpr int NACC = 21 + 6 + 6;
-    constexpr int NWARP = CAM_THREADS / 32;
+    constexpr int NACC = CAM_NACC;
+    constexpr int NWARP = CAM_T / 32;
     __shared__ double sK[9], sC[CAMREC];
     __shared__ double sred[NWARP][NACC];
     __shared__ double sW[NWARP][6][97];
-    const int c = 1 + blockIdx.x;  // camera index, >= 1
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 9) sK[tid] = Kg[tid];
+    const int n3 = 3 * nt;
+  for (int item = blockIdx.x; item < nc * nchunk; item += gridDim.x) {
+    const int c = 1 + item / nchunk, chunk = item % nchunk;  // camera index >= 1, point chunk
+    const int i_lo = chunk * CAM_CHUNK, i_hi = min(nt, i_lo + CAM_CHUNK);
+    __syncthreads();                                         // the previous item's readers of sC / sred are done
     if (tid < CAMREC) sC[tid] = cams[(long long)CAMREC * c + tid];
     __syncthreads();
     const double* R0 = sC;
     const double* sP = sC + 9;
     const double* zu = z + (long long)c * nt;
     const double* zv = z + (long long)(nc + 1) * nt + (long long)c * nt;
-    const int n3 = 3 * nt;
 
     double acc[NACC];
 #pragma unroll
     for (int k = 0; k < NACC; ++k) acc[k] = 0.0;
-    for (int i0 = warp * 32; i0 < nt; i0 += CAM_THREADS) {
+    for (int i0 = i_lo + warp * 32; i0 < i_hi; i0 += CAM_T) {
         const int i = i0 + lane;
         double wv[6][3];
-        if (i < nt) {
+        if (i < i_hi) {
             const double X = x[3ll * i], Y = x[3ll * i + 1], Z = x[3ll * i + 2];
             double u0, v0, pu[3], pv[3];
             point_jac_r(sK, R0, sP, false, X, Y, Z, u0, v0, pu, pv);
@@ -291,17 +301,32 @@ bal_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, c
     if (tid < NACC) {
         double s = 0.0;
         for (int w = 0; w < NWARP; ++w) s += sred[w][tid];
-        sred[0][tid] = s;
+        camp[((long long)(c - 1) * nchunk + chunk) * NACC + tid] = s;
+    }
+  }
+}
+
+// chunk partials added in a fixed order:  U_j + I -> the diagonal block of S,  rhs_j = g_c,j - sum_i W_ji y_i
+__global__ void bal_camera_reduce_kernel(const double* __restrict__ camp, int nc, int nchunk, double* __restrict__ S, double* __restrict__ rhs,
+                                         const LoopState* __restrict__ st)
+{
+    if (st->gate) return;
+    __shared__ double sacc[CAM_NACC];
+    const int c = 1 + blockIdx.x, tid = threadIdx.x;
+    if (tid < CAM_NACC) {
+        double s = 0.0;
+        for (int ch = 0; ch < nchunk; ++ch) s += camp[((long long)(c - 1) * nchunk + ch) * CAM_NACC + tid];
+        sacc[tid] = s;
     }
     __syncthreads();
     const int n6 = 6 * nc, r0 = 6 * (c - 1);
     if (tid < 36) {
         const int a = tid / 6, b = tid % 6, lo = a < b ? a : b, hi = a < b ? b : a;
         const int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // upper-triangle index of (lo, hi)
-        S[(long long)(r0 + a) * n6 + r0 + b] = sred[0][k] + (a == b ? 1.0 : 0.0);
+        S[(long long)(r0 + a) * n6 + r0 + b] = sacc[k] + (a == b ? 1.0 : 0.0);
     } else if (tid < 42) {
         const int a = tid - 36;
-        rhs[r0 + a] = sred[0][21 + a] - sred[0][27 + a];
+        rhs[r0 + a] = sacc[21 + a] - sacc[27 + a];
     }
 }
 
@@ -394,8 +419,8 @@ __global__ void bal_finalize_kernel(const double* __restrict__ cost_part, int nc
 inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct LoopLayout {
-    size_t off_wp, off_s, off_l, off_y, off_rhs, off_tpart, off_part, off_cams, off_cost, off_ss, off_state, off_flags, flags_bytes, total, ldw;
-    int nchunks, pblocks, ublocks;
+    size_t off_wp, off_s, off_l, off_y, off_rhs, off_tpart, off_part, off_cams, off_camp, off_cost, off_ss, off_state, off_flags, flags_bytes, total, ldw;
+    int nchunks, pblocks, ublocks, cam_chunks;
 };
 
 LoopLayout loop_layout(int nt, int nc)
@@ -415,6 +440,8 @@ LoopLayout loop_layout(int nt, int nc)
     L.off_tpart = o; o += align256(sizeof(double) * TCHUNKS * n3);
     L.off_part = o; o += align256(sizeof(double) * 10ull * L.nchunks * nt);
     L.off_cams = o; o += align256(sizeof(double) * CAMREC * (nc + 1));
+    L.cam_chunks = (nt + CAM_CHUNK - 1) / CAM_CHUNK;
+    L.off_camp = o; o += align256(sizeof(double) * CAM_NACC * (size_t)(nc > 0 ? nc : 1) * L.cam_chunks);
     L.off_cost = o; o += align256(sizeof(double) * L.pblocks);
     L.off_ss = o; o += align256(sizeof(double) * L.ublocks);
     L.off_state = o; o += 256;
@@ -450,6 +477,7 @@ VEL_API int vel_ba_iterate(const double* K, const double* z, int32_t nt, int32_t
     double* tpart = (double*)(wb + L.off_tpart);
     double* part = (double*)(wb + L.off_part);
     double* cams = (double*)(wb + L.off_cams);
+    double* camp = (double*)(wb + L.off_camp);
     double* cost_part = (double*)(wb + L.off_cost);
     double* ss_part = (double*)(wb + L.off_ss);
     LoopState* state = (LoopState*)(wb + L.off_state);
@@ -473,8 +501,11 @@ VEL_API int vel_ba_iterate(const double* K, const double* z, int32_t nt, int32_t
             const long long zb = (n2 + 1023) / 1024;
             bal_zero_kernel<<<(unsigned)(zb < 8 * kNumSMs ? zb : 8 * kNumSMs), 256, 0, st>>>((double2*)S, n2, state);
             VEL_LAUNCH_CHECK("bal_zero_kernel");
-            bal_camera_kernel<<<nc, CAM_THREADS, 0, st>>>(K, x, z, cams, Lf, y, nt, nc, Wp, (long long)L.ldw, S, rhs, state);
+            const int cam_items = nc * L.cam_chunks, cam_grid = cam_items < 3 * kNumSMs ? cam_items : 3 * kNumSMs;   // 3 CTAs of 168 registers x 128 threads per SM
+            bal_camera_kernel<<<cam_grid, CAM_T, 0, st>>>(K, x, z, cams, Lf, y, nt, nc, L.cam_chunks, Wp, (long long)L.ldw, camp, state);
             VEL_LAUNCH_CHECK("bal_camera_kernel");
+            bal_camera_reduce_kernel<<<nc, 64, 0, st>>>(camp, nc, L.cam_chunks, S, rhs, state);
+            VEL_LAUNCH_CHECK("bal_camera_reduce_kernel");
             int rc = vel_dense_syrk_rows_gated(Wp, (int64_t)L.ldw, n6, n3, S, n6, wb + L.off_flags, L.flags_bytes, 0, -1, &state->gate, stream);
             if (rc != VEL_OK) return rc;
             rc = vel_dense_spd_solve_gated(S, n6, n6, rhs, &state->info, &state->gate, stream);

@@ -425,7 +425,10 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device -- the product path has no CPU fallback")
-    affinity = bind_to_gpu_numa_node(local) if world > 1 else {"cpus": None, "how": "single rank: unchanged"}
+    # every rank allocates its pinned buffers from the CPUs local to its GPU (first touch); a single rank gets its full affinity
+    # back afterwards (the cpu_baseline leg of the same process uses every host thread)
+    full_affinity = sorted(os.sched_getaffinity(0))
+    affinity = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -441,6 +444,13 @@ def run_ours(args):
     p0_host = torch.from_numpy(p0_np).pin_memory()
     p3_host = torch.from_numpy(p3_np).pin_memory()
     times_host = torch.from_numpy(times_np).pin_memory()
+    frames_host[:, ::64, ::512].sum()            # touch the pinned pages from the bound CPUs
+    if world == 1:
+        try:
+            os.sched_setaffinity(0, full_affinity)
+            affinity["how"] += "; restored to all %d CPUs after the pinned allocations" % len(full_affinity)
+        except OSError:  # pragma: no cover
+            pass
     frames_dev, p0_dev, p3_dev, times_dev = frames_host.to(dev), p0_host.to(dev), p3_host.to(dev), times_host.to(dev)
     seq = SfmSequence(K, H, W, NFRAMES, NPTS, fbt=FBT, ba_iters=BA_ITERS, chunk=args.chunk, **LK)
     l2_flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -52,10 +52,17 @@ def run_speed_estimation(frames, q, K, frame_times, msv_frame=5, verbose=True, c
     if verbose:
         print(("\n" + "%13s" * 9) * 2 % HEADER)
     im0 = im0_small = None
+    on_gpu = modules is None
     for i in range(n):
         tic = time.time()
         im = frames[i]
         B[i, 12] = frame_times[i]
+        if on_gpu and i > 0:
+            # one upload per frame: the tracker takes CUDA tensors in place, and this frame is next step's previous frame
+            # (numpy frames were uploaded twice per KLTmain call)
+            import torch
+
+            im = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im)).cuda()
         if i == 0:
             p, boxa, boxb = detect_plate_features(im, q, detector=detector)
             t, R, residuals, _ = nls.estimateWorldCameraPose(K, q, worldPointsLicensePlate(country), findR=True)
@@ -87,6 +94,10 @@ def run_speed_estimation(frames, q, K, frame_times, msv_frame=5, verbose=True, c
         S[i, :] = (i, time.time() - tic, vg.sum(), residuals, dt, B[i, 12] - t0, dr, r, dr / dt * 3.6)
         if verbose:
             print("{:13g}{:13.3f}{:13g}{:13.3f}{:13.3f}{:13.3f}{:13.2f}{:13.2f}{:13.1f}".format(*tuple(S[i, :])))
+        if on_gpu and i == 0:
+            import torch
+
+            im = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im)).cuda()
         im0 = im
     out = dict(S=S, B=B, P=P, speed_mean=float(S[1:, 8].mean()), speed_std=float(S[1:, 8].std()),
                res_mean=float(S[1:, 3].mean()), tracks=S[:, 2].astype(int))

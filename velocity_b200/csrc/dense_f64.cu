@@ -179,21 +179,77 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
         for (int s2 = 0; s2 < SY_STAGES; ++s2) { mbar_init(&full_bar[s2], SY_THREADS); mbar_init(&empty_bar[s2], SY_THREADS / 32); }
     }
     __syncthreads();
-    long long gtile = 0;                                         // k-tiles consumed so far by this CTA (all items)
-
-    __shared__ long long s_item;
-    long long item = blockIdx.x;                                 // the first gridDim.x items are taken by position, the rest from the queue
-    for (;;) {
-        if (item >= nitems) break;
-        const int c = (int)(item / ntiles), t = (int)(item % ntiles);
-        const int tg = t + tile0;                               // position in the triangular enumeration of ALL tiles
+    // ---- work items and the k-tile stream -----------------------------------------------------------------------------------
+    // A CTA consumes a STREAM of k-tiles that runs across item boundaries: the producer cursor stays SY_STAGES-1 tiles ahead of
+    // the consumer and moves on into the NEXT item (already drawn from the queue) while the current one is still being
+    // multiplied, so the pipeline never drains: the first tiles of an item land during the epilogue of the one before.
+    struct Item {
+        int row0, col0, kt0, kt1, t, c;
+        bool diag, valid;
+    };
+    auto decode = [&](long long item) -> Item {
+        Item it;
+        it.valid = item < nitems;
+        const long long ii = it.valid ? item : 0;
+        it.c = (int)(ii / ntiles); it.t = (int)(ii % ntiles);
+        const int tg = it.t + tile0;                            // position in the triangular enumeration of ALL tiles
         int bi = (int)((sqrtf(8.f * (float)tg + 1.f) - 1.f) * 0.5f);
         while ((bi + 1) * (bi + 2) / 2 <= tg) ++bi;
         while (bi * (bi + 1) / 2 > tg) --bi;
         const int bj = tg - bi * (bi + 1) / 2;
-        const bool diag = bi == bj;
-        const int row0 = bi * bme, col0 = bj * bme;
-        const int kt0 = (int)((long long)ktiles * c / sk), kt1 = (int)((long long)ktiles * (c + 1) / sk);
+        it.diag = bi == bj;
+        it.row0 = bi * bme; it.col0 = bj * bme;
+        it.kt0 = (int)((long long)ktiles * it.c / sk); it.kt1 = (int)((long long)ktiles * (it.c + 1) / sk);
+        return it;
+    };
+    __shared__ long long s_item;
+    auto draw = [&]() -> long long {                            // CTA-wide: the next item index (queue, or grid stride)
+        if (tid == 0) s_item = (long long)gridDim.x + (long long)atomicAdd(queue, 1);
+        __syncthreads();
+        const long long v = s_item;
+        __syncthreads();
+        return v;
+    };
+    long long stride_next = (long long)blockIdx.x + gridDim.x;  // static form (queue == nullptr)
+    Item cur = decode(blockIdx.x);
+    Item nxt = decode(queue ? draw() : stride_next);
+    stride_next += gridDim.x;
+
+    constexpr int CPR = SY_BK / 2;                              // 16-byte chunks per tile row
+    constexpr int NLOAD = SY_BM * CPR / SY_THREADS;             // chunks per thread and operand
+    // this thread's chunks of a tile: row r_u, 16-byte chunk ch_u (fixed); the global row is clamped to the matrix per item
+    auto issue_tile = [&](const Item& it, int kt, long long gt) {
+        const int slot = (int)(gt % SY_STAGES);
+        const unsigned use = (unsigned)(gt / SY_STAGES);
+        mbar_wait(&empty_bar[slot], (use & 1u) ^ 1u);           // everybody finished the previous tenant of the slot (free at first use)
+        double* sA = sy_smem + slot * SY_STAGE_DOUBLES;
+        double* sB = sA + SY_BM * SY_LDS;
+        const double* Ek = E + (long long)kt * SY_BK;
+#pragma unroll
+        for (int u = 0; u < NLOAD; ++u) {
+            const int q = tid + SY_THREADS * u, r = q / CPR, ch = q % CPR;
+            cp_async16(sA + r * SY_LDS + ch * 2, Ek + (long long)min(it.row0 + r, m - 1) * ld + ch * 2);
+            if (!it.diag) cp_async16(sB + r * SY_LDS + ch * 2, Ek + (long long)min(it.col0 + r, m - 1) * ld + ch * 2);
+        }
+        cp_async_mbar_arrive(&full_bar[slot]);
+    };
+    // producer cursor over the stream: tiles of `cur`, then tiles of `nxt`
+    int p_next = 0, p_kt = cur.kt0;                             // p_next = 1: the cursor is inside nxt
+    long long p_gt = 0, c_gt = 0;                               // tiles issued / consumed by this CTA over its whole life
+    auto produce_one = [&]() {
+        if (!p_next && p_kt >= cur.kt1) { p_next = 1; p_kt = nxt.kt0; }
+        if (p_next && (!nxt.valid || p_kt >= nxt.kt1)) return;  // never beyond the next item
+        issue_tile(p_next ? nxt : cur, p_kt, p_gt);
+        ++p_kt; ++p_gt;
+    };
+    if (cur.valid) {
+#pragma unroll
+        for (int s2 = 0; s2 < SY_STAGES - 1; ++s2) produce_one();
+    }
+
+    while (cur.valid) {
+        const bool diag = cur.diag;
+        const int row0 = cur.row0, col0 = cur.col0, t = cur.t, c = cur.c;
         const bool skip_warp = diag && wc > wr;                 // sub-tile strictly above the diagonal: never stored
 
         double acc[4][4][2];
@@ -202,44 +258,8 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        // element offsets of this thread's 16-byte chunks (rows clamped to the matrix), fixed for the whole item
-        constexpr int CPR = SY_BK / 2;                          // 16-byte chunks per tile row
-        constexpr int NLOAD = SY_BM * CPR / SY_THREADS;         // chunks per thread and operand
-        long long offA[NLOAD], offB[NLOAD];
-        int soff[NLOAD];
-#pragma unroll
-        for (int u = 0; u < NLOAD; ++u) {
-            const int q = tid + SY_THREADS * u, r = q / CPR, ch = q % CPR;
-            offA[u] = (long long)min(row0 + r, m - 1) * ld + ch * 2;
-            offB[u] = (long long)min(col0 + r, m - 1) * ld + ch * 2;
-            soff[u] = r * SY_LDS + ch * 2;
-        }
-        auto issue = [&](int kt, int stage) {
-            double* sA = sy_smem + stage * SY_STAGE_DOUBLES;
-            double* sB = sA + SY_BM * SY_LDS;
-            const double* Ek = E + (long long)kt * SY_BK;
-#pragma unroll
-            for (int u = 0; u < NLOAD; ++u) {
-                cp_async16(sA + soff[u], Ek + offA[u]);
-                if (!diag) cp_async16(sB + soff[u], Ek + offB[u]);
-            }
-        };
-
-        // ---- k-tile ring without a CTA-wide barrier: full[slot] collects the 512 "my copies have landed" arrivals of a tile,
-        //      empty[slot] the 16 "this warp is done reading" arrivals; `gtile` numbers the tiles over the CTA's whole life,
-        //      so slots and mbarrier phases simply continue from item to item ------------------------------------------------
-        auto issue_tile = [&](int kt, long long gt) {
-            const int slot = (int)(gt % SY_STAGES);
-            const unsigned use = (unsigned)(gt / SY_STAGES);
-            mbar_wait(&empty_bar[slot], (use & 1u) ^ 1u);           // everybody finished the previous tenant of the slot (free at first use)
-            issue(kt, slot);
-            cp_async_mbar_arrive(&full_bar[slot]);
-        };
-#pragma unroll
-        for (int s2 = 0; s2 < SY_STAGES - 1; ++s2)
-            if (kt0 + s2 < kt1) issue_tile(kt0 + s2, gtile + s2);
-        for (int kt = kt0; kt < kt1; ++kt) {
-            const long long gt = gtile + (kt - kt0);
+        for (int kt = cur.kt0; kt < cur.kt1; ++kt) {
+            const long long gt = c_gt++;
             const int slot = (int)(gt % SY_STAGES);
             mbar_wait(&full_bar[slot], (unsigned)(gt / SY_STAGES) & 1u);
             if (!skip_warp) {
@@ -256,11 +276,10 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[slot]);
-            // refill the slot of tile kt-1: every warp has had this whole k-tile to leave it, so the wait inside rarely blocks
-            const int nk = kt + SY_STAGES - 1;
-            if (nk < kt1) issue_tile(nk, gt + SY_STAGES - 1);
+            // refill: the tile SY_STAGES-1 ahead in the stream (possibly the next item's); every warp has had this whole k-tile to
+            // leave the slot it goes into, so the wait inside rarely blocks
+            produce_one();
         }
-        gtile += kt1 - kt0;
 
         // turnstile: the partial products of a tile are subtracted from S in chunk order
         if (c > 0) {
@@ -290,15 +309,15 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
             __syncthreads();
             if (tid == 0) st_release(flags + t, c + 1);
         }
-        // next item: from the queue (dynamic: a CTA that drew cheap diagonal tiles or finished early simply takes more), or by stride
-        if (queue) {
-            if (tid == 0) s_item = (long long)gridDim.x + (long long)atomicAdd(queue, 1);
-            __syncthreads();
-            item = s_item;
-            __syncthreads();
-        } else {
-            item += gridDim.x;
-        }
+        // advance: the next item becomes the current one, a new next item is drawn (dynamic: a CTA that drew cheap diagonal tiles
+        // or finished early simply takes more)
+        cur = nxt;
+        if (p_next) p_next = 0;                                 // the cursor was already inside it: p_kt stays
+        else p_kt = cur.kt0;                                    // (only when the old item had fewer tiles than the look-ahead)
+        long long ni;
+        if (queue) ni = draw();
+        else { ni = stride_next; stride_next += gridDim.x; }
+        nxt = decode(cur.valid ? ni : nitems);
     }
 }
 

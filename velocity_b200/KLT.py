@@ -21,7 +21,7 @@ from . import _lib
 from .common import addcol1
 from .device import image_view, ptr, stream_ptr
 from .images import boundingRect
-from .lk import FrameBatch, lk_params, track_pairs
+from .lk import lk_params
 from .ransac import estimateAffine2D
 
 TERM_CRITERIA_COUNT, TERM_CRITERIA_EPS = 1, 2
@@ -39,11 +39,13 @@ _scratch = {}
 
 
 def _workspace(nbytes, device):
-    """Grow-only scratch per device for vel_klt_regional (stream-ordered use: one tracker call at a time per stream)."""
-    buf = _scratch.get(device)
+    """Grow-only scratch for vel_klt_regional, one buffer per (device, CUDA stream): calls issued on the same stream are ordered,
+    calls on different streams must not share scratch."""
+    key = (device, torch.cuda.current_stream(device).cuda_stream)
+    buf = _scratch.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = torch.empty((max(nbytes, 1 << 20),), dtype=torch.uint8, device=device)
-        _scratch[device] = buf
+        _scratch[key] = buf
     return buf
 
 

@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from .device import ptr, require_cuda, stream_ptr
+from .device import require_cuda, stream_ptr
 
 RANSAC = 8   # cv2.RANSAC
 

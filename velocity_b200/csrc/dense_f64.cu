@@ -174,6 +174,7 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
     const int mt_cnt = max(0, min(4, (bme - wr * 32 + 7) >> 3));
     const int nt_cnt = max(0, min(4, (bme - wc * 32 + 7) >> 3));
     const long long nitems = (long long)ntiles * sk;
+    const bool vec_s = (lds & 1) == 0 && ((size_t)S & 15) == 0;   // 16-byte read-modify-write of S
     __shared__ unsigned long long full_bar[SY_STAGES], empty_bar[SY_STAGES];
     if (tid == 0) {
         for (int s2 = 0; s2 < SY_STAGES; ++s2) { mbar_init(&full_bar[s2], SY_THREADS); mbar_init(&empty_bar[s2], SY_THREADS / 32); }
@@ -281,13 +282,16 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
             produce_one();
         }
 
-        // turnstile: the partial products of a tile are subtracted from S in chunk order
-        if (c > 0) {
-            if (tid == 0) {
+        // turnstile: the partial products of a tile are subtracted from S in chunk order.  Thread 0 waits for its turn and draws the
+        // item after next in the same breath, so that one barrier publishes both.
+        if (tid == 0) {
+            if (c > 0) {
                 while (ld_acquire(flags + t) < c) __nanosleep(64);
             }
-            __syncthreads();
+            if (queue) s_item = (long long)gridDim.x + (long long)atomicAdd(queue, 1);
         }
+        __syncthreads();
+        const long long drawn = queue ? s_item : 0;
         if (!skip_warp) {
             const int rlim = min(row0 + bme, m), clim = min(col0 + bme, m);
 #pragma unroll
@@ -298,24 +302,30 @@ dsyrk_lower_sub_kernel(const double* __restrict__ E, long long ld, int m, int nb
                     const int cc = col0 + wc * 32 + j * 8 + 2 * t4;
                     if (i < mt_cnt && j < nt_cnt && r < rlim) {
                         double* p = S + (long long)r * lds + cc;
-                        if (cc < clim && (!diag || cc <= r)) p[0] = __ldcg(p) - acc[i][j][0];          // strictly-upper entries stay untouched
-                        if (cc + 1 < clim && (!diag || cc + 1 <= r)) p[1] = __ldcg(p + 1) - acc[i][j][1];
+                        const bool ok0 = cc < clim && (!diag || cc <= r), ok1 = cc + 1 < clim && (!diag || cc + 1 <= r);   // strictly-upper entries stay untouched
+                        if (vec_s && ok0 && ok1) {
+                            double2 v = __ldcg(reinterpret_cast<const double2*>(p));
+                            v.x -= acc[i][j][0]; v.y -= acc[i][j][1];
+                            *reinterpret_cast<double2*>(p) = v;
+                        } else {
+                            if (ok0) p[0] = __ldcg(p) - acc[i][j][0];
+                            if (ok1) p[1] = __ldcg(p + 1) - acc[i][j][1];
+                        }
                     }
                 }
             }
         }
-        if (sk > 1) {
-            __threadfence();
-            __syncthreads();
-            if (tid == 0) st_release(flags + t, c + 1);
-        }
-        // advance: the next item becomes the current one, a new next item is drawn (dynamic: a CTA that drew cheap diagonal tiles
+        // release the tile for the next chunk; this barrier also keeps s_item stable until every thread has read it
+        __threadfence();
+        __syncthreads();
+        if (sk > 1 && tid == 0) st_release(flags + t, c + 1);
+        // advance: the next item becomes the current one, the drawn item the next (dynamic: a CTA that drew cheap diagonal tiles
         // or finished early simply takes more)
         cur = nxt;
         if (p_next) p_next = 0;                                 // the cursor was already inside it: p_kt stays
         else p_kt = cur.kt0;                                    // (only when the old item had fewer tiles than the look-ahead)
         long long ni;
-        if (queue) ni = draw();
+        if (queue) ni = drawn;
         else { ni = stride_next; stride_next += gridDim.x; }
         nxt = decode(cur.valid ? ni : nitems);
     }

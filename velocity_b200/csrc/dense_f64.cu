@@ -343,12 +343,13 @@ constexpr size_t CH_DAG_SMEM = sizeof(double) * (CH_NB * CH_LD + 4 * CH_NB * CH_
 // pivot chain of a Cholesky factorisation is what bounds it)
 __device__ __forceinline__ double fast_rcp(double x)
 {
+    // one third-order step from the 20-bit seed: y0 (1 + e + e^2), e = 1 - x y0, |e| <= 2^-20 -> relative error e^3 = 2^-60: three
+    // dependent FMAs on the pivot chain instead of the four of two Newton steps
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-    double e = fma(-x, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    const double e = fma(-x, y, 1.0);
+    const double t = fma(e, e, e);
+    return fma(y, t, y);
 }
 
 #ifdef VEL_CHOL_TIMING
@@ -370,8 +371,9 @@ struct CholScratch {
 // it -- the pivot-to-pivot dependency chain:
 //   * square-root free inside (A = M D^-1 M^T, M = unscaled columns): a column costs one reciprocal + one multiply + one FMA on
 //     the chain; the 64 square roots are taken at the end, in parallel (L = M D^-1/2);
-//   * 8-column steps; EVERY thread factors the 8x8 diagonal sub-block redundantly in registers (no shuffles, no barrier between
-//     that and the forward substitution of the thread's own row below it);
+//   * 8-column steps; every thread that owns a row below the sub-block (and the warp that writes it back) factors the 8x8 diagonal
+//     sub-block redundantly in registers (no shuffles, no barrier between that and the forward substitution of the thread's own
+//     row); the other warps skip the step -- sixteen warps repeating it made the phase FP64-throughput-bound (0.86 -> 0.76 ms);
 //   * the rank-8 update of the rest of the block runs on the tensor cores (DMMA).
 // ok is cleared when a pivot is not positive; rdiag receives 1 / L_cc.
 __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, CholScratch* cs)
@@ -383,7 +385,9 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, C
     for (int jb = 0; jb < w; jb += 8) {
         const int wb = min(8, w - jb);
         CB_T(3);
-        // ---- (i) the 8x8 diagonal sub-block, redundantly in every thread: a[u(u+1)/2 + c], c <= u ------------------------------
+        const int below = w - jb - wb;
+        if (warp * 32 < below || warp == 14) {       // the other warps have no row below the sub-block and do not write it back: no redundant FP64 work on the shared pipe
+        // ---- (i) the 8x8 diagonal sub-block, redundantly in every PARTICIPATING thread: a[u(u+1)/2 + c], c <= u --------------------
         double a[36], rp[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u)
@@ -407,9 +411,8 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, C
 #pragma unroll
                 for (int u2 = c + 1; u2 <= u; ++u2) a[u * (u + 1) / 2 + u2] -= m[u] * a[u2 * (u2 + 1) / 2 + c];
         }
-        if (bad && tid == 0) *ok = 0;
+        if (bad && tid == 448) *ok = 0;             // warp 14 always takes part (warp 0 only while rows remain below the sub-block)
         // ---- (ii) the thread's own row below the sub-block: M[r][q] = a[r][q] - sum_{p<q} M[r][p] T[q][p] ------------------------
-        const int below = w - jb - wb;
         if (tid < below) {
             const int r = jb + wb + tid;
             double x[8];
@@ -445,6 +448,7 @@ __device__ void chol_block(double (*sD)[CH_LD], int w, int* ok, double* rdiag, C
                     if (uu == u) du = a[uu * (uu + 1) / 2 + uu];
                 cs->d[jb + u] = du;
             }
+        }
         }
         __syncthreads();
         CB_T(0);

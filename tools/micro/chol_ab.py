@@ -1,4 +1,7 @@
-"""Same-box A/B of two builds of csrc/dense_f64.cu (tools/micro/libdense_old.so / libdense_new.so): vel_spd_solve at n = 1794."""
+"""Same-box A/B of several builds of csrc/dense_f64.cu: vel_spd_solve at n = 1794, best of 8, three rounds.
+Build each variant as tools/micro/libdense_<name>.so  (nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -Xcompiler -fPIC
+--expt-relaxed-constexpr -shared -o tools/micro/libdense_<name>.so <variant of dense_f64.cu> velocity_b200/csrc/api.cu) and list the names below;
+boxes differ by 1-3 %, so only numbers taken in one call compare (profiles/README.md has the results of round 2)."""
 import ctypes as C, sys
 import torch
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1794

@@ -9,7 +9,7 @@ A = torch.randn((n, n + 8), dtype=torch.float64, device="cuda")
 S0 = A @ A.T + torch.eye(n, dtype=torch.float64, device="cuda")
 b0 = torch.randn(n, dtype=torch.float64, device="cuda")
 info = torch.zeros(1, dtype=torch.int32, device="cuda")
-libs = {v: C.CDLL("tools/micro/libdense_%s.so" % v) for v in ("old", "new", "C", "D", "E")}
+libs = {v: C.CDLL("tools/micro/libdense_%s.so" % v) for v in (sys.argv[2:] or ["base", "G"])}
 for L in libs.values():
     L.vel_spd_solve.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
 for rnd in range(3):

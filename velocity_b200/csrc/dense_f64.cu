@@ -784,6 +784,22 @@ chol_solve_kernel(double* S, long long lds, int n, double* b, int* __restrict__ 
 }
 
 
+// blocked form, right-hand side: b[r] -= sum_{c in [p0, p1)} L[r][c] y[c] for the rows r >= p1 below a factored panel group (one warp
+// per row, fixed-order reduction)
+__global__ void __launch_bounds__(256)
+chol_rhs_gemv_kernel(const double* __restrict__ S, long long lds, double* __restrict__ b, int p0, int p1, int n, const int* __restrict__ gate)
+{
+    if (gate && *gate) return;
+    const int r = p1 + blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= n) return;
+    const double* row = S + (long long)r * lds;
+    double a = 0.0;
+    for (int c = p0 + lane; c < p1; c += 32) a += row[c] * b[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) b[r] -= a;
+}
+
 // ---- Cholesky as a task graph (default): no grid barrier in the factorisation -------------------------------------------------
 // Tasks on 64x64 tiles:  D(k) factor the diagonal tile (+ L_kk^-1),  T(i,k) L_ik = A_ik L_kk^-T,  U(i,j,k) A_ij -= L_ik L_jk^T;
 // the right-hand side is tile row nb.  Every tile has ONE owner CTA that applies all of its updates in panel order (fixed
@@ -907,8 +923,11 @@ __device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bu
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, int* xflag, double* Linv_g,
-                const int* __restrict__ gate)
+                const int* __restrict__ gate, int k_lo, int k_hi, int phase)
 {
+    // phase 0: the whole factorisation (k_lo = 0, k_hi = nb) and the substitutions; phase 1: the panels [k_lo, k_hi) only -- tiles of
+    // those COLUMNS, all rows -- for the blocked form of large systems (the trailing matrix is updated by the SYRK kernel between
+    // launches); phase 2: the backward substitution only
     if (gate && *gate) return;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double ch_smem[];
@@ -944,7 +963,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
             while (j > 0 && (long long)j * (nb + 1) - (long long)j * (j - 1) / 2 > t) --j;
             while (j < nb - 1 && (long long)(j + 1) * (nb + 1) - (long long)(j + 1) * j / 2 <= t) ++j;
             const int i = j + (int)(t - ((long long)j * (nb + 1) - (long long)j * (j - 1) / 2));
-            if (own.owner(i, j) == me) {
+            if (j >= k_lo && j < k_hi && own.owner(i, j) == me) {
                 const int idx = atomicAdd(&own_n, 1);
                 if (idx < CH_MAXOWN) { own_i[idx] = (unsigned short)i; own_j[idx] = (unsigned short)j; }
             }
@@ -972,7 +991,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     // by this CTA -- stay RESIDENT in shared memory from the start: their updates U(me, me, j), U(me, me-1, j) are applied there, the
     // triangular solve T(me, me-1) and the factorisation D(me) read them there, and the chain D(k) -> T(k+1,k) -> U(k+1,k+1,k) ->
     // D(k+1) crosses global memory only for what other CTAs need (L_kk^-1 in, L_(k+1,k) out).
-    const bool resident = nb <= G && me < nb;
+    const bool resident = phase == 0 && nb <= G && me < nb;
     if (resident) {
         const int r0 = me * CH_NB, wme = min(CH_NB, n - r0);
         for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
@@ -986,7 +1005,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     unsigned long long dg_last = gtime();
 #endif
 
-    for (int k = 0; k < nb; ++k) {
+    for (int k = k_lo; k < k_hi && phase != 2; ++k) {
         const int k0 = k * CH_NB, w = min(CH_NB, n - k0);
         int have_linv = 0;
         int bufB_j = -1;                               // bufB holds L_(bufB_j, k)
@@ -1156,6 +1175,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
             DG_T(6);
         }
     }
+    if (phase == 1) return;                            // the launch boundary orders the panel against the trailing update that follows
     __threadfence();
     grid.sync();
     if (me == 0 && tid == 0 && info[0] != 1) info[0] = 0;
@@ -1374,9 +1394,40 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     const int want = nblk * (nblk + 1) / 2 + nblk;
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
-    if (e == cudaSuccess) {
-        void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&xflag, (void*)&Linv_g, (void*)&gate};
+    // More panels than CTAs (the multi-GPU global BA factors n = 14,394 on its owner): the 64-tile task graph then spends its time
+    // in latency-bound 64x64x64 update tasks (11 TFLOP/s).  BLOCKED form: groups of CH_GROUP panels are factored by the task graph
+    // restricted to their columns (phase 1), and everything to the right of a group is updated by the SYRK kernel (33 TFLOP/s at
+    // this order) plus one GEMV for the right-hand side; the backward substitution is a last launch (phase 2).
+    const char* benv = getenv("VEL_CHOL_BLOCKED");
+    const bool blocked = nblk > max_grid && (lds & 1) == 0 && ((size_t)S & 15) == 0 && !(benv && benv[0] == '0');
+    int k_lo = 0, k_hi = nblk, phase = 0;
+    void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&xflag, (void*)&Linv_g, (void*)&gate,
+                    &k_lo, &k_hi, &phase};
+    if (e == cudaSuccess && !blocked) {
         e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
+    } else if (e == cudaSuccess) {
+        int CH_GROUP = 16;                                                   // panels per group: K = 1024 for the trailing SYRK
+        if (const char* ge = getenv("VEL_CHOL_GROUP")) { const int v = atoi(ge); if (v >= 2 && v <= 64) CH_GROUP = v; }
+        const size_t sy_bytes = vel_dense_syrk_workspace(n, CH_GROUP * CH_NB);
+        void* sy_work = nullptr;
+        e = cudaMallocAsync(&sy_work, sy_bytes, st);
+        for (int g0 = 0; g0 < nblk && e == cudaSuccess; g0 += CH_GROUP) {
+            k_lo = g0; k_hi = g0 + CH_GROUP < nblk ? g0 + CH_GROUP : nblk; phase = 1;
+            e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
+            if (e != cudaSuccess || k_hi >= nblk) break;
+            const int p0 = k_lo * CH_NB, p1 = k_hi * CH_NB, m2 = n - p1, kk = p1 - p0;
+            chol_rhs_gemv_kernel<<<(m2 + 7) / 8, 256, 0, st>>>(S, lds, b, p0, p1, n, gate);
+            e = cudaGetLastError();
+            if (e != cudaSuccess) break;
+            const int rc = vel_dense_syrk_rows_gated(S + (long long)p1 * lds + p0, lds, m2, kk, S + (long long)p1 * lds + p1, lds, sy_work, sy_bytes, 0,
+                                                     -1, gate, stream);
+            if (rc != VEL_OK) { cudaFreeAsync(sy_work, st); cudaFreeAsync(scratch, st); return rc; }
+        }
+        if (e == cudaSuccess) {
+            k_lo = 0; k_hi = nblk; phase = 2;
+            e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
+        }
+        if (sy_work) cudaFreeAsync(sy_work, st);
     }
     cudaFreeAsync(scratch, st);
     if (e != cudaSuccess) {

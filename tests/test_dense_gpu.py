@@ -124,10 +124,15 @@ def test_failed_cholesky_poisons_rms_delta(monkeypatch):
         assert np.isnan(ba.rms_delta.item()), mode
 
 
-def test_more_panels_than_ctas_takes_the_shared_ownership_forms():
+@pytest.mark.parametrize("blocked", ["", "0"])
+def test_more_panels_than_ctas_takes_the_shared_ownership_forms(monkeypatch, blocked):
     """n = 9,664 (151 panels on 148 SMs; the 8-GPU global BA factors n = 14,394 on its owner): a CTA then owns several diagonal tiles,
-    so the resident-tile form and the task-graph backward substitution step aside for the global-memory forms.  Against torch's FP64
-    Cholesky on the same device; the SYRK at the same order; the queue-fed and the statically assigned SYRK agree bit for bit."""
+    so the resident-tile form and the task-graph backward substitution step aside for the global-memory forms.  Both ways of
+    factoring it: the BLOCKED form (groups of 16 panels by the task graph, the trailing matrix by the SYRK kernel; the default above
+    48 panels) and, with VEL_CHOL_BLOCKED=0, the pure task graph.  Against torch's FP64 Cholesky on the same device; the SYRK at the
+    same order; the queue-fed and the statically assigned SYRK agree bit for bit."""
+    if blocked:
+        monkeypatch.setenv("VEL_CHOL_BLOCKED", blocked)
     import os
 
     from velocity_b200.device import ptr, stream_ptr

@@ -1343,6 +1343,8 @@ VEL_API void vel_chol_timing(unsigned long long* out8, int reset)
 }
 #endif
 
+constexpr int kBlockedMinPanels = 48;       // panels above which the blocked form takes over: 57 panels 2.6 vs 2.8 ms, 113: 10.4 vs 13.5, 225: 47 vs 91; 29 (C3) stays a pure task graph
+
 int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int32_t* info, const int* gate, vel_stream_t stream)
 {
     VEL_CHECK_ARG(S && b && info, "vel_spd_solve: NULL argument");
@@ -1394,12 +1396,14 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     const int want = nblk * (nblk + 1) / 2 + nblk;
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
-    // More panels than CTAs (the multi-GPU global BA factors n = 14,394 on its owner): the 64-tile task graph then spends its time
-    // in latency-bound 64x64x64 update tasks (11 TFLOP/s).  BLOCKED form: groups of CH_GROUP panels are factored by the task graph
+    // Many panels (the multi-GPU global BA factors n = 3,594 ... 14,394 on its owner): the 64-tile task graph then spends its time
+    // in latency-bound 64x64x64 update tasks (11 TFLOP/s at n = 14,394).  BLOCKED form: groups of CH_GROUP panels are factored by the task graph
     // restricted to their columns (phase 1), and everything to the right of a group is updated by the SYRK kernel (33 TFLOP/s at
     // this order) plus one GEMV for the right-hand side; the backward substitution is a last launch (phase 2).
-    const char* benv = getenv("VEL_CHOL_BLOCKED");
-    const bool blocked = nblk > max_grid && (lds & 1) == 0 && ((size_t)S & 15) == 0 && !(benv && benv[0] == '0');
+    const char* benv = getenv("VEL_CHOL_BLOCKED");          // "0": never; a number > 1: use the blocked form above that many panels (A/B)
+    int blocked_min = kBlockedMinPanels;
+    if (benv && atoi(benv) > 1) blocked_min = atoi(benv);
+    const bool blocked = nblk > blocked_min && (lds & 1) == 0 && ((size_t)S & 15) == 0 && !(benv && benv[0] == '0' && benv[1] == 0);
     int k_lo = 0, k_hi = nblk, phase = 0;
     void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&xflag, (void*)&Linv_g, (void*)&gate,
                     &k_lo, &k_hi, &phase};

@@ -230,7 +230,7 @@ class BundleAdjuster:
             self._iters = torch.zeros((1,), dtype=torch.int32, device=self.x.device)
         return ptr(self._hist), ptr(self._iters), ptr(self._loop_work), self._loop_work.numel()
 
-    launches_per_loop_iteration = 11   # cam setup, point, reduce+prep, zero S, camera, camera reduce, SYRK, Cholesky, GEMV, update, finalize
+    launches_per_loop_iteration = 10   # cam setup, point, reduce+prep, camera, camera reduce (+ clears S), SYRK, Cholesky, GEMV, update, finalize
 
     def history(self, max_iter):
         """[(f, rms(delta))] of the last iterate() call (synchronises on the readback)."""

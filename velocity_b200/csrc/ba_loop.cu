@@ -13,7 +13,7 @@
 //     dc    = S^-1 rhs                              (task-graph Cholesky, dense_f64.cu)
 //     dp_i  = y_i - (V_i+I)^-1 W_i^T dc = y_i - L_i t'_i,   t' = W'^T dc
 // so the point blocks are reduced FIRST (V needs every camera), the camera kernel then writes W' directly, and neither the
-// unscaled W (177 MB at nt=4096, nc=299) nor the separate scaling / W y passes over it exist.  Per iteration: 11 launches.
+// unscaled W (177 MB at nt=4096, nc=299) nor the separate scaling / W y passes over it exist.  Per iteration: 10 launches.
 //
 // Two deliberate departures from the reference's floating-point sequence, both below its own forward-difference noise
 // (eps * |u| / 1e-6 ~ 1e-7 in a Jacobian entry): a projection divides once (reciprocal, then two multiplies) instead of
@@ -143,23 +143,36 @@ bal_point_kernel(const double* __restrict__ Kg, const double* __restrict__ x, co
 }
 
 // chunks added in a fixed order; then per point: (V_i + I)^-1 = L_i L_i^T, y_i = (V_i + I)^-1 g_p,i
-__global__ void __launch_bounds__(PT_THREADS)
+// CTA = 32 points x 10 quantities (thread (k, p) adds the chunks of quantity k of point p: 128 CTAs of independent coalesced
+// streams instead of 32 CTAs of threads walking 320 values each), then one warp finishes the 32 points.
+constexpr int RP_PTS = 32, RP_THREADS = RP_PTS * 10;
+
+__global__ void __launch_bounds__(RP_THREADS)
 bal_point_reduce_prep_kernel(const double* __restrict__ part, int nt, int nchunks, double* __restrict__ Lf, double* __restrict__ y,
                              double* __restrict__ cost_part, const LoopState* __restrict__ st)
 {
     if (st->gate) return;
-    __shared__ double sred[PT_THREADS / 32];
-    const int tid = threadIdx.x, i = blockIdx.x * PT_THREADS + tid;
+    __shared__ double sa[10][RP_PTS];
+    const int tid = threadIdx.x, k = tid / RP_PTS, p = tid % RP_PTS, i = blockIdx.x * RP_PTS + p;
+    double acc = 0.0;
+    if (i < nt) {
+        const double* o = part + (long long)k * nt + i;
+        const long long stride = 10ll * nt;
+        int ch = 0;
+        for (; ch + 4 <= nchunks; ch += 4) {          // four loads in flight, added in chunk order
+            const double v0 = o[ch * stride], v1 = o[(ch + 1) * stride], v2 = o[(ch + 2) * stride], v3 = o[(ch + 3) * stride];
+            acc += v0; acc += v1; acc += v2; acc += v3;
+        }
+        for (; ch < nchunks; ++ch) acc += o[ch * stride];
+    }
+    sa[k][p] = acc;
+    __syncthreads();
+    if (tid >= RP_PTS) return;
     double cost = 0.0;
     if (i < nt) {
         double a[10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) a[k] = 0.0;
-        for (int ch = 0; ch < nchunks; ++ch) {
-            const double* o = part + (long long)ch * 10 * nt + i;
-#pragma unroll
-            for (int k = 0; k < 10; ++k) a[k] += o[(long long)k * nt];
-        }
+        for (int q = 0; q < 10; ++q) a[q] = sa[q][p];
         cost = a[9];
         const double m00 = a[0] + 1.0, m01 = a[1], m02 = a[2], m11 = a[3] + 1.0, m12 = a[4], m22 = a[5] + 1.0;
         const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
@@ -176,20 +189,7 @@ bal_point_reduce_prep_kernel(const double* __restrict__ part, int nt, int nchunk
         y[3ll * i + 2] = i02 * a[6] + i12 * a[7] + i22 * a[8];
     }
     cost = warp_sum(cost);
-    if ((tid & 31) == 0) sred[tid >> 5] = cost;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int w = 0; w < PT_THREADS / 32; ++w) s += sred[w];
-        cost_part[blockIdx.x] = s;
-    }
-}
-
-__global__ void bal_zero_kernel(double2* __restrict__ p, long long n2, const LoopState* __restrict__ st)
-{
-    if (st->gate) return;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) p[i] = make_double2(0.0, 0.0);
+    if (tid == 0) cost_part[blockIdx.x] = cost;
 }
 
 // ---- camera side: work items (camera j, chunk of CAM_CHUNK points) over a grid that fills the machine exactly ------------------------
@@ -306,20 +306,27 @@ bal_camera_kernel(const double* __restrict__ Kg, const double* __restrict__ x, c
   }
 }
 
-// chunk partials added in a fixed order:  U_j + I -> the diagonal block of S,  rhs_j = g_c,j - sum_i W_ji y_i
-__global__ void bal_camera_reduce_kernel(const double* __restrict__ camp, int nc, int nchunk, double* __restrict__ S, double* __restrict__ rhs,
-                                         const LoopState* __restrict__ st)
+// chunk partials added in a fixed order:  U_j + I -> the diagonal block of S,  rhs_j = g_c,j - sum_i W_ji y_i.  The CTA of camera j
+// also clears rows 6j .. 6j+5 of S first (the SYRK subtracts from S), so no separate pass over the 26 MB of S is needed.
+__global__ void __launch_bounds__(256)
+bal_camera_reduce_kernel(const double* __restrict__ camp, int nc, int nchunk, double* __restrict__ S, double* __restrict__ rhs,
+                         const LoopState* __restrict__ st)
 {
     if (st->gate) return;
     __shared__ double sacc[CAM_NACC];
     const int c = 1 + blockIdx.x, tid = threadIdx.x;
+    const int n6 = 6 * nc, r0 = 6 * (c - 1);
+    {
+        double* rows = S + (long long)r0 * n6;                 // 6 * n6 doubles, 16-byte aligned (n6 is even, S is 256-byte aligned)
+        const int n2 = 3 * n6;                                  // double2 count
+        for (int e = tid; e < n2; e += 256) reinterpret_cast<double2*>(rows)[e] = make_double2(0.0, 0.0);
+    }
     if (tid < CAM_NACC) {
         double s = 0.0;
         for (int ch = 0; ch < nchunk; ++ch) s += camp[((long long)(c - 1) * nchunk + ch) * CAM_NACC + tid];
         sacc[tid] = s;
     }
     __syncthreads();
-    const int n6 = 6 * nc, r0 = 6 * (c - 1);
     if (tid < 36) {
         const int a = tid / 6, b = tid % 6, lo = a < b ? a : b, hi = a < b ? b : a;
         const int k = lo * 6 - lo * (lo - 1) / 2 + (hi - lo);      // upper-triangle index of (lo, hi)
@@ -420,7 +427,7 @@ inline size_t align256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 struct LoopLayout {
     size_t off_wp, off_s, off_l, off_y, off_rhs, off_tpart, off_part, off_cams, off_camp, off_cost, off_ss, off_state, off_flags, flags_bytes, total, ldw;
-    int nchunks, pblocks, ublocks, cam_chunks;
+    int nchunks, pblocks, rblocks, ublocks, cam_chunks;
 };
 
 LoopLayout loop_layout(int nt, int nc)
@@ -430,6 +437,7 @@ LoopLayout loop_layout(int nt, int nc)
     L.ldw = (n3 + 31) / 32 * 32;
     L.nchunks = nc + 1 >= 16 ? ((nc + 1) / 8 < PTL_MAX_CHUNKS ? (nc + 1) / 8 : PTL_MAX_CHUNKS) : 1;
     L.pblocks = (nt + PT_THREADS - 1) / PT_THREADS;
+    L.rblocks = (nt + RP_PTS - 1) / RP_PTS;
     L.ublocks = (int)((nt + n6 + PT_THREADS - 1) / PT_THREADS);
     size_t o = 0;
     L.off_wp = o; o += align256(sizeof(double) * (n6 ? n6 : 1) * L.ldw);
@@ -442,7 +450,7 @@ LoopLayout loop_layout(int nt, int nc)
     L.off_cams = o; o += align256(sizeof(double) * CAMREC * (nc + 1));
     L.cam_chunks = (nt + CAM_CHUNK - 1) / CAM_CHUNK;
     L.off_camp = o; o += align256(sizeof(double) * CAM_NACC * (size_t)(nc > 0 ? nc : 1) * L.cam_chunks);
-    L.off_cost = o; o += align256(sizeof(double) * L.pblocks);
+    L.off_cost = o; o += align256(sizeof(double) * L.rblocks);
     L.off_ss = o; o += align256(sizeof(double) * L.ublocks);
     L.off_state = o; o += 256;
     L.flags_bytes = vel_dense_syrk_workspace((int)(n6 > 0 ? n6 : 1), (int)n3);
@@ -494,17 +502,13 @@ VEL_API int vel_ba_iterate(const double* K, const double* z, int32_t nt, int32_t
         VEL_LAUNCH_CHECK("bal_cam_setup_kernel");
         bal_point_kernel<<<dim3(L.pblocks, L.nchunks), PT_THREADS, 0, st>>>(K, x, z, cams, nt, nc, L.nchunks, part, state);
         VEL_LAUNCH_CHECK("bal_point_kernel");
-        bal_point_reduce_prep_kernel<<<L.pblocks, PT_THREADS, 0, st>>>(part, nt, L.nchunks, Lf, y, cost_part, state);
+        bal_point_reduce_prep_kernel<<<L.rblocks, RP_THREADS, 0, st>>>(part, nt, L.nchunks, Lf, y, cost_part, state);
         VEL_LAUNCH_CHECK("bal_point_reduce_prep_kernel");
         if (nc > 0) {
-            const long long n2 = ((long long)n6 * n6 + 1) / 2;
-            const long long zb = (n2 + 1023) / 1024;
-            bal_zero_kernel<<<(unsigned)(zb < 8 * kNumSMs ? zb : 8 * kNumSMs), 256, 0, st>>>((double2*)S, n2, state);
-            VEL_LAUNCH_CHECK("bal_zero_kernel");
             const int cam_items = nc * L.cam_chunks, cam_grid = cam_items < 3 * kNumSMs ? cam_items : 3 * kNumSMs;   // 3 CTAs of 168 registers x 128 threads per SM
             bal_camera_kernel<<<cam_grid, CAM_T, 0, st>>>(K, x, z, cams, Lf, y, nt, nc, L.cam_chunks, Wp, (long long)L.ldw, camp, state);
             VEL_LAUNCH_CHECK("bal_camera_kernel");
-            bal_camera_reduce_kernel<<<nc, 64, 0, st>>>(camp, nc, L.cam_chunks, S, rhs, state);
+            bal_camera_reduce_kernel<<<nc, 256, 0, st>>>(camp, nc, L.cam_chunks, S, rhs, state);
             VEL_LAUNCH_CHECK("bal_camera_reduce_kernel");
             int rc = vel_dense_syrk_rows_gated(Wp, (int64_t)L.ldw, n6, n3, S, n6, wb + L.off_flags, L.flags_bytes, 0, -1, &state->gate, stream);
             if (rc != VEL_OK) return rc;
@@ -515,7 +519,7 @@ VEL_API int vel_ba_iterate(const double* K, const double* z, int32_t nt, int32_t
         }
         bal_update_kernel<<<L.ublocks, PT_THREADS, 0, st>>>(Lf, y, tpart, rhs, nt, nc, x, ss_part, state);
         VEL_LAUNCH_CHECK("bal_update_kernel");
-        bal_finalize_kernel<<<1, 32, 0, st>>>(cost_part, L.pblocks, ss_part, L.ublocks, (long long)n3 + n6, tol, hist, state, iters_run);
+        bal_finalize_kernel<<<1, 32, 0, st>>>(cost_part, L.rblocks, ss_part, L.ublocks, (long long)n3 + n6, tol, hist, state, iters_run);
         VEL_LAUNCH_CHECK("bal_finalize_kernel");
     }
     return VEL_OK;

@@ -606,6 +606,10 @@ def run_ours(args):
                          "unit": "GB/s", "frac": k2_gbs / peaks["hbm_gbs"], "traffic": traffic, "peak_kind": peak_kind,
                          "bytes_per_launch": C2_PAIRS * K2_BYTES_PER_PAIR_FB, "ms_per_launch": k2_ms, "pairs_per_launch": C2_PAIRS,
                          "valid_fraction": c2_valid,
+                         "step_composition": "one C3 step by ncu launch list (profiles/r2f_launches.csv): dsyrk_lower_sub_kernel x10 45 %, "
+                                             "chol_dag_kernel x10 25 %, lk_seq_w15h_kernel 22 %, bal_camera_kernel x10 2.4 %; their legs below: "
+                                             "k8_schur_syrk (tensor/FP64), k8_cholesky (latency), in_sequence (K2 as it runs in the step); this object "
+                                             "keeps the kernel north_star names (K2, HBM byte model) in its C2 batch form",
                          "note": "measured on one launch over %d consecutive pairs of the same sequence (BASELINE configs[1] batch form); K2 is "
                                  "instruction-issue bound (ncu), its DRAM traffic is ~4x below the byte model because every pyramid is read from "
                                  "HBM once and served from L2/L1 for its other roles; inside the C3 step the same kernel runs one pair per launch "

@@ -163,3 +163,27 @@ def test_more_panels_than_ctas_takes_the_shared_ownership_forms(monkeypatch, blo
     assert info.item() == 0
     assert (bw - xw).abs().max().item() <= 1e-10 * xw.abs().max().item()
     assert (torch.tril(Aw) - Lw).abs().max().item() <= 1e-11 * Lw.abs().max().item()
+
+
+def test_blocked_form_reports_a_matrix_that_is_not_positive_definite():
+    """The blocked factorisation (n = 3,264: 51 panels > 48) keeps the contract of vel_spd_solve: info = 1 when a pivot is not
+    positive (here deep inside the fourth group of panels), 0 for the repaired matrix, whose solution then matches torch."""
+    from velocity_b200.device import ptr, stream_ptr
+
+    L = _lib()
+    n = 3264
+    g = torch.Generator(device="cuda").manual_seed(3)
+    E = torch.randn((n, 256), dtype=torch.float64, device="cuda", generator=g) / 16.0
+    A = (torch.eye(n, dtype=torch.float64, device="cuda") * 2.0 + E @ E.T).contiguous()
+    b = torch.randn((n,), dtype=torch.float64, device="cuda", generator=g)
+    info = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    bad = A.clone()
+    bad[3100, 3100] = -5.0
+    bw = b.clone()
+    L.check(L.lib().vel_spd_solve(ptr(bad), n, n, ptr(bw), ptr(info), stream_ptr()), "spd_solve")
+    assert info.item() == 1
+    Aw, bw = A.clone(), b.clone()
+    L.check(L.lib().vel_spd_solve(ptr(Aw), n, n, ptr(bw), ptr(info), stream_ptr()), "spd_solve")
+    assert info.item() == 0
+    xw = torch.cholesky_solve(b[:, None], torch.linalg.cholesky(A))[:, 0]
+    assert (bw - xw).abs().max().item() <= 1e-11 * xw.abs().max().item()

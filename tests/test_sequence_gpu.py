@@ -170,12 +170,13 @@ def test_c3_full_size_speed_within_one_percent():
 
 
 def test_in_kernel_frame_loop_equals_per_pair_launches(monkeypatch):
-    """vel_klt_sequence has three forms: the 15x15 sequence kernel (frame loop inside, ONE template per frame serving the
-    backward pass of pair j-1 and the forward pass of pair j), the batch kernel with the frame loop inside (VEL_LK_SEQ=twice)
-    and one K2 launch per pair (any window; VEL_LK_SEQ=pairs).  Same tracks, same masks, same errors, bit for bit."""
+    """vel_klt_sequence has four forms: the 15x15 sequence kernel (frame loop inside, ONE template per frame serving the
+    backward pass of pair j-1 and the forward pass of pair j), the same kernel with the search neighbourhood staged in shared memory
+    by TMA (VEL_LK_SEQ=tma, the A/B variant), the batch kernel with the frame loop inside (VEL_LK_SEQ=twice) and one K2 launch per
+    pair (any window; VEL_LK_SEQ=pairs).  Same tracks, same masks, same errors, bit for bit."""
     K, frames, p0, p3, times = scene_with_dying_tracks()
     a, _ = run_gpu(K, frames, p0, p3, times)
-    for mode in ("pairs", "twice"):      # one K2 launch per pair / frame loop inside the batch kernel (template built per pass)
+    for mode in ("pairs", "twice", "tma"):   # one K2 launch per pair / frame loop in the batch kernel (template per pass) / TMA boxes
         monkeypatch.setenv("VEL_LK_SEQ", mode)
         b, _ = run_gpu(K, frames, p0, p3, times)
         assert torch.equal(a.alive, b.alive), mode

@@ -19,6 +19,8 @@
 //   lk_track_cols_kernel   16..63 px wide windows (51x51 lk_fine, cv2's default 21x21): CTA per point, template in smem
 //   lk_track_kernel        every other window up to 127x127: group of 32 / 128 threads per point, int64 sums
 // J is gathered from global memory through L1/L2 (the whole pyramid of a 1080p frame is 2.7 MB, i.e. L2 resident).
+#include <cuda.h>
+
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
@@ -1073,6 +1075,40 @@ VEL_API int vel_lk_track(const uint8_t* prev_frames, int64_t prev_frame_stride, 
 // Internal entry of vel_klt_sequence (sequence.cu): the whole frame run in ONE launch of lk_track_w15h_kernel<true> when the
 // configuration is the one that kernel serves (15x15 window, every row pitch a multiple of 4 bytes).  Returns 1 when launched,
 // 0 when the caller has to take the per-pair path, < 0 on error.
+namespace {
+typedef CUresult (*SeqEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// one 3-D byte map (x, row, frame) per pyramid level, box 32 x 32 x 1
+bool seq_make_maps(SeqTma* tm, const uint8_t* frames, int64_t frame_stride, int pitch, const uint8_t* pyr, int64_t pyr_stride,
+                   const vel_pyr_layout* L, int nframes)
+{
+    static SeqEncodeTiledFn enc = nullptr;
+    if (!enc) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+            return false;
+        enc = (SeqEncodeTiledFn)p;
+    }
+    for (int l = 0; l <= L->max_level; ++l) {
+        const uint8_t* base = l == 0 ? frames : pyr + L->offset[l];
+        const long long fs = l == 0 ? frame_stride : pyr_stride;
+        const int pt = l == 0 ? pitch : L->pitch[l];
+        if ((((size_t)base) & 15) != 0 || (fs & 15) != 0 || (pt & 15) != 0 || L->width[l] < TMA_BOX || L->height[l] < TMA_BOX) return false;
+        cuuint64_t dims[3] = {(cuuint64_t)L->width[l], (cuuint64_t)L->height[l], (cuuint64_t)nframes};
+        cuuint64_t strides[2] = {(cuuint64_t)pt, (cuuint64_t)fs};
+        cuuint32_t box[3] = {TMA_BOXW, TMA_BOX, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        if (enc(&tm->map[l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+}  // namespace
+
 int vel_lk_sequence_w15h(const uint8_t* frames, int64_t frame_stride, int32_t pitch, const uint8_t* pyr, int64_t pyr_stride,
                          const vel_pyr_layout* layout, int32_t nframes, int32_t npts, const vel_lk_params* params, float* tracks,
                          uint8_t* alive, float* err, vel_stream_t stream)
@@ -1114,7 +1150,14 @@ int vel_lk_sequence_w15h(const uint8_t* frames, int64_t frame_stride, int32_t pi
         return 1;
     }
     dim3 grid((npts + 2 * WS_WARPS - 1) / (2 * WS_WARPS), 1);
-    lk_seq_w15h_kernel<<<grid, 32 * WS_WARPS, 0, (cudaStream_t)stream>>>(A);
+    SeqTma tm;
+    memset(&tm, 0, sizeof(tm));
+    // VEL_LK_SEQ=tma: the search neighbourhoods staged by TMA (the A/B of that design; results identical, see profiles/README.md)
+    if (seq && strcmp(seq, "tma") == 0 && layout->max_level <= 2 && seq_make_maps(&tm, frames, frame_stride, pitch, pyr, pyr_stride, layout, nframes)) {
+        lk_seq_w15h_kernel<true><<<grid, 32 * WS_WARPS, 0, (cudaStream_t)stream>>>(A, tm);
+    } else {
+        lk_seq_w15h_kernel<false><<<grid, 32 * WS_WARPS, 0, (cudaStream_t)stream>>>(A, tm);
+    }
     VEL_LAUNCH_CHECK("lk_seq_w15h_kernel");
     return 1;
 }

@@ -14,9 +14,60 @@
 
 // Newton iterations of one pyramid level against image J (+ the final patch error when want_err); same arithmetic, same order
 // as the loop in lk_track_w15h_kernel
+// ---- TMA-staged search neighbourhood (VEL_LK_SEQ=tma; the A/B of north_star's "TMA-staged patches") -------------------------------
+// Per level and role the half-warp's lane 0 requests ONE 48 x 32-byte box of the search image around the start position
+// (cp.async.bulk.tensor, 3-D map x / row / frame per pyramid level) BEFORE the template is built, so the box lands while the
+// template's ~400 instructions run; the Newton iterations then gather their 16 x 16 footprint from shared memory as long as it
+// stays inside the box (start -8 .. +5 px at least) and fall back to the global gather otherwise (or when the footprint's
+// 32 x 32 neighbourhood would leave the frame: the TMA unit zero-fills, LK needs REFLECT_101).
+// MEASURED (tools/micro/tma_u8_box.cu): a tiled-mode box must START on a 16-byte boundary of global memory -- with one-byte
+// elements the innermost coordinate has to be a multiple of 16, or the request faults ("illegal instruction").  Hence the box
+// is 48 bytes wide and starts at the search origin rounded down to 16.
+struct SeqTma {
+    CUtensorMap map[3];
+};
+constexpr int TMA_BOX = 32;                        // rows of the box, and the neighbourhood (32 x 32) that must lie inside the frame
+constexpr int TMA_BOXW = 48;                       // bytes per box row (16-byte aligned start + 32 + slack)
+
+__device__ __forceinline__ void seq_mbar_init(unsigned bar, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void seq_mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void seq_mbar_wait(unsigned bar, unsigned parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "SEQ_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra SEQ_DONE_%=;\n\t"
+        "bra SEQ_WAIT_%=;\n\t"
+        "SEQ_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void seq_tma_load_3d(unsigned dst, const CUtensorMap* map, int c0, int c1, int c2, unsigned bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+
+// the lane's five J rows from the staged box (same bytes, same word/funnel-shift form as wh_gather)
+__device__ __forceinline__ void tile_gather(const uint8_t* tile, int dx, int dy, int rq, int cg, unsigned (&w0)[5], unsigned (&w1)[5])
+{
+    const unsigned off = (unsigned)(dy + 4 * rq) * TMA_BOXW + (unsigned)(dx + 4 * cg);
+    const unsigned mis = off & 3u, sh = mis * 8u;
+    const uint8_t* r = tile + (off - mis);
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        const unsigned l = *reinterpret_cast<const unsigned*>(r), h = *reinterpret_cast<const unsigned*>(r + 4);
+        w0[k] = __funnelshift_r(l, h, sh);
+        w1[k] = __funnelshift_rc(l, h, sh + 8u);
+        if (k < 3 || (k == 3 && rq != 3)) r += TMA_BOXW;         // as wh_gather: tile row 16 is never needed
+    }
+}
+
 __device__ __forceinline__ void w15_search(const Img& J, const int4 (&rP)[12], float A11, float A12, float A22, float D, int level, int max_count,
                                            float eps2, bool want_err, int rq, int cg, unsigned hmask, int lane, float& next_x, float& next_y,
-                                           int& status, float& err)
+                                           int& status, float& err, const uint8_t* tile = nullptr, int box_x = 0, int box_y = 0)
 {
     const float half = 7.0f;
     float nx = fsub(next_x, half), ny = fsub(next_y, half);
@@ -37,7 +88,11 @@ __device__ __forceinline__ void w15_search(const Img& J, const int4 (&rP)[12], f
         const int W0 = (int)__byte_perm((unsigned)w.w00, (unsigned)w.w01, 0x5410);
         const int W1 = (int)__byte_perm((unsigned)w.w10, (unsigned)w.w11, 0x5410);
         unsigned w0[5], w1[5];
-        wh_gather(J, inx, iny, rq, cg, w0, w1);
+        // staged box: rows iny .. iny+16, bytes inx .. inx+19 of the footprint (incl. the second word of the last column group)
+        if (tile && inx >= box_x && iny >= box_y && inx + 20 <= box_x + TMA_BOXW && iny + 17 <= box_y + TMA_BOX)
+            tile_gather(tile, inx - box_x, iny - box_y, rq, cg, w0, w1);
+        else
+            wh_gather(J, inx, iny, rq, cg, w0, w1);
         int df[16];
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr) {
@@ -89,9 +144,12 @@ __device__ __forceinline__ void w15_search(const Img& J, const int4 (&rP)[12], f
 
 constexpr int WS_WARPS = 2;                        // 4 points per CTA: 1024 CTAs for 4096 tracks, 6.9 per SM
 
+template <bool TMA>
 __global__ void __launch_bounds__(32 * WS_WARPS, 10)
-lk_seq_w15h_kernel(const LkArgs A)
+lk_seq_w15h_kernel(const LkArgs A, const __grid_constant__ SeqTma T)
 {
+    __shared__ __align__(128) uint8_t s_tile[TMA ? WS_WARPS : 1][2][2][TMA ? TMA_BOXW * TMA_BOX : 16];
+    __shared__ __align__(8) unsigned long long s_bar[WS_WARPS][2][2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int4 rP[12];
     const int slot = lane >> 4, hl = lane & 15;
@@ -104,6 +162,17 @@ lk_seq_w15h_kernel(const LkArgs A)
     const int npairs = A.seq_pairs;
     const bool use_fb = A.fbt >= 0.f;
 
+    unsigned tph[2] = {0u, 0u};                        // TMA: phase of the role's barrier that the NEXT request completes
+    bool tpend[2] = {false, false};                    //      a request is in flight (or landed) and has not been waited for
+    if (TMA) {
+        if (hl == 0) {
+            seq_mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][0]), 1);
+            seq_mbar_init((unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
+        __syncwarp();
+    }
     bool live = false;                                 // alive[j-1] verdict (alive[0] is given)
     float px = 0.f, py = 0.f;                          // the point in frame j
     float qx0 = 0.f, qy0 = 0.f;                        // the point in frame j-1 (start of pair j-1)
@@ -141,6 +210,33 @@ lk_seq_w15h_kernel(const LkArgs A)
             if (ipx < -W15 || ipx >= I.w || ipy < -W15 || ipy >= I.h) {
                 if (level == 0) { bst = 0; fst = 0; ferr = 0.f; }
                 continue;
+            }
+            // TMA: request the search boxes of both roles now; they land while the template is built
+            bool thave[2] = {false, false};
+            int tbx[2] = {0, 0}, tby[2] = {0, 0};
+            if (TMA && level < 3) {
+#pragma unroll
+                for (int role = 0; role < 2; ++role) {
+                    if (!(role ? f_act : b_act)) continue;
+                    const float sx0 = role ? fnx : bnx, sy0 = role ? fny : bny;
+                    const int ox = __float2int_rd(fsub(sx0, half)) - 8, oy = __float2int_rd(fsub(sy0, half)) - 8;
+                    if (ox < 0 || oy < 0 || ox + TMA_BOX > I.w || oy + TMA_BOX > I.h) continue;
+                    const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][role]);
+                    if (tpend[role]) { seq_mbar_wait(bar, tph[role] ^ 1u); tpend[role] = false; }   // an earlier box nobody consumed
+                    __syncwarp(hmask);                      // every lane of the half is done reading the buffer's previous tenant
+                    // (lanes 0 and 16 reach the request together with different boxes: the compiler serialises the uniform-datapath
+                    // UTMALDG with an ELECT loop, nothing to do here)
+                    if (hl == 0) {
+                        seq_mbar_expect_tx(bar, TMA_BOXW * TMA_BOX);
+                        const unsigned dst = (unsigned)__cvta_generic_to_shared(&s_tile[warp][slot][role][0]);
+                        const int fz = role ? j + 1 : j - 1;
+                        if (level == 0) seq_tma_load_3d(dst, &T.map[0], ox & ~15, oy, fz, bar);
+                        else if (level == 1) seq_tma_load_3d(dst, &T.map[1], ox & ~15, oy, fz, bar);
+                        else seq_tma_load_3d(dst, &T.map[2], ox & ~15, oy, fz, bar);
+                    }
+                    thave[role] = true; tbx[role] = ox & ~15; tby[role] = oy;
+                    tpend[role] = true; tph[role] ^= 1u;
+                }
             }
             Weights w = bilin_weights(fsub(prev_x, (float)ipx), fsub(prev_y, (float)ipy));
             int W0 = (int)__byte_perm((unsigned)w.w00, (unsigned)w.w01, 0x5410);
@@ -311,7 +407,16 @@ lk_seq_w15h_kernel(const LkArgs A)
                 else { J.p = A.prev_pyr + jf * A.prev_pyr_stride + A.lv.off[level]; J.pitch = A.lv.pitch[level]; }
                 float sx_ = role ? fnx : bnx, sy_ = role ? fny : bny, e_ = 0.f;
                 int st_ = role ? fst : bst;
-                w15_search(J, rP, A11, A12, A22, D, level, A.max_count, A.eps2, role == 1 && level == 0, rq, cg, hmask, lane, sx_, sy_, st_, e_);
+                const uint8_t* tile = nullptr;
+                if (TMA && thave[role]) {
+                    if (tpend[role]) {
+                        seq_mbar_wait((unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][role]), tph[role] ^ 1u);
+                        tpend[role] = false;
+                    }
+                    tile = &s_tile[warp][slot][role][0];
+                }
+                w15_search(J, rP, A11, A12, A22, D, level, A.max_count, A.eps2, role == 1 && level == 0, rq, cg, hmask, lane, sx_, sy_, st_, e_,
+                           tile, tbx[role], tby[role]);
                 if (role) { fnx = sx_; fny = sy_; fst = st_; ferr = e_; }
                 else { bnx = sx_; bny = sy_; bst = st_; }
             }
@@ -347,6 +452,11 @@ lk_seq_w15h_kernel(const LkArgs A)
             fst_prev = fst;
         }
         if (!__any_sync(0xffffffffu, live)) {               // both tracks of this warp are gone: park the remaining rows and leave
+            if (TMA) {                                      // no box may still be on its way into this CTA's shared memory
+#pragma unroll
+                for (int role = 0; role < 2; ++role)
+                    if (tpend[role]) { seq_mbar_wait((unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][role]), tph[role] ^ 1u); tpend[role] = false; }
+            }
             if (hl == 0 && in_set) {
                 for (int k2 = j + 1; k2 <= npairs; ++k2) {
                     A.alive[(long long)k2 * A.npts + pt] = 0;
@@ -357,5 +467,10 @@ lk_seq_w15h_kernel(const LkArgs A)
             }
             return;
         }
+    }
+    if (TMA) {
+#pragma unroll
+        for (int role = 0; role < 2; ++role)
+            if (tpend[role]) seq_mbar_wait((unsigned)__cvta_generic_to_shared(&s_bar[warp][slot][role]), tph[role] ^ 1u);
     }
 }

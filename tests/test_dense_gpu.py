@@ -72,6 +72,16 @@ def test_spd_solve(n):
     assert info.item() == 1
 
 
+@pytest.mark.parametrize("grid", ["32", "8"])
+def test_spd_solve_on_fewer_ctas_than_the_device_has(monkeypatch, grid):
+    """The task-graph factorisation on a grid a smaller device would give it (VEL_CHOL_GRID): 32 CTAs for 29 panels -- the panel
+    CTAs keep their two critical tiles resident AND share in the other tiles (an ownership test that only held when they did not
+    share was found here) -- and 8 CTAs, where a CTA owns several diagonal tiles and nothing stays resident."""
+    monkeypatch.setenv("VEL_CHOL_GRID", grid)
+    test_spd_solve(1794)
+    test_spd_solve(300)
+
+
 @pytest.mark.parametrize("name", ["ba_small", "ba_medium", "ba_256x10", "ba_512x20"])
 def test_bundle_adjustment_with_native_solver(monkeypatch, name):
     """fcnNLS_batch with this library's own SYRK + Cholesky (VEL_BA_SOLVER=native) against the reference's golden results,

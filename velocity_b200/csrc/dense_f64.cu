@@ -1064,7 +1064,9 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                 }
             } else {
                 const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
-                const bool res_t = resident && i == me;         // the resident sub-diagonal tile (then k == me - 1)
+                // the resident sub-diagonal tile; on a grid with fewer than 2 nb CTAs the panel CTAs share in the other tiles and may own
+                // more of row `me` (found with VEL_CHOL_GRID=32: every tile of that row was then read from bufT)
+                const bool res_t = resident && i == me && k == me - 1;
                 if (!res_t) chol_load_tile(S, lds, r0, wi, k0, w, bufA, vec);
                 __syncthreads();
                 double acc[2][2][2] = {};
@@ -1396,6 +1398,7 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     const int want = nblk * (nblk + 1) / 2 + nblk;
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
+    if (const char* ge = getenv("VEL_CHOL_GRID")) { const int v = atoi(ge); if (v >= 1 && v < grid) grid = v; }      // tests: the forms a device with fewer SMs takes
     // Many panels (the multi-GPU global BA factors n = 3,594 ... 14,394 on its owner): the 64-tile task graph then spends its time
     // in latency-bound 64x64x64 update tasks (11 TFLOP/s at n = 14,394).  BLOCKED form: groups of CH_GROUP panels are factored by the task graph
     // restricted to their columns (phase 1), and everything to the right of a group is updated by the SYRK kernel (33 TFLOP/s at

@@ -112,6 +112,20 @@ int vel_corner_subpix_u8(const uint8_t* img, int32_t width, int32_t height, int3
 int vel_estimate_affine2d_ransac(const float* from_xy, const float* to_xy, int32_t npts, double threshold, double confidence,
                                  int32_t max_iters, int32_t refine, uint8_t* inliers, double* T, int32_t* info, vel_stream_t stream);
 
+/* The tracker's call shape of the same fit (utils/KLT.py:116-117 and :127): `T, inl = cv2.estimateAffine2D(p0[v], p[v]); v[v] = inl`
+ * with v the status mask of the LK stage before it, as ONE launch on device data: the rows of from_xy / to_xy [npts][2] with
+ * mask[i] != 0 are compacted in order, the `to` points first mapped in float32 as to * to_scale + (to_off_x, to_off_y) -- the
+ * `p /= scale` of :114 (to_scale 4) or the map-back of the translated ROI, :89 (the offset) --, the fit runs on the compacted
+ * rows exactly as vel_estimate_affine2d_ransac, and mask_out[i] = mask[i] & inlier (mask_out may be mask itself).
+ * to_mapped (may be NULL) receives the mapped `to` of ALL rows.  info (int32 [4], DEVICE) = {found, inliers, iterations, rows
+ * kept}; fewer than 3 rows kept = not found (cv2 returns None).  work: vel_estimate_affine2d_ransac_masked_workspace(npts)
+ * bytes, 8-byte aligned.  npts 1..8192. */
+size_t vel_estimate_affine2d_ransac_masked_workspace(int32_t npts);
+int vel_estimate_affine2d_ransac_masked(const float* from_xy, const float* to_xy, const uint8_t* mask, int32_t npts, float to_scale,
+                                        float to_off_x, float to_off_y, double threshold, double confidence, int32_t max_iters,
+                                        int32_t refine, void* work, size_t work_bytes, uint8_t* mask_out, float* to_mapped, double* T,
+                                        int32_t* info, vel_stream_t stream);
+
 /* K2.  cv2calcOpticalFlowPyrLK (utils/KLT.py:37-51) for a batch of frame pairs: pyramidal
  * Lucas-Kanade forward pass and, when params->fb_threshold >= 0, the backward pass from the
  * forward result fused in the same kernel with

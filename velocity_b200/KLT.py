@@ -22,7 +22,7 @@ from .common import addcol1
 from .device import image_view, ptr, stream_ptr
 from .images import boundingRect
 from .lk import lk_params
-from .ransac import estimateAffine2D
+from .ransac import estimateAffine2D, estimateAffine2D_masked_device
 
 TERM_CRITERIA_COUNT, TERM_CRITERIA_EPS = 1, 2
 
@@ -104,15 +104,11 @@ def _remap_affine_device(im, T32, x0, x1, y0, y1):
     return out
 
 
-def KLTregional(im0, im, p0, T, lk_param, fbt=1.0, translateFlag=False):
-    """ROI tracker: warp the current frame into the previous frame's coordinates (integer shift or
-    affine remap), LK forward+backward on the ROI, map the result back through T.  The device work is one call
-    (vel_klt_regional); the ROI rectangle (utils/KLT.py:60) and the map-back (:88-93) are the reference's numpy."""
-    T = np.asarray(T).astype(np.float32)
-    p0 = np.asarray(p0)
-    d0, dn = _as_cuda_image(im0), _as_cuda_image(im)
+def _klt_regional_enqueue(d0, dn, p0, T, lk_param, fbt, translateFlag):
+    """The device part of KLTregional, nothing synchronised: returns (pa_d [N,2] f32 in ROI coordinates, st_d [N] u8, xy0, (dx, dy))."""
     x0, x1, y0, y1 = boundingRect(p0, tuple(dn.shape), border=(50, 50))
     xy0 = np.float32([x0, y0])
+    dx = dy = 0
     if translateFlag:
         dx, dy = int(T[2, 0]), int(T[2, 1])
         if y0 + dy < 0 or x0 + dx < 0 or y1 + dy > dn.shape[0] or x1 + dx > dn.shape[1]:
@@ -120,7 +116,18 @@ def KLTregional(im0, im, p0, T, lk_param, fbt=1.0, translateFlag=False):
     # p0 - xy0 in numpy's arithmetic (float64 when the caller's points are float64), then float32 as cv2 takes them
     p0_roi = np.ascontiguousarray(np.asarray(p0 - xy0, np.float32).reshape(-1, 2))
     pts = torch.from_numpy(p0_roi).to(d0.device)
-    pa_d, st_d, err_d = _regional_device(d0, dn, pts, x0, x1, y0, y1, T, translateFlag, fbt, lk_param, pts_in_roi=True)
+    pa_d, st_d, _ = _regional_device(d0, dn, pts, x0, x1, y0, y1, T, translateFlag, fbt, lk_param, pts_in_roi=True)
+    return pa_d, st_d, xy0, (dx, dy)
+
+
+def KLTregional(im0, im, p0, T, lk_param, fbt=1.0, translateFlag=False):
+    """ROI tracker: warp the current frame into the previous frame's coordinates (integer shift or
+    affine remap), LK forward+backward on the ROI, map the result back through T.  The device work is one call
+    (vel_klt_regional); the ROI rectangle (utils/KLT.py:60) and the map-back (:88-93) are the reference's numpy."""
+    T = np.asarray(T).astype(np.float32)
+    p0 = np.asarray(p0)
+    d0, dn = _as_cuda_image(im0), _as_cuda_image(im)
+    pa_d, st_d, xy0, (dx, dy) = _klt_regional_enqueue(d0, dn, p0, T, lk_param, fbt, translateFlag)
     packed = torch.cat([pa_d, st_d.to(torch.float32).unsqueeze(1)], 1).cpu().numpy()      # one D2H copy
     pa, v = np.ascontiguousarray(packed[:, 0:2]), packed[:, 2] != 0
     if translateFlag:
@@ -142,30 +149,47 @@ def _decimate4_device(im):
 def KLTmain(im, im0, im0_small, p0):
     """Three-stage tracker: quarter-scale LK -> RANSAC -> translated-ROI LK (FB 1.0) -> RANSAC ->
     affine-ROI fine LK (FB 0.3).  Returns (p[v] float32, v bool [N], im_small) like the reference;
-    im_small is returned in the form it was produced (CUDA tensor), pass it back as im0_small."""
+    im_small is returned in the form it was produced (CUDA tensor), pass it back as im0_small.
+    Each LK stage hands its points and status mask to the robust fit ON THE DEVICE (vel_estimate_affine2d_ransac_masked: the
+    `estimateAffine2D(p0[v], p[v]); v[v] = inliers` of utils/KLT.py:116-117 in one launch), so a frame costs three read-backs -- what
+    the host needs to size the next stage (the mean translation, the 2x3 affine) and the result -- instead of five, and one upload of
+    p0 for both fits."""
     p0 = np.asarray(p0)
     d_im, d_im0 = _as_cuda_image(im), _as_cuda_image(im0)
     scale = 1 / 4
     im_small = _decimate4_device(d_im)
     if im0_small is None:
         im0_small = _decimate4_device(d_im0)
-    p, v, _ = cv2calcOpticalFlowPyrLK(im0_small, im_small, p0 * scale, None, **LK_COARSE)
-    p /= scale
-    T23, inliers = estimateAffine2D(p0[v], p[v])
-    v[v] = inliers.ravel().astype(bool)
-
+    p0_dev = torch.from_numpy(np.ascontiguousarray(np.asarray(p0, np.float32).reshape(-1, 2))).to(d_im.device)
+    n = p0_dev.shape[0]
+    if n == 0:                                              # the reference fails the same way (estimateAffine2D returns None, utils/KLT.py:117)
+        raise AttributeError("KLTmain: no points to track")
+    # stage 1 (utils/KLT.py:113-121): p0 * scale is exact in float32 (a power of two), so the device copy serves
+    out, status, _ = lk_device(im0_small, im_small, p0_dev * scale, **LK_COARSE)
+    mask1, p1_dev, tail1 = estimateAffine2D_masked_device(p0_dev, out, status, to_scale=1 / scale)
+    host = torch.cat([p1_dev.reshape(-1), mask1.to(torch.float32), tail1.view(torch.float32)]).cpu().numpy()       # read-back 1
+    p, v = host[:2 * n].reshape(n, 2), host[2 * n:3 * n] != 0
+    if not host[3 * n + 12:3 * n + 16].view(np.int32)[0]:
+        raise AttributeError("KLTmain: estimateAffine2D found no model after the coarse stage (the reference fails on None here, utils/KLT.py:117)")
     translation = p[v] - p0[v]
     T = np.eye(3, 2)
     T[2] = translation.mean(0)
-    p, v = KLTregional(d_im0, d_im, p0, T, LK_COARSE, fbt=1, translateFlag=True)
 
-    if v.sum() > 10:
-        T23, inliers = estimateAffine2D(p0[v], p[v])
+    # stage 2 (:122-130): translated ROI, forward-backward 1 px; the fit only has to deliver T23
+    pa_d, st_d, xy0, (dx, dy) = _klt_regional_enqueue(d_im0, d_im, p0, T.astype(np.float32), LK_COARSE, 1, True)
+    off = (xy0 + [dx, dy]).astype(np.float32)
+    _, _, tail2 = estimateAffine2D_masked_device(p0_dev, pa_d, st_d, to_off=(off[0], off[1]))
+    t2 = tail2.cpu().numpy()                                                                                      # read-back 2
+    found, _, _, kept = (int(x) for x in t2[6:8].view(np.int32))
+    if kept > 10:
+        if not found:
+            raise AttributeError("KLTmain: estimateAffine2D found no model after the translated stage (the reference fails on None.T here, utils/KLT.py:132)")
+        T23 = t2[:6].reshape(2, 3).copy()
     else:
         print("KLT coarse-affine failure, running SURF matches full scale.")
         T23, inliers = estimateAffine2D_SURF(d_im0, d_im, p0, scale=1)
 
-    p, v = KLTregional(d_im0, d_im, p0, T23.T, LK_FINE, fbt=0.3)
+    p, v = KLTregional(d_im0, d_im, p0, T23.T, LK_FINE, fbt=0.3)                                                    # read-back 3
     return p[v], v, im_small
 
 

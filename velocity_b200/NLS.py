@@ -49,12 +49,27 @@ def nls_batch_device(K, p, pw, first, count, x0, dof):
 
 
 def _single(K, p, pw, x, dof):
-    n = int(np.asarray(pw).shape[0])
-    first = torch.zeros(1, dtype=torch.int32, device="cuda")
-    count = torch.full((1,), n, dtype=torch.int32, device="cuda")
-    xd, it = nls_batch_device(_dev64(K), _dev64(p).reshape(-1, 2), _dev64(pw).reshape(-1, 3), first, count,
-                              _dev64(np.asarray(x, np.float64)[:dof]).reshape(1, dof), dof)
-    return xd.cpu().numpy()[0], int(it.item())
+    """One pose problem from host arrays: ONE upload (K | x0 | p | pw | first,count packed in a float64 buffer) and ONE read-back
+    (x | iters) -- the per-frame call of the drop-in loop (vidExample.py:139)."""
+    require_cuda()
+    pw = np.asarray(pw, np.float64).reshape(-1, 3)
+    p = np.asarray(p, np.float64).reshape(-1, 2)
+    n = pw.shape[0]
+    host = np.empty(9 + dof + 5 * n + 1, np.float64)
+    host[0:9] = np.asarray(K, np.float64).ravel()
+    host[9:9 + dof] = np.asarray(x, np.float64).ravel()[:dof]
+    o_p, o_pw, o_int = 9 + dof, 9 + dof + 2 * n, 9 + dof + 5 * n
+    host[o_p:o_pw] = p.ravel()
+    host[o_pw:o_int] = pw.ravel()
+    host[o_int:o_int + 1].view(np.int32)[:] = (0, n)                      # first, count
+    dev = torch.from_numpy(host).cuda()
+    out = torch.empty((dof + 1,), dtype=torch.float64, device=dev.device)   # x | iters (int32 in the last 8 bytes)
+    base, obase = dev.data_ptr(), out.data_ptr()
+    fn = _lib.lib().vel_nls_t if dof == 3 else _lib.lib().vel_nls_rt
+    _lib.check(fn(C.c_void_p(base), C.c_void_p(base + 8 * o_p), C.c_void_p(base + 8 * o_pw), C.c_void_p(base + 8 * o_int), C.c_void_p(base + 8 * o_int + 4),
+                  1, C.c_void_p(base + 72), C.c_void_p(obase), C.c_void_p(obase + 8 * dof), stream_ptr()), "vel_nls_t" if dof == 3 else "vel_nls_rt")
+    res = out.cpu().numpy()
+    return res[:dof].copy(), int(res[dof:dof + 1].view(np.int32)[0])
 
 
 def fcnNLS_t(K, p, pw, x):

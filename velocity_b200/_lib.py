@@ -49,6 +49,9 @@ SIGNATURES = {
     "vel_good_features_harris_u8": (C.c_int, [_P, _I32, _I32, _I32, _I32, C.c_double, _I32, C.c_double, _P, C.c_size_t, _P, _P, _P, _P]),
     "vel_corner_subpix_u8": (C.c_int, [_P, _I32, _I32, _I32, _P, _I32, _I32, _I32, _I32, C.c_double, _P]),
     "vel_estimate_affine2d_ransac": (C.c_int, [_P, _P, _I32, C.c_double, C.c_double, _I32, _I32, _P, _P, _P, _P]),
+    "vel_estimate_affine2d_ransac_masked_workspace": (C.c_size_t, [_I32]),
+    "vel_estimate_affine2d_ransac_masked": (C.c_int, [_P, _P, _P, _I32, C.c_float, C.c_float, C.c_float, C.c_double, C.c_double, _I32, _I32, _P,
+                                                     C.c_size_t, _P, _P, _P, _P, _P]),
     "vel_lk_track": (C.c_int, [_P, _I64, _I32, _P, _I64, _P, _I64, _I32, _P, _I64, C.POINTER(PyrLayout), _I32, _P, _I64, _I32,
                                C.POINTER(LkParams), _P, _P, _P, _P, _P]),
     "vel_klt_regional_workspace": (C.c_size_t, [_I32, _I32, _I32, _I32, _I32, _I32]),

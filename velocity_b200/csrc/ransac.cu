@@ -104,18 +104,17 @@ __device__ void block_sum(double (&v)[K], RsShared& S, int tid)
     }
 }
 
-__global__ void __launch_bounds__(RS_THREADS)
-ransac_affine2d_kernel(const float2* __restrict__ from, const float2* __restrict__ to, int n, double thresh, double conf, int max_iters,
-                       int refine, uint8_t* __restrict__ inliers, double* __restrict__ T, int* __restrict__ info)
+// the whole CTA; from / to may have been written earlier in the same kernel (the masked form compacts into scratch): plain loads
+__device__ void ransac_affine2d_body(RsShared& S, const float2* from, const float2* to, int n, double thresh, double conf, int max_iters,
+                                     int refine, uint8_t* inliers, double* T, int* info)
 {
-    __shared__ RsShared S;
     const int tid = threadIdx.x;
     float2 f[RS_MAX_PER_THREAD], t[RS_MAX_PER_THREAD];
 #pragma unroll
     for (int q = 0; q < RS_MAX_PER_THREAD; ++q) {
         const int i = tid + q * RS_THREADS;
-        f[q] = i < n ? __ldg(from + i) : make_float2(0.f, 0.f);
-        t[q] = i < n ? __ldg(to + i) : make_float2(0.f, 0.f);
+        f[q] = i < n ? from[i] : make_float2(0.f, 0.f);
+        t[q] = i < n ? to[i] : make_float2(0.f, 0.f);
     }
     for (int i = tid; i < n; i += RS_THREADS) inliers[i] = 0;
     const float thr2 = (float)(thresh * thresh);
@@ -248,6 +247,67 @@ ransac_affine2d_kernel(const float2* __restrict__ from, const float2* __restrict
     }
 }
 
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_affine2d_kernel(const float2* __restrict__ from, const float2* __restrict__ to, int n, double thresh, double conf, int max_iters,
+                       int refine, uint8_t* __restrict__ inliers, double* __restrict__ T, int* __restrict__ info)
+{
+    __shared__ RsShared S;
+    ransac_affine2d_body(S, from, to, n, thresh, conf, max_iters, refine, inliers, T, info);
+}
+
+// The tracker's own call shape (utils/KLT.py:116-117, :127): `T, inl = estimateAffine2D(p0[v], p[v]); v[v] = inl` with v the
+// status mask of the LK stage before it -- compaction, fit and scatter in one launch, so the LK output never leaves the device:
+// from_c / to_c = the rows where mask != 0 in order (to first mapped as to * to_scale + to_off in float32: the `p /= scale` of
+// :114 and the map-back of the translated ROI, :89), the fit on those, mask_out[i] = mask[i] & inlier.  info[3] = rows kept.
+__global__ void __launch_bounds__(RS_THREADS)
+ransac_affine2d_masked_kernel(const float2* __restrict__ from, const float2* __restrict__ to, const uint8_t* mask, int n_full,
+                              float to_scale, float to_off_x, float to_off_y, double thresh, double conf, int max_iters, int refine,
+                              float2* cf, float2* ct, int* cidx, uint8_t* cinl, uint8_t* mask_out, float2* __restrict__ to_out,
+                              double* __restrict__ T, int* __restrict__ info)
+{
+    __shared__ RsShared S;
+    __shared__ int wsum[RS_THREADS / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n_full + RS_THREADS - 1) / RS_THREADS, lo = min(tid * per, n_full), hi = min(lo + per, n_full);
+    int cnt = 0;
+    for (int i = lo; i < hi; ++i) cnt += mask[i] != 0;
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int w = 0; w < RS_THREADS / 32; ++w) { const int v = wsum[w]; wsum[w] = run; run += v; }
+        s_total = run;
+    }
+    __syncthreads();
+    int pos = wsum[warp] + incl - cnt;
+    for (int i = lo; i < hi; ++i) {
+        const float2 tv = to[i];
+        const float2 tm = make_float2(__fadd_rn(__fmul_rn(tv.x, to_scale), to_off_x), __fadd_rn(__fmul_rn(tv.y, to_scale), to_off_y));
+        if (to_out) to_out[i] = tm;                       // the mapped points of ALL rows (the caller's `p`)
+        if (mask[i] != 0) { cf[pos] = from[i]; ct[pos] = tm; cidx[pos] = i; ++pos; }
+    }
+    const int n = s_total;
+    __syncthreads();
+    if (tid == 0) info[3] = n;
+    if (n < 3) {                                          // cv2 returns (None, None): nothing to scatter, the caller decides
+        for (int i = tid; i < n_full; i += RS_THREADS) mask_out[i] = 0;
+        if (tid == 0) { info[0] = 0; info[1] = 0; info[2] = 0; }
+        return;
+    }
+    ransac_affine2d_body(S, cf, ct, n, thresh, conf, max_iters, refine, cinl, T, info);
+    __syncthreads();
+    for (int i = tid; i < n_full; i += RS_THREADS) mask_out[i] = 0;
+    __syncthreads();
+    for (int i = tid; i < n; i += RS_THREADS) mask_out[cidx[i]] = cinl[i];
+}
+
 }  // namespace
 
 VEL_API int vel_estimate_affine2d_ransac(const float* from_xy, const float* to_xy, int32_t npts, double threshold, double confidence,
@@ -262,5 +322,33 @@ VEL_API int vel_estimate_affine2d_ransac(const float* from_xy, const float* to_x
                                                                       reinterpret_cast<const float2*>(to_xy), npts, threshold, confidence,
                                                                       max_iters, refine, inliers, T, info);
     VEL_LAUNCH_CHECK("ransac_affine2d_kernel");
+    return VEL_OK;
+}
+
+VEL_API size_t vel_estimate_affine2d_ransac_masked_workspace(int32_t npts)
+{
+    if (npts <= 0) return 0;
+    return (size_t)npts * (2 * sizeof(float2) + sizeof(int) + 1) + 64;
+}
+
+VEL_API int vel_estimate_affine2d_ransac_masked(const float* from_xy, const float* to_xy, const uint8_t* mask, int32_t npts, float to_scale,
+                                                float to_off_x, float to_off_y, double threshold, double confidence, int32_t max_iters,
+                                                int32_t refine, void* work, size_t work_bytes, uint8_t* mask_out, float* to_mapped, double* T,
+                                                int32_t* info, vel_stream_t stream)
+{
+    VEL_CHECK_ARG(from_xy && to_xy && mask && mask_out && T && info && work, "vel_estimate_affine2d_ransac_masked: NULL argument");
+    VEL_CHECK_ARG(npts >= 1 && npts <= RS_THREADS * RS_MAX_PER_THREAD, "vel_estimate_affine2d_ransac_masked: npts %d outside [1,%d]", npts,
+                  RS_THREADS * RS_MAX_PER_THREAD);
+    VEL_CHECK_ARG(threshold > 0. && max_iters >= 1, "vel_estimate_affine2d_ransac_masked: bad threshold / iteration budget");
+    VEL_CHECK_ARG(work_bytes >= vel_estimate_affine2d_ransac_masked_workspace(npts) && ((size_t)work & 7) == 0,
+                  "vel_estimate_affine2d_ransac_masked: workspace too small or misaligned");
+    float2* cf = (float2*)work;
+    float2* ct = cf + npts;
+    int* cidx = (int*)(ct + npts);
+    uint8_t* cinl = (uint8_t*)(cidx + npts);
+    ransac_affine2d_masked_kernel<<<1, RS_THREADS, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float2*>(from_xy), reinterpret_cast<const float2*>(to_xy), mask, npts, to_scale, to_off_x, to_off_y, threshold,
+        confidence, max_iters, refine, cf, ct, cidx, cinl, mask_out, reinterpret_cast<float2*>(to_mapped), T, info);
+    VEL_LAUNCH_CHECK("ransac_affine2d_masked_kernel");
     return VEL_OK;
 }

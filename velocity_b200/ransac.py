@@ -44,3 +44,27 @@ def estimateAffine2D(from_, to, inliers=None, method=RANSAC, ransacReprojThresho
     if not info[0]:
         return None, mask
     return T, mask
+
+
+def estimateAffine2D_masked_device(from_dev, to_dev, mask_dev, to_scale=1.0, to_off=(0.0, 0.0), ransacReprojThreshold=3.0, maxIters=2000,
+                                   confidence=0.99, refineIters=10):
+    """`T, inl = estimateAffine2D(from_[v], to[v]); v[v] = inl` (utils/KLT.py:116-117) on DEVICE data in one launch, nothing synchronised:
+    from_dev / to_dev float32 [n,2] CUDA, mask_dev uint8 [n] CUDA (the LK status).  `to` is first mapped as to * to_scale + to_off in
+    float32.  Returns CUDA tensors (mask_out uint8 [n], to_mapped float32 [n,2], T float64 [6], info int32 [4] = found, inliers,
+    iterations, rows kept)."""
+    require_cuda()
+    n = from_dev.shape[0]
+    dev = from_dev.device
+    L = _lib.lib()
+    nbytes = int(L.vel_estimate_affine2d_ransac_masked_workspace(n))
+    work = torch.empty((nbytes + 7) // 8, dtype=torch.float64, device=dev)
+    mask_out = torch.empty((n,), dtype=torch.uint8, device=dev)
+    to_mapped = torch.empty((n, 2), dtype=torch.float32, device=dev)
+    tail = torch.empty(8, dtype=torch.float64, device=dev)                 # T (6 doubles) | info (4 int32)
+    _lib.check(L.vel_estimate_affine2d_ransac_masked(C.c_void_p(from_dev.data_ptr()), C.c_void_p(to_dev.data_ptr()), C.c_void_p(mask_dev.data_ptr()), n,
+                                                     float(to_scale), float(to_off[0]), float(to_off[1]), float(ransacReprojThreshold),
+                                                     float(confidence), int(maxIters), 1 if refineIters else 0, C.c_void_p(work.data_ptr()),
+                                                     work.numel() * 8, C.c_void_p(mask_out.data_ptr()), C.c_void_p(to_mapped.data_ptr()),
+                                                     C.c_void_p(tail.data_ptr()), C.c_void_p(tail.data_ptr() + 48), stream_ptr()),
+               "vel_estimate_affine2d_ransac_masked")
+    return mask_out, to_mapped, tail

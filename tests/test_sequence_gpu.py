@@ -136,6 +136,15 @@ def test_sequence_results_to_host():
     S1 = out["S"].clone()
     seq.run(torch.from_numpy(frames).pin_memory(), p0, p3, times, out=out)
     assert torch.equal(S1.nan_to_num(), out["S"].nan_to_num())
+    # sync=False: the small tables are there when the call returns, the P export lands behind the NEXT sequence's launches
+    P1 = out["P"].clone()
+    out2 = {k: torch.full_like(v, -7.0).pin_memory() for k, v in out.items()}
+    pinned = torch.from_numpy(frames).pin_memory()
+    for _ in range(2):
+        seq.run(pinned, p0, p3, times, out=out2, sync=False)
+        assert torch.equal(S1.nan_to_num(), out2["S"].nan_to_num())
+    seq.wait_results()
+    assert torch.equal(P1.nan_to_num(), out2["P"].nan_to_num())
 
 
 def test_c3_full_size_speed_within_one_percent():

@@ -70,6 +70,7 @@ class SfmSequence:
         self.x0 = torch.empty((3 * npts + 6 * (nframes - 1),), dtype=torch.float64, device=dev)
         self.P = None
         self.copy_stream = torch.cuda.Stream(device=dev)
+        self._back_stream, self._back = None, None              # read-back of run(..., sync=False)
         self.x0_host = (C.c_double * 3)(0.0, 0.0, 1.0)       # estimateWorldCameraPose's default t (utils/NLS.py:9)
         self.ba = None
         self.launches = 0
@@ -273,15 +274,45 @@ class SfmSequence:
         return self.idx[:nsel], x[:3 * nsel].view(nsel, 3), torch.cat([torch.zeros((1, 3), dtype=torch.float64, device=self.dev),
                                                                        x[3 * nsel:3 * nsel + 3 * (n - 1)].view(n - 1, 3)])
 
-    def run(self, frames, p0, p3, frame_times, t0=(0.0, 0.0, 0.0), out=None, bundle=True):
+    def run(self, frames, p0, p3, frame_times, t0=(0.0, 0.0, 0.0), out=None, bundle=True, sync=True):
         """One whole sequence.  With `out` (dict of pinned host tensors 'S', 'S_ba', 'B', and optionally 'P') the results
-        are copied back and the call synchronises; otherwise everything stays on the device."""
+        are copied back and the call synchronises; otherwise everything stays on the device.
+        sync=False (a caller that runs sequence after sequence): the small tables are on the host when the call returns, the
+        large 'P' export (24.6 MB at C3) travels on a side stream while the NEXT sequence is already being tracked;
+        wait_results() waits for it (copies into the same host buffer stay in order)."""
         self.h2d_bytes = self.d2h_bytes = 0
         self._mark("start")
         self.track(frames, p0)
         self._mark("track")
+        compute = torch.cuda.current_stream(self.dev)
+        if out is not None and not sync:
+            # the small tables ride behind the bundle adjustment on the compute stream and are complete when solve() has read
+            # the history back
+            hist = self.solve(p3, frame_times, t0=t0, bundle=bundle)
+            for name, src in (("S", self.S), ("S_ba", self.S_ba), ("B", self.B)):
+                if name in out:
+                    out[name].copy_(src, non_blocking=True)
+                    self.d2h_bytes += src.numel() * 4
+            if "P" in out:
+                if self._back is not None:
+                    compute.wait_event(self._back[1])          # the export buffer is reused: the previous copy must have left it
+                exp = self.export_P()                          # nothing of the next sequence writes into it before its own export
+                ready = torch.cuda.Event()
+                ready.record(compute)
+                if self._back_stream is None:
+                    self._back_stream = torch.cuda.Stream(device=self.dev)
+                self._back_stream.wait_event(ready)
+                with torch.cuda.stream(self._back_stream):
+                    out["P"].copy_(exp, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._back_stream)
+                self._back = (exp, done)
+                self.d2h_bytes += self.P.numel() * 4
+            compute.synchronize()
+            return hist
         hist = self.solve(p3, frame_times, t0=t0, bundle=bundle)
         if out is not None:
+            self.wait_results()
             for name, src in (("S", self.S), ("S_ba", self.S_ba), ("B", self.B)):
                 if name in out:
                     out[name].copy_(src, non_blocking=True)
@@ -289,8 +320,14 @@ class SfmSequence:
             if "P" in out:
                 out["P"].copy_(self.export_P(), non_blocking=True)
                 self.d2h_bytes += self.P.numel() * 4
-            torch.cuda.current_stream(self.dev).synchronize()
+            compute.synchronize()
         return hist
+
+    def wait_results(self):
+        """Block until the read-back a run(..., sync=False) left in flight has landed in its host buffers."""
+        if self._back is not None:
+            self._back[1].synchronize()
+            self._back = None
 
 
 def plane_points_from_pose(K, R, t, p):

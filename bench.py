@@ -491,8 +491,17 @@ def run_ours(args):
     # ---- end-to-end timing through the public host-buffer API ----------------------------------------------------------------
     out = dict(S=torch.empty((NFRAMES, 9)).pin_memory(), S_ba=torch.empty((NFRAMES, 9)).pin_memory(),
                B=torch.empty((NFRAMES, 14)).pin_memory(), P=torch.empty((5, NPTS, NFRAMES)).pin_memory())
-    for _ in range(2):
-        seq.run(frames_host, p0_host, p3_host, times_host, out=out)
+    # warm-up in exactly the form of the timed loop (prefetch with the small inputs, L2 flush, asynchronous read-back): the first use
+    # of each of them loads a module / allocates a staging tensor (tools/e2e_steps.py: 16 ms before the first timed step otherwise)
+    nwarm = max(args.warmup, 3)
+    seq.prefetch(frames_host, p0_host, p3_host, times_host)
+    for s in range(nwarm):
+        l2_flush.zero_()
+        if s + 1 < nwarm:
+            seq.prefetch(frames_host, p0_host, p3_host, times_host)
+        seq.run(frames_host, p0_host, p3_host, times_host, out=out, sync=False)
+    seq.wait_results()
+    torch.cuda.synchronize()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     h2d_small = p0_host.numel() * 4 + p3_host.numel() * 8 + times_host.numel() * 4

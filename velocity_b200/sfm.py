@@ -200,8 +200,10 @@ class SfmSequence:
         self._buf_free[b] = done
 
     # ---- stages 2-4 -----------------------------------------------------------------------------------------------------
-    def solve(self, p3, frame_times, t0=(0.0, 0.0, 0.0), subset=None, bundle=True, verbose=False):
-        """Per-frame translation + speed table, then triangulation over all frames and the bundle adjustment."""
+    def solve(self, p3, frame_times, t0=(0.0, 0.0, 0.0), subset=None, bundle=True, verbose=False, before_sync=None):
+        """Per-frame translation + speed table, then triangulation over all frames and the bundle adjustment.
+        before_sync: called once everything is enqueued and before the history is read back (the one synchronisation at the end):
+        work enqueued there -- run()'s read-backs -- needs no synchronisation of its own."""
         L = _lib.lib()
         n, npts = self.n, self.npts
         p3, frame_times = self._staged("p3", p3), self._staged("frame_times", frame_times)
@@ -218,6 +220,8 @@ class SfmSequence:
         self.launches += 3
         self._mark("pose")
         if not bundle or n < 2:
+            if before_sync is not None:
+                before_sync()
             return None
         _lib.check(L.vel_seq_select(ptr(self.alive[n - 1]), sub, npts, ptr(self.idx), ptr(self.count), stream_ptr()), "vel_seq_select")
         nsel = int(self.count.item())                      # the one data-dependent size: full-length tracks (utils/NLS.py:190)
@@ -249,6 +253,8 @@ class SfmSequence:
                    "vel_seq_ba_cameras")
         _lib.check(L.vel_seq_stats(ptr(self.B_ba), ptr(self.alive), n, npts, ptr(self.S_ba), stream_ptr()), "vel_seq_stats")
         self._mark("bundle")
+        if before_sync is not None:
+            before_sync()
         hist = self.ba.history(self.ba_iters)
         if verbose:
             for it, (f, xr) in enumerate(hist):
@@ -286,29 +292,31 @@ class SfmSequence:
         self._mark("track")
         compute = torch.cuda.current_stream(self.dev)
         if out is not None and not sync:
-            # the small tables ride behind the bundle adjustment on the compute stream and are complete when solve() has read
-            # the history back
-            hist = self.solve(p3, frame_times, t0=t0, bundle=bundle)
-            for name, src in (("S", self.S), ("S_ba", self.S_ba), ("B", self.B)):
-                if name in out:
-                    out[name].copy_(src, non_blocking=True)
-                    self.d2h_bytes += src.numel() * 4
-            if "P" in out:
-                if self._back is not None:
-                    compute.wait_event(self._back[1])          # the export buffer is reused: the previous copy must have left it
-                exp = self.export_P()                          # nothing of the next sequence writes into it before its own export
-                ready = torch.cuda.Event()
-                ready.record(compute)
-                if self._back_stream is None:
-                    self._back_stream = torch.cuda.Stream(device=self.dev)
-                self._back_stream.wait_event(ready)
-                with torch.cuda.stream(self._back_stream):
-                    out["P"].copy_(exp, non_blocking=True)
-                done = torch.cuda.Event()
-                done.record(self._back_stream)
-                self._back = (exp, done)
-                self.d2h_bytes += self.P.numel() * 4
-            compute.synchronize()
+            def read_back():
+                # behind the bundle adjustment on the compute stream: complete when solve() has read the history back
+                for name, src in (("S", self.S), ("S_ba", self.S_ba), ("B", self.B)):
+                    if name in out:
+                        out[name].copy_(src, non_blocking=True)
+                        self.d2h_bytes += src.numel() * 4
+                if "P" in out:
+                    if self._back is not None:
+                        compute.wait_event(self._back[1])      # the export buffer is reused: the previous copy must have left it
+                    exp = self.export_P()                      # nothing of the next sequence writes into it before its own export
+                    ready = torch.cuda.Event()
+                    ready.record(compute)
+                    if self._back_stream is None:
+                        self._back_stream = torch.cuda.Stream(device=self.dev)
+                    self._back_stream.wait_event(ready)
+                    with torch.cuda.stream(self._back_stream):
+                        out["P"].copy_(exp, non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(self._back_stream)
+                    self._back = (exp, done)
+                    self.d2h_bytes += self.P.numel() * 4
+
+            hist = self.solve(p3, frame_times, t0=t0, bundle=bundle, before_sync=read_back)
+            if hist is None:                                   # no bundle adjustment, hence no history read-back: synchronise here
+                compute.synchronize()
             return hist
         hist = self.solve(p3, frame_times, t0=t0, bundle=bundle)
         if out is not None:

@@ -60,8 +60,11 @@ __device__ __forceinline__ void project_rk(const double* K, double ax, double ay
     const double q0 = ax * K[0] + ay * K[3] + az * K[6];
     const double q1 = ax * K[1] + ay * K[4] + az * K[7];
     const double q2 = ax * K[2] + ay * K[5] + az * K[8];
-    u = q0 / q2;
-    v = q1 / q2;
+    // one reciprocal instead of two divisions (an FP64 division is ~25 instructions on this part and the pose fit is bound by them);
+    // u, v move by at most an ulp, far below the forward-difference noise of the Jacobian they feed
+    const double r = 1.0 / q2;
+    u = q0 * r;
+    v = q1 * r;
 }
 
 // (H + I) d = g, 3x3 symmetric, Gaussian elimination with partial pivoting (same as nls.cu)
@@ -88,7 +91,8 @@ __device__ void solve3_damped(const double* Hu /*6: 00 01 02 11 12 22*/, const d
 }
 
 // One CTA per frame f = 1 + blockIdx.x.  Points that are alive at frame f (and in `subset`, if given) enter the fit.
-__global__ void __launch_bounds__(POSE_THREADS)
+// 3 CTAs per SM: the 299 frames of a C3 sequence then run as ONE wave on 148 SMs (at 2 per SM, 296 slots, three CTAs ran alone afterwards)
+__global__ void __launch_bounds__(POSE_THREADS, 3)
 seq_pose_t_kernel(const double* __restrict__ Kg, const float2* __restrict__ tracks, const uint8_t* __restrict__ alive,
                   const uint8_t* __restrict__ subset, const double* __restrict__ p3, int npts, double x0a, double x0b, double x0c,
                   const float* B0, float* B, float* __restrict__ S, float2* __restrict__ proj,
@@ -108,7 +112,7 @@ seq_pose_t_kernel(const double* __restrict__ Kg, const float2* __restrict__ trac
     if (tid == 0) { sx[0] = x0a; sx[1] = x0b; sx[2] = x0c; s_done = 0; }
     __syncthreads();
 
-    const double dx = 1e-6;
+    const double dx = 1e-6, inv_dx = 1e6;
     int it = 0;
     for (; it < POSE_MAX_ITER; ++it) {
         double acc[NACC];
@@ -120,9 +124,10 @@ seq_pose_t_kernel(const double* __restrict__ Kg, const float2* __restrict__ trac
             const double bx = p3[3 * i] + sx[0], by = p3[3 * i + 1] + sx[1], bz = p3[3 * i + 2] + sx[2];
             double u0, v0, u, v, ju[3], jv[3];
             project_rk(sK, bx, by, bz, u0, v0);
-            project_rk(sK, bx + dx, by, bz, u, v); ju[0] = (u - u0) / dx; jv[0] = (v - v0) / dx;
-            project_rk(sK, bx, by + dx, bz, u, v); ju[1] = (u - u0) / dx; jv[1] = (v - v0) / dx;
-            project_rk(sK, bx, by, bz + dx, u, v); ju[2] = (u - u0) / dx; jv[2] = (v - v0) / dx;
+            // (u - u0) * 1e6 for the reference's (u - u0) / 1e-6 (utils/NLS.py:113-118): 1e6 is exact, the quotient differs in the last bit
+            project_rk(sK, bx + dx, by, bz, u, v); ju[0] = (u - u0) * inv_dx; jv[0] = (v - v0) * inv_dx;
+            project_rk(sK, bx, by + dx, bz, u, v); ju[1] = (u - u0) * inv_dx; jv[1] = (v - v0) * inv_dx;
+            project_rk(sK, bx, by, bz + dx, u, v); ju[2] = (u - u0) * inv_dx; jv[2] = (v - v0) * inv_dx;
             const double ru = (double)pz.x - u0, rv = (double)pz.y - v0;
             int k = 0;
 #pragma unroll

@@ -14,14 +14,20 @@ namespace {
 constexpr int TRI_THREADS = 128;
 
 // ---- N-view least squares -------------------------------------------------------------------------
+// S1_i = sum_f (I - u u^T), S2_i = sum_f (I - u u^T) A_f, C0_i = S1_i^-1 S2_i (utils/MSV.py:146-175).  grid = (point blocks, frame
+// chunks): a thread sums its point's rays over one chunk of frames (one thread per point over all 300 frames left the machine to
+// 128 warps on a chain of dependent loads: 190 us at C3); the chunk sums are added in chunk order by the solve kernel --
+// deterministic, no atomics.
+constexpr int TRI_NACC = 9;
 __global__ void __launch_bounds__(TRI_THREADS)
-tri_nv_kernel(const double* __restrict__ A, const double* __restrict__ U, int nf, int nv, double* __restrict__ C0)
+tri_nv_partial_kernel(const double* __restrict__ A, const double* __restrict__ U, int nf, int nv, int f_per_chunk, double* __restrict__ part)
 {
     const int i = blockIdx.x * TRI_THREADS + threadIdx.x;
     if (i >= nv) return;
+    const int f0 = blockIdx.y * f_per_chunk, f1 = min(nf, f0 + f_per_chunk);
     const long long plane = (long long)nf * nv;
     double m00 = 0, m01 = 0, m02 = 0, m11 = 0, m12 = 0, m22 = 0, b0 = 0, b1 = 0, b2 = 0;
-    for (int f = 0; f < nf; ++f) {
+    for (int f = f0; f < f1; ++f) {
         const double ux = U[(long long)f * nv + i], uy = U[plane + (long long)f * nv + i], uz = U[2 * plane + (long long)f * nv + i];
         const double ax = A[3 * f], ay = A[3 * f + 1], az = A[3 * f + 2];
         const double v00 = 1 - ux * ux, v01 = -ux * uy, v02 = -ux * uz, v11 = 1 - uy * uy, v12 = -uy * uz, v22 = 1 - uz * uz;
@@ -30,6 +36,25 @@ tri_nv_kernel(const double* __restrict__ A, const double* __restrict__ U, int nf
         b1 += ax * v01 + ay * v11 + az * v12;
         b2 += ax * v02 + ay * v12 + az * v22;
     }
+    double* o = part + (long long)blockIdx.y * TRI_NACC * nv + i;        // [chunk][quantity][point]: coalesced
+    o[0] = m00; o[(long long)nv] = m01; o[2ll * nv] = m02; o[3ll * nv] = m11; o[4ll * nv] = m12; o[5ll * nv] = m22;
+    o[6ll * nv] = b0; o[7ll * nv] = b1; o[8ll * nv] = b2;
+}
+
+__global__ void __launch_bounds__(TRI_THREADS)
+tri_nv_solve_kernel(const double* __restrict__ part, int nv, int nchunks, double* __restrict__ C0)
+{
+    const int i = blockIdx.x * TRI_THREADS + threadIdx.x;
+    if (i >= nv) return;
+    double q[TRI_NACC];
+#pragma unroll
+    for (int k = 0; k < TRI_NACC; ++k) q[k] = 0.0;
+    for (int c = 0; c < nchunks; ++c) {
+        const double* o = part + (long long)c * TRI_NACC * nv + i;
+#pragma unroll
+        for (int k = 0; k < TRI_NACC; ++k) q[k] += o[(long long)k * nv];
+    }
+    const double m00 = q[0], m01 = q[1], m02 = q[2], m11 = q[3], m12 = q[4], m22 = q[5], b0 = q[6], b1 = q[7], b2 = q[8];
     // C0 = inv(S1) @ S2 for the symmetric 3x3 S1 (adjugate form)
     const double c00 = m11 * m22 - m12 * m12, c01 = m02 * m12 - m01 * m22, c02 = m01 * m12 - m02 * m11;
     const double c11 = m00 * m22 - m02 * m02, c12 = m01 * m02 - m00 * m12, c22 = m00 * m11 - m01 * m01;
@@ -217,8 +242,28 @@ VEL_API int vel_triangulate_nv(const double* A, const double* U, int32_t nf, int
     VEL_CHECK_ARG(A && U && C0, "vel_triangulate_nv: NULL argument");
     VEL_CHECK_ARG(nf >= 1 && nv >= 0, "vel_triangulate_nv: bad sizes nf=%d nv=%d", nf, nv);
     if (nv == 0) return VEL_OK;
-    tri_nv_kernel<<<(nv + TRI_THREADS - 1) / TRI_THREADS, TRI_THREADS, 0, (cudaStream_t)stream>>>(A, U, nf, nv, C0);
-    VEL_LAUNCH_CHECK("tri_nv_kernel");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int pblocks = (nv + TRI_THREADS - 1) / TRI_THREADS;
+    // enough frame chunks to fill the machine (~4 CTAs per SM), at least 8 frames each
+    int nchunks = (4 * kNumSMs + pblocks - 1) / pblocks;
+    if (nchunks > (nf + 7) / 8) nchunks = (nf + 7) / 8;
+    if (nchunks < 1) nchunks = 1;
+    const int f_per_chunk = (nf + nchunks - 1) / nchunks;
+    nchunks = (nf + f_per_chunk - 1) / f_per_chunk;
+    double* part = nullptr;
+    vel_keep_async_pool_cached();
+    VEL_CUDA(cudaMallocAsync((void**)&part, sizeof(double) * TRI_NACC * (size_t)nv * nchunks, st));
+    tri_nv_partial_kernel<<<dim3(pblocks, nchunks), TRI_THREADS, 0, st>>>(A, U, nf, nv, f_per_chunk, part);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        tri_nv_solve_kernel<<<pblocks, TRI_THREADS, 0, st>>>(part, nv, nchunks, C0);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(part, st);
+    if (e != cudaSuccess) {
+        vel_set_error("vel_triangulate_nv: %s", cudaGetErrorString(e));
+        return VEL_ERR_CUDA;
+    }
     return VEL_OK;
 }
 

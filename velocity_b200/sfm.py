@@ -237,7 +237,7 @@ class SfmSequence:
         x0 = self.x0[:3 * nsel + 6 * (n - 1)]
         _lib.check(L.vel_seq_pack_ba(ptr(self.tracks), ptr(self.idx), n, npts, nsel, ptr(C0), ptr(self.B), ptr(z), ptr(x0), stream_ptr()),
                    "vel_seq_pack_ba")
-        self.launches += 6
+        self.launches += 7                                 # select, rays, triangulation (partial + solve), pack ...
         self._mark("triangulate")
         if self.ba is None or (self.ba.nt, self.ba.nc) != (nsel, n - 1):
             self.ba = BundleAdjuster(self.K, z, x0, nsel, n - 1)

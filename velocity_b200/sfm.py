@@ -192,9 +192,17 @@ class SfmSequence:
         self.frames = self._bufs[b]
         self.batch.frames = self.frames
         self.h2d_bytes += n * self.h * self.w
-        for lo, hi, ev in events:
-            compute.wait_event(ev)
+        # chunk by chunk behind the upload -- but chunks that have already landed (a prefetched sequence usually has, all of it) are
+        # taken together: one pyramid launch and one sequence kernel over their whole frame range instead of one pair per chunk
+        i = 0
+        while i < len(events):
+            j = i
+            while j + 1 < len(events) and events[j + 1][2].query():
+                j += 1
+            lo, hi = events[i][0], events[j][1]
+            compute.wait_event(events[j][2])
             self._track_range(max(lo - 1, 0), hi - 1, lo)
+            i = j + 1
         done = torch.cuda.Event()
         done.record(compute)
         self._buf_free[b] = done

@@ -845,9 +845,10 @@ __device__ __forceinline__ void dag_signal(int* flag)
 // inverted by 64 threads in parallel (one 8-step chain), then three levels h = 8, 16, 32 fill the off-diagonal blocks with
 //     Inv[R][C] = -Inv[R][R] * (L[R][C] * Inv[C][C])        R = lower half, C = upper half of a 2h x 2h diagonal block
 // as two small tensor-core (DMMA) products per level.  tmp = [64][CH_LDT] scratch.  Rows/columns >= w behave as identity.
-__device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int w, double* sI, double* tmp)
+// stage 1 of tri_inverse_block: sI = 0, then the inverses of the eight 8x8 diagonal blocks (block-diagonal sI)
+__device__ void tri_inverse_diag(double (*sD)[CH_LD], const double* rdiag, int w, double* sI)
 {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
+    const int tid = threadIdx.x;
     for (int e = tid; e < CH_NB * CH_LDT; e += CH_THREADS) sI[e] = 0.0;
     __syncthreads();
     if (tid < 64) {
@@ -867,6 +868,12 @@ __device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int 
         for (int u = 0; u < 8; ++u) sI[(m0 + u) * CH_LDT + m0 + c] = x[u];
     }
     __syncthreads();
+}
+
+// stages 2-4: the off-diagonal blocks by recursive doubling (see tri_inverse_block)
+__device__ void tri_inverse_levels(double (*sD)[CH_LD], int w, double* sI, double* tmp)
+{
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t4 = lane & 3;
     for (int h = 8; h < CH_NB; h *= 2) {
         const int tpd = h >> 3, tpp = tpd * tpd, npair = CH_NB / (2 * h), ntile = npair * tpp;
         // tmp[R][C] = L[R][C] * Inv[C][C]
@@ -901,6 +908,44 @@ __device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int 
     }
 }
 
+__device__ void tri_inverse_block(double (*sD)[CH_LD], const double* rdiag, int w, double* sI, double* tmp)
+{
+    tri_inverse_diag(sD, rdiag, w, sI);
+    tri_inverse_levels(sD, w, sI, tmp);
+}
+
+// X = A L^-T for the 64 x 64 tile A (bufTile, row-major [64][CH_LDT]) and the lower-triangular 64 x 64 L (bufL, same layout; entries
+// above the diagonal are never read), by blocked forward substitution over the eight column blocks of X
+//     X_s = (A_s - sum_{m<s} X_m L_sm^T) L_ss^-T,         dinv[s] = L_ss^-1 (8 x 8, row-major)
+// -> X (row-major [64][CH_LDT]).  Rows are independent: warp w < 8 owns rows 8w .. 8w+7 and walks its eight steps alone (two DMMAs
+// per earlier block + two for the diagonal block: a chain of 72 DMMAs, ~1.3 us) -- the critical T task of the next panel runs this
+// on L_kk as soon as the panel is factored, instead of waiting for the full inverse of L_kk (tri_inverse_levels, ~2.8 us).
+__device__ void trsm_tile_64(const double* bufTile, const double* bufL, const double* dinv, double* X)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t4 = lane & 3;
+    if (warp >= 8) return;
+    const int r = warp * 8 + g;
+    for (int s2 = 0; s2 < 8; ++s2) {
+        double d0 = 0.0, d1 = 0.0;
+        for (int m = 0; m < s2; ++m)
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+                dmma884(d0, d1, X[r * CH_LDT + 8 * m + 4 * kk + t4], bufL[(8 * s2 + g) * CH_LDT + 8 * m + 4 * kk + t4]);
+        // tmp = A_s - acc, parked in X's own block s (only this warp touches rows 8w .. 8w+7)
+        X[r * CH_LDT + 8 * s2 + 2 * t4] = bufTile[r * CH_LDT + 8 * s2 + 2 * t4] - d0;
+        X[r * CH_LDT + 8 * s2 + 2 * t4 + 1] = bufTile[r * CH_LDT + 8 * s2 + 2 * t4 + 1] - d1;
+        __syncwarp();
+        double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+            dmma884(e0, e1, X[r * CH_LDT + 8 * s2 + 4 * kk + t4], dinv[s2 * 64 + g * 8 + 4 * kk + t4]);
+        __syncwarp();
+        X[r * CH_LDT + 8 * s2 + 2 * t4] = e0;
+        X[r * CH_LDT + 8 * s2 + 2 * t4 + 1] = e1;
+        __syncwarp();
+    }
+}
+
 // C(64x64 accumulators of the calling thread layout) = A(64 x kw) * B(64 x kw)^T from two staged tiles
 __device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bufB, double (&acc)[2][2][2])
 {
@@ -923,7 +968,7 @@ __device__ __forceinline__ void tile_mma_64(const double* bufA, const double* bu
 
 __global__ void __launch_bounds__(CH_THREADS, 1)
 chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ info, int* dflag, int* tflag, int* xflag, double* Linv_g,
-                const int* __restrict__ gate, int k_lo, int k_hi, int phase)
+                const int* __restrict__ gate, int k_lo, int k_hi, int phase, int* eflag, double* Dinv_g)
 {
     // phase 0: the whole factorisation (k_lo = 0, k_hi = nb) and the substitutions; phase 1: the panels [k_lo, k_hi) only -- tiles of
     // those COLUMNS, all rows -- for the blocked form of large systems (the trailing matrix is updated by the SYRK kernel between
@@ -941,6 +986,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
     __shared__ unsigned short own_i[CH_MAXOWN], own_j[CH_MAXOWN];
     __shared__ double rdiag[CH_NB];
     __shared__ double sx[2][CH_NB];
+    __shared__ double sDinv[8 * 64];                               // the eight L_ss^-1 of the panel above this CTA's resident tile
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
     const int nb = (n + CH_NB - 1) / CH_NB;
@@ -1026,22 +1072,59 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                 DG_T(0);
                 chol_block(sD, w, &s_ok, rdiag, &cs);
                 DG_T(1);
-                tri_inverse_block(sD, rdiag, w, sI, bufA);
+                tri_inverse_diag(sD, rdiag, w, sI);
+                // The next panel's critical tile (k+1, k) does not wait for the whole inverse: its owner solves against L_kk itself
+                // (trsm_tile_64), which needs the factor and the inverses of its eight diagonal blocks -- published now, early.
+                const bool early = resident && k + 1 < nb && w == CH_NB;
+                if (early) {
+                    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                        const int r = e >> 6, c2 = e & 63;
+                        if (c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+                    }
+                    {
+                        const int blk = tid >> 6, rr = (tid >> 3) & 7, cc = tid & 7;          // 512 threads = 8 blocks x 8 x 8
+                        Dinv_g[(long long)k * 512 + tid] = sI[(8 * blk + rr) * CH_LDT + 8 * blk + cc];
+                    }
+                    dag_signal(eflag + k);
+                }
+                tri_inverse_levels(sD, w, sI, bufA);
                 DG_T(2);
-                // the inverse is what the waiting T tasks need: publish it first, the factor itself (read by nobody before the
-                // kernel's final barrier) afterwards
+                // the inverse is what the other waiting T tasks need: publish it first, the factor itself (read by nobody else before
+                // the kernel's final barrier) afterwards
                 for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
                     const int r = e >> 6, c2 = e & 63;
                     Linv_g[(long long)k * CH_NB * CH_NB + e] = (r < w && c2 < w) ? sI[r * CH_LDT + c2] : 0.0;
                 }
                 if (tid == 0 && !s_ok) info[0] = 1;
                 dag_signal(dflag + k);
-                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
-                    const int r = e >> 6, c2 = e & 63;
-                    if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+                if (!early) {
+                    for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                        const int r = e >> 6, c2 = e & 63;
+                        if (r < w && c2 <= r) S[(long long)(k0 + r) * lds + k0 + c2] = sD[r][c2];
+                    }
                 }
                 DG_T(3);
                 have_linv = 1;
+                continue;
+            }
+            if (resident && i == me && k == me - 1) {
+                // the critical tile (me, me-1), resident in bufT: solved against L_kk as soon as panel k is factored (early flag)
+                DG_T(7);
+                dag_wait(eflag + k);
+                DG_T(4);
+                chol_load_tile(S, lds, k0, CH_NB, k0, CH_NB, bufA, vec);       // L_kk (what lies above its diagonal is never read)
+                sDinv[tid] = __ldcg(Dinv_g + (long long)k * 512 + tid);
+                __syncthreads();
+                trsm_tile_64(bufT, bufA, sDinv, bufB);                         // L_(me,k) -> bufB, where U(me, me, k) wants it
+                __syncthreads();
+                const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
+                for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
+                    const int r = e >> 6, c2 = e & 63;
+                    if (r < wi) S[(long long)(r0 + r) * lds + k0 + c2] = bufB[r * CH_LDT + c2];
+                }
+                bufB_j = i;
+                dag_signal(tflag + (long long)i * nb + k);
+                DG_T(5);
                 continue;
             }
             if (!have_linv) {
@@ -1384,9 +1467,10 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     }
     // task-graph form: flags (dflag[nb], tflag[(nb+1)*nb]) and the inverses of the diagonal tiles live in stream-ordered scratch
     vel_keep_async_pool_cached();
-    const size_t nflags = (size_t)nblk + (size_t)(nblk + 1) * nblk + (size_t)nblk;     // dflag | tflag | xflag
+    const size_t nflags = (size_t)nblk + (size_t)(nblk + 1) * nblk + (size_t)nblk + (size_t)nblk;     // dflag | tflag | xflag | eflag
     const size_t flag_bytes = align256(sizeof(int) * nflags);
-    const size_t bytes = flag_bytes + sizeof(double) * (size_t)nblk * CH_NB * CH_NB;
+    const size_t linv_bytes = sizeof(double) * (size_t)nblk * CH_NB * CH_NB;
+    const size_t bytes = flag_bytes + linv_bytes + sizeof(double) * (size_t)nblk * 512;              // + the diagonal-block inverses per panel
     char* scratch = nullptr;
     VEL_CUDA(cudaMallocAsync((void**)&scratch, bytes, st));
     cudaError_t e = cudaMemsetAsync(scratch, 0, flag_bytes, st);
@@ -1394,7 +1478,9 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     int* dflag = (int*)scratch;
     int* tflag = dflag + nblk;
     int* xflag = tflag + (size_t)(nblk + 1) * nblk;
+    int* eflag = xflag + nblk;
     double* Linv_g = (double*)(scratch + flag_bytes);
+    double* Dinv_g = (double*)(scratch + flag_bytes + linv_bytes);
     const int want = nblk * (nblk + 1) / 2 + nblk;
     int grid = max_grid;
     if (want < grid) grid = want < 1 ? 1 : want;
@@ -1409,7 +1495,7 @@ int vel_dense_spd_solve_gated(double* S, int64_t lds, int32_t n, double* b, int3
     const bool blocked = nblk > blocked_min && (lds & 1) == 0 && ((size_t)S & 15) == 0 && !(benv && benv[0] == '0' && benv[1] == 0);
     int k_lo = 0, k_hi = nblk, phase = 0;
     void* args[] = {(void*)&S, &lds_, &n_, (void*)&b, (void*)&info, (void*)&dflag, (void*)&tflag, (void*)&xflag, (void*)&Linv_g, (void*)&gate,
-                    &k_lo, &k_hi, &phase};
+                    &k_lo, &k_hi, &phase, (void*)&eflag, (void*)&Dinv_g};
     if (e == cudaSuccess && !blocked) {
         e = cudaLaunchCooperativeKernel((void*)chol_dag_kernel, dim3(grid), dim3(CH_THREADS), args, CH_DAG_SMEM, st);
     } else if (e == cudaSuccess) {

@@ -1055,6 +1055,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
         const int k0 = k * CH_NB, w = min(CH_NB, n - k0);
         int have_linv = 0;
         int bufB_j = -1;                               // bufB holds L_(bufB_j, k)
+        bool early_u = false;                          // U(me, me, k) was applied right behind the critical solve
         while (p_lo < own_n && own_j[p_lo] < k) ++p_lo;
         int p = p_lo;
         // ---------------- D(k) and T(i,k): own tiles of column k ----------------
@@ -1118,6 +1119,21 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
                 trsm_tile_64(bufT, bufA, sDinv, bufB);                         // L_(me,k) -> bufB, where U(me, me, k) wants it
                 __syncthreads();
                 const int r0 = i * CH_NB, wi = min(CH_NB, n - r0);
+                {
+                    // U(me, me, k) at once: it is what D(me) waits for -- the copy of L_(me,k) to global memory and its flag (below) are
+                    // for the other CTAs
+                    double acc[2][2][2] = {};
+                    if (!(sc > sr)) tile_mma_64(bufB, bufB, acc);
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj) {
+                            const int r = sr + ii * 8 + g, c2 = sc + jj * 8 + 2 * t4;
+                            if (r < wi && c2 < wi && c2 <= r) sD[r][c2] -= acc[ii][jj][0];
+                            if (r < wi && c2 + 1 < wi && c2 + 1 <= r) sD[r][c2 + 1] -= acc[ii][jj][1];
+                        }
+                    early_u = true;
+                }
                 for (int e = tid; e < CH_NB * CH_NB; e += CH_THREADS) {
                     const int r = e >> 6, c2 = e & 63;
                     if (r < wi) S[(long long)(r0 + r) * lds + k0 + c2] = bufB[r * CH_LDT + c2];
@@ -1177,6 +1193,7 @@ chol_dag_kernel(double* S, long long lds, int n, double* b, int* __restrict__ in
         // ---------------- U(i,j,k): own tiles of the columns j > k ----------------
         for (; p < own_n; ++p) {
             const int i = own_i[p], j = own_j[p];
+            if (early_u && i == me && j == me) continue;
             const int c0 = j * CH_NB, wj = min(CH_NB, n - c0);
             if (j != bufB_j) {
                 DG_T(7);
